@@ -1,0 +1,48 @@
+"""In-tree build of the CUDA library and the calc-witness CLI (nvcc cross-compiles sm_100a without a GPU).
+
+  python circom-witnesscalc_b200/build.py [--force] [--verbose]
+
+Outputs (git-ignored, shipped to the GPU box by gpurun):
+  circom-witnesscalc_b200/lib/libcircom_witnesscalc.so   the C-ABI library of include/graph_witness.h
+  circom-witnesscalc_b200/bin/calc-witness               CLI with the reference's argv contract
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "lib", "libcircom_witnesscalc.so")
+BIN = os.path.join(HERE, "bin", "calc-witness")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SOURCES = ["engine.cu", "graph.cpp", "plan.cpp", "inputs.cpp", "wtns.cpp", "capi.cpp"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    os.makedirs(os.path.dirname(BIN), exist_ok=True)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "graph_witness.h")]
+    if force or _newer(LIB, deps):
+        cmd = [NVCC, "-shared", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas,-Wno-misleading-indentation", "-std=c++17", "-O3", "-lineinfo", *ARCH,
+               "-Xptxas", "-v" if verbose else "-O3", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    if force or _newer(BIN, [LIB, os.path.join(CSRC, "calc_witness_main.cpp")]):
+        cmd = ["g++", "-O2", "-std=c++17", "-o", BIN, os.path.join(CSRC, "calc_witness_main.cpp"),
+               "-L" + os.path.dirname(LIB), "-lcircom_witnesscalc", "-Wl,-rpath,$ORIGIN/../lib"]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(LIB)

@@ -1,0 +1,149 @@
+// extern "C" boundary: include/graph_witness.h.  Replaces /root/reference/src/lib.rs:28-111
+// (prepare_status, gw_calc_witness).  Nothing may unwind across this boundary (the reference's
+// unwrap()/panic!s would be UB here, lib.rs:130,160,196): every entry point catches everything.
+#include "../../include/graph_witness.h"
+
+#include <string.h>
+
+#include <list>
+#include <memory>
+#include <mutex>
+
+#include "engine.hpp"
+#include "inputs.hpp"
+#include "wtns.hpp"
+
+using namespace gw;
+
+struct gw_graph {
+  std::unique_ptr<Engine> engine;
+  std::vector<std::string> input_names;
+};
+
+static void set_status(const gw_status_t* status_c, GW_ERROR_CODE code, const char* msg) {   // lib.rs:28-38
+  gw_status_t* status = const_cast<gw_status_t*>(status_c);
+  if (!status) return;
+  status->code = code;
+  status->error_msg = nullptr;
+  if (msg) {
+    size_t n = strlen(msg);
+    status->error_msg = (char*)malloc(n + 1);
+    if (status->error_msg) memcpy(status->error_msg, msg, n + 1);
+  }
+}
+
+template <typename F> static int guarded(const gw_status_t* status, F&& f) {
+  try { f(); set_status(status, OK, nullptr); return 0; }
+  catch (const std::exception& e) { set_status(status, ERROR, e.what()); return 1; }
+  catch (...) { set_status(status, ERROR, "unknown error"); return 1; }
+}
+
+static void calc_one(Engine& eng, const char* json, void** wtns_data, size_t* wtns_len) {
+  InputList in = deserialize_inputs(json, strlen(json));
+  std::vector<U256> buf = build_inputs_buffer(eng.graph, in);
+  const uint32_t W = eng.plan.n_witness;
+  size_t n = wtns_size(W);
+  uint8_t* out = (uint8_t*)malloc(n);
+  if (!out) throw Error("Failed to allocate memory for wtns_data");
+  try {
+    wtns_write_header(out, W);
+    eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, 0);
+  } catch (...) { free(out); throw; }
+  *wtns_data = out; *wtns_len = n;
+}
+
+// gw_calc_witness is stateless for the caller; parsed graphs are kept in a small cache keyed by content
+static std::mutex g_cache_mu;
+static std::list<std::pair<std::pair<uint64_t, size_t>, std::shared_ptr<Engine>>> g_cache;
+static std::shared_ptr<Engine> cached_engine(const uint8_t* data, size_t len) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < len; i++) { h ^= data[i]; h *= 1099511628211ull; }
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+    if (it->first.first == h && it->first.second == len) { g_cache.splice(g_cache.begin(), g_cache, it); return g_cache.front().second; }
+  std::shared_ptr<Engine> e(new Engine(data, len));
+  g_cache.emplace_front(std::make_pair(h, len), e);
+  if (g_cache.size() > 4) g_cache.pop_back();
+  return e;
+}
+
+extern "C" {
+
+int gw_calc_witness(const char* inputs, const void* graph_data, const size_t graph_data_len, void** wtns_data,
+                    size_t* wtns_len, const gw_status_t* status) {
+  if (!inputs) { set_status(status, ERROR, "inputs is null"); return 1; }             // lib.rs:51-54
+  if (!graph_data) { set_status(status, ERROR, "graph_data is null"); return 1; }     // lib.rs:56-59
+  if (graph_data_len == 0) { set_status(status, ERROR, "graph_data_len is 0"); return 1; }   // lib.rs:61-64
+  if (!wtns_data || !wtns_len) { set_status(status, ERROR, "wtns_data or wtns_len is null"); return 1; }
+  return guarded(status, [&]() {
+    std::shared_ptr<Engine> e = cached_engine((const uint8_t*)graph_data, graph_data_len);
+    calc_one(*e, inputs, wtns_data, wtns_len);
+  });
+}
+
+int gw_graph_load(const void* graph_data, size_t graph_data_len, gw_graph_t** graph, gw_status_t* status) {
+  if (!graph_data || graph_data_len == 0 || !graph) { set_status(status, ERROR, "graph_data is null or empty"); return 1; }
+  return guarded(status, [&]() {
+    std::unique_ptr<gw_graph> g(new gw_graph());
+    g->engine.reset(new Engine((const uint8_t*)graph_data, graph_data_len));
+    for (auto& kv : g->engine->graph.inputs) g->input_names.push_back(kv.first);
+    *graph = g.release();
+  });
+}
+
+void gw_graph_free(gw_graph_t* graph) { delete graph; }
+
+int gw_graph_info(const gw_graph_t* graph, gw_graph_info_t* info) {
+  if (!graph || !info) return 1;
+  const Plan& p = graph->engine->plan;
+  memset(info, 0, sizeof *info);
+  info->n_nodes = p.stats.graph_nodes; info->n_ops = p.stats.graph_ops;
+  info->n_inputs = p.n_inputs; info->n_witness = p.n_witness;
+  info->n_input_signals = (uint32_t)graph->input_names.size();
+  info->n_instrs = (uint32_t)p.code.size(); info->n_regs = p.n_regs; info->n_spill = p.n_spill;
+  info->n_mul = p.stats.op_count[OP_MUL] + p.stats.op_count[OP_SQR]; info->n_div = p.stats.op_count[OP_DIV];
+  info->n_spill_ld = p.stats.spill_ld; info->n_spill_st = p.stats.spill_st;
+  return 0;
+}
+
+int gw_graph_input_signal(const gw_graph_t* graph, uint32_t i, const char** name, uint32_t* offset, uint32_t* len) {
+  if (!graph || i >= graph->input_names.size()) return 1;
+  auto it = graph->engine->graph.inputs.find(graph->input_names[i]);
+  if (name) *name = graph->input_names[i].c_str();
+  if (offset) *offset = it->second.first;
+  if (len) *len = it->second.second;
+  return 0;
+}
+
+int gw_graph_calc_witness(gw_graph_t* graph, const char* inputs_json, void** wtns_data, size_t* wtns_len, gw_status_t* status) {
+  if (!graph || !inputs_json || !wtns_data || !wtns_len) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() { calc_one(*graph->engine, inputs_json, wtns_data, wtns_len); });
+}
+
+int gw_calc_witness_batch(gw_graph_t* graph, const uint8_t* inputs, size_t n_sets, uint8_t* witness, uint32_t* flags,
+                          int n_gpus, gw_status_t* status) {
+  if (!graph || (n_sets && (!inputs || !witness))) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() {
+    int ndev = cuda_device_count();
+    if (ndev == 0) throw Error("no CUDA device available: this library has no CPU fallback");
+    if (n_gpus < 1) n_gpus = 1;
+    if (n_gpus > ndev) throw Error("n_gpus exceeds the number of visible CUDA devices");
+    graph->engine->run_host(inputs, n_sets, witness, flags, n_gpus, 0);
+  });
+}
+
+int gw_calc_witness_batch_device(gw_graph_t* graph, int device, const void* d_inputs, size_t n_sets, void* d_witness,
+                                 uint32_t* d_flags, void* cuda_stream, gw_status_t* status) {
+  if (!graph || (n_sets && (!d_inputs || !d_witness))) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() { graph->engine->run_device(device, d_inputs, n_sets, d_witness, d_flags, cuda_stream); });
+}
+
+void gw_wtns_header(uint32_t n_witness, uint8_t* dst76) { wtns_write_header(dst76, n_witness); }
+
+int gw_device_count(void) { return cuda_device_count(); }
+
+double gw_microbench_imad(int device, int which) {
+  try { return imad_microbench(device, which); } catch (...) { return -1.0; }
+}
+
+}  // extern "C"

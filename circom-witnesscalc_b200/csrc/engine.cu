@@ -1,0 +1,347 @@
+// Batch witness evaluator for sm_100a: the device half of what replaces
+// /root/reference/src/graph.rs:367-391 (graph::evaluate).
+//
+// Execution model (throughput mode): one thread = one input set ("witness").  All 32 lanes of a
+// warp run the SAME instruction of the plan for 32 different witnesses, so opcode dispatch is
+// warp-uniform and there is no divergence.  Each warp streams the 16-byte instructions itself:
+// lane l loads instruction base+l (one coalesced 512 B read), the next block of 32 is prefetched
+// while the current one executes, and the instruction being executed is broadcast with shuffles, so
+// warps never synchronise with each other.  Values live in a per-witness register file in shared
+// memory laid out [register][half][thread] as uint4 (conflict-free LDS.128/STS.128); values that do
+// not fit are spilled to HBM witness-major ([slot][half][thread], coalesced 128-bit accesses).
+// Witness values are written canonical, 32 B each, at witness[w][position].
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <thread>
+
+#include "engine.hpp"
+#include "alu.cuh"
+
+namespace gw {
+
+struct KParams {
+  const uint4* code; uint32_t n_instr;
+  const uint4* consts;
+  const uint4* inputs;     // [B][I][2]
+  uint4* out;              // [B][W][2]
+  uint4* spill;            // [n_spill][2][spill_threads]
+  uint32_t* status;        // [B] or null
+  unsigned long long B;
+  uint32_t I, W;
+  uint32_t n_tiles;
+  unsigned long long spill_threads;
+};
+
+__device__ __forceinline__ fe fe_from(uint4 lo, uint4 hi) {
+  fe r; r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w; r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w; return r;
+}
+__device__ __forceinline__ uint4 fe_lo(const fe& a) { return make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]); }
+__device__ __forceinline__ uint4 fe_hi(const fe& a) { return make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]); }
+
+template <int T>
+__global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
+  extern __shared__ uint4 rf[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const unsigned long long gthread = (unsigned long long)blockIdx.x * T + tid;
+  const uint32_t n = p.n_instr;
+
+  auto rf_load = [&](uint32_t r) { return fe_from(rf[(r * 2) * T + tid], rf[(r * 2 + 1) * T + tid]); };
+  auto rf_store = [&](uint32_t r, const fe& v) { rf[(r * 2) * T + tid] = fe_lo(v); rf[(r * 2 + 1) * T + tid] = fe_hi(v); };
+  auto const_load = [&](uint32_t c) { return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1)); };
+
+  for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const unsigned long long w = (unsigned long long)tile * T + tid;
+    const bool active = w < p.B;
+    const unsigned long long wl = active ? w : p.B - 1;
+    const uint4* in = p.inputs + wl * p.I * 2;
+    uint4* out = p.out + wl * p.W * 2;
+    uint32_t st = 0;
+
+    uint4 nxt = __ldg(p.code + min((uint32_t)lane, n - 1));
+    for (uint32_t base = 0; base < n; base += 32) {
+      const uint4 cur = nxt;
+      if (base + 32 < n) nxt = __ldg(p.code + min(base + 32 + lane, n - 1));
+      const int cnt = min(32u, n - base);
+      for (int k = 0; k < cnt; k++) {
+        uint4 ins;
+        ins.x = __shfl_sync(0xffffffffu, cur.x, k);
+        ins.y = __shfl_sync(0xffffffffu, cur.y, k);
+        ins.z = __shfl_sync(0xffffffffu, cur.z, k);
+        ins.w = __shfl_sync(0xffffffffu, cur.w, k);
+        uint32_t op = ins.x & 0xFFu;
+        const uint32_t dst = ins.x >> 16;
+        fe A, Bv, R;
+        Bv = fe_zero();
+
+        if (op == OP_SPILL_ST) {
+          fe v = rf_load(ins.y);
+          p.spill[((size_t)ins.z * 2) * p.spill_threads + gthread] = fe_lo(v);
+          p.spill[((size_t)ins.z * 2 + 1) * p.spill_threads + gthread] = fe_hi(v);
+          continue;
+        }
+        if (op == OP_SPILL_LD) {
+          R = fe_from(p.spill[((size_t)ins.y * 2) * p.spill_threads + gthread],
+                      p.spill[((size_t)ins.y * 2 + 1) * p.spill_threads + gthread]);
+          rf_store(dst, R);
+          continue;
+        }
+        if (op == OP_INPUT) {
+          R = fe_reduce256(fe_from(__ldg(in + 2 * (size_t)ins.y), __ldg(in + 2 * (size_t)ins.y + 1)));
+        } else {
+          A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
+          if (op == OP_OUT) {
+            if (active) { out[2 * (size_t)ins.w] = fe_lo(A); out[2 * (size_t)ins.w + 1] = fe_hi(A); }
+            continue;
+          }
+          fe C;
+          if (op_has_b(op)) Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z);
+          if (op == OP_TERN) C = (ins.x & F_C_CONST) ? const_load(ins.w) : rf_load(ins.w);
+          R = alu_exec(op, A, Bv, C, st);
+        }
+        if (dst != NO_DST) rf_store(dst, R);
+        if ((ins.x & F_OUT) && active) { out[2 * (size_t)ins.w] = fe_lo(R); out[2 * (size_t)ins.w + 1] = fe_hi(R); }
+      }
+    }
+    if (p.status != nullptr && active) p.status[w] = st;
+  }
+}
+
+// ---- integer-pipe microbenchmark (roofline denominator for multiplication-heavy graphs) ---------
+// WHICH = 0: rows of (mad.lo.cc, madc.hi.cc) pairs exactly as in u256_mul_wide -> IMAD.WIDE.U32(.X)
+//            with carry predicates; counts one op per 32x32+64 multiply-accumulate,
+//         1: mad.lo.u32 (IMAD), 2: mad.hi.u32 (IMAD.HI.U32), 3: add.u32 (ALU pipe, for comparison).
+// Every multiplicand comes from another accumulator, so nothing is loop-invariant.  32 ops per
+// loop iteration and thread.  Reports executed ops per second over the whole chip.
+template <int WHICH>
+__global__ void imad_bench_kernel(uint32_t* out, int iters, uint32_t y) {
+  uint32_t x = threadIdx.x * 2654435761u + 12345u + blockIdx.x;
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = x + i * 131u;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (WHICH == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          uint32_t* e = s + 8 * r;
+          uint32_t m = s[8 * (1 - r) + u];
+          asm volatile("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1;"
+                       "madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3;"
+                       "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;"
+                       "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"
+                       : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7])
+                       : "r"(y), "r"(y ^ 0x55u), "r"(y + 3u), "r"(y * 3u), "r"(m));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (WHICH == 1) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(s[i]) : "r"(s[(i + 1) & 7]), "r"(y));
+          else if (WHICH == 2) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(s[i]) : "r"(s[(i + 1) & 7]), "r"(y));
+          else asm volatile("add.u32 %0, %0, %1;" : "+r"(s[i]) : "r"(s[(i + 1) & 7]));
+        }
+      }
+    }
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc ^= s[i];
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x); } while (0)
+
+double imad_microbench(int device, int which) {
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  uint32_t* d; CUDA_CHECK(cudaMalloc(&d, 4));
+  const int iters = 4000, threads = 256, blocks = prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  auto go = [&](int n) {
+    if (which == 0) imad_bench_kernel<0><<<blocks, threads>>>(d, n, 0x9e3779b9u);
+    else if (which == 1) imad_bench_kernel<1><<<blocks, threads>>>(d, n, 0x9e3779b9u);
+    else if (which == 2) imad_bench_kernel<2><<<blocks, threads>>>(d, n, 0x9e3779b9u);
+    else imad_bench_kernel<3><<<blocks, threads>>>(d, n, 0x9e3779b9u);
+  };
+  go(50);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CUDA_CHECK(cudaEventRecord(e0));
+    go(iters);
+    CUDA_CHECK(cudaEventRecord(e1));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  double ops = (double)blocks * threads * (double)iters * 32.0;
+  return ops / (best * 1e-3);
+}
+
+// ---- engine ------------------------------------------------------------------------------------------
+struct Engine::Dev {
+  int device = -1;
+  int sms = 0, ctas_per_sm = 0;
+  uint4* code = nullptr; uint4* consts = nullptr;
+  uint4* spill = nullptr; size_t spill_threads = 0;
+  // staging for the host-buffer API
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  uint4* d_in[2] = {nullptr, nullptr}; uint4* d_out[2] = {nullptr, nullptr};
+  uint32_t* d_status[2] = {nullptr, nullptr};
+  size_t chunk = 0;
+  std::mutex mu;
+};
+
+static int env_int(const char* name, int dflt) { const char* s = getenv(name); return (s && *s) ? atoi(s) : dflt; }
+
+Engine::Engine(const uint8_t* graph_data, size_t len) {
+  graph = deserialize_witnesscalc_graph(graph_data, len);
+  threads = env_int("GW_THREADS", 128);
+  if (threads != 64 && threads != 128 && threads != 256) throw Error("GW_THREADS must be 64, 128 or 256");
+  PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", 24);
+  plan = compile_plan(graph, opt);
+}
+
+Engine::~Engine() {
+  for (auto& kv : devs) {
+    Dev* d = kv.second;
+    cudaSetDevice(d->device);
+    cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
+    for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
+    delete d;
+  }
+}
+
+template <int T> static void launch_t(const KParams& p, int grid, size_t smem, cudaStream_t s) {
+  eval_batch_kernel<T><<<grid, T, smem, s>>>(p);
+}
+template <int T> static int setup_t(size_t smem) {
+  CUDA_CHECK(cudaFuncSetAttribute(eval_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int nb = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, eval_batch_kernel<T>, T, smem));
+  return nb;
+}
+
+Engine::Dev* Engine::dev(int device) {
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = devs.find(device);
+  if (it != devs.end()) return it->second;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) throw Error("no CUDA device available: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) throw Error("CUDA device index out of range");
+  CUDA_CHECK(cudaSetDevice(device));
+  Dev* d = new Dev();
+  d->device = device;
+  cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  d->sms = prop.multiProcessorCount;
+  size_t smem = (size_t)plan.n_regs * 32 * threads;
+  if (smem > (size_t)prop.sharedMemPerBlockOptin) throw Error("register file does not fit shared memory: lower GW_REGS or GW_THREADS");
+  d->ctas_per_sm = threads == 64 ? setup_t<64>(smem) : threads == 128 ? setup_t<128>(smem) : setup_t<256>(smem);
+  if (d->ctas_per_sm < 1) throw Error("kernel cannot be resident with this register-file size");
+  CUDA_CHECK(cudaMalloc(&d->code, plan.code.size() * sizeof(Instr)));
+  CUDA_CHECK(cudaMemcpy(d->code, plan.code.data(), plan.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&d->consts, plan.consts.size() * 32));
+  CUDA_CHECK(cudaMemcpy(d->consts, plan.consts.data(), plan.consts.size() * 32, cudaMemcpyHostToDevice));
+  d->spill_threads = (size_t)d->sms * d->ctas_per_sm * threads;
+  if (plan.n_spill) CUDA_CHECK(cudaMalloc(&d->spill, (size_t)plan.n_spill * 32 * d->spill_threads));
+  devs[device] = d;
+  return d;
+}
+
+void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
+  if (B == 0 || plan.code.empty()) return;
+  KParams p;
+  p.code = d->code; p.n_instr = (uint32_t)plan.code.size(); p.consts = d->consts;
+  p.inputs = (const uint4*)d_inputs; p.out = (uint4*)d_witness; p.spill = d->spill; p.status = d_status;
+  p.B = B; p.I = plan.n_inputs; p.W = plan.n_witness;
+  size_t n_tiles = (B + threads - 1) / threads;
+  if (n_tiles > 0xFFFFFFFFull) throw Error("batch too large");
+  p.n_tiles = (uint32_t)n_tiles;
+  p.spill_threads = d->spill_threads;
+  int grid = (int)std::min<size_t>(n_tiles, (size_t)d->sms * d->ctas_per_sm);
+  size_t smem = (size_t)plan.n_regs * 32 * threads;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (threads == 64) launch_t<64>(p, grid, smem, s); else if (threads == 128) launch_t<128>(p, grid, smem, s); else launch_t<256>(p, grid, smem, s);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void Engine::run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
+  Dev* d = dev(device);
+  CUDA_CHECK(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(d->mu);     // the spill area is shared by all launches on this device
+  launch(d, d_inputs, B, d_witness, d_status, stream);
+}
+
+// host buffers: chunked, double-buffered H2D -> kernel -> D2H on two streams
+void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status) {
+  Dev* d = dev(device);
+  CUDA_CHECK(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(d->mu);
+  const size_t in_b = (size_t)plan.n_inputs * 32, out_b = (size_t)plan.n_witness * 32;
+  // chunk: enough witnesses to fill the chip a few times, bounded by a memory budget per buffer
+  size_t budget = (size_t)env_int("GW_CHUNK_MB", 4096) << 20;
+  size_t chunk = std::max<size_t>(threads, std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 4 * d->spill_threads));
+  chunk = std::min(chunk, std::max<size_t>(B, 1));
+  if (chunk > d->chunk) {
+    for (int i = 0; i < 2; i++) {
+      cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]);
+      CUDA_CHECK(cudaMalloc(&d->d_in[i], chunk * in_b));
+      CUDA_CHECK(cudaMalloc(&d->d_out[i], std::max<size_t>(chunk * out_b, 32)));
+      CUDA_CHECK(cudaMalloc(&d->d_status[i], chunk * 4));
+      if (!d->stream[i]) CUDA_CHECK(cudaStreamCreateWithFlags(&d->stream[i], cudaStreamNonBlocking));
+    }
+    d->chunk = chunk;
+  }
+  // Both streams share the spill area, so kernels of consecutive chunks must not overlap: an event
+  // chains kernel k+1 behind kernel k while the copies of the two streams overlap with it.
+  cudaEvent_t kdone[2]; CUDA_CHECK(cudaEventCreateWithFlags(&kdone[0], cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&kdone[1], cudaEventDisableTiming));
+  int k = 0;
+  for (size_t off = 0; off < B; off += chunk, k ^= 1) {
+    size_t nb = std::min(chunk, B - off);
+    cudaStream_t s = d->stream[k];
+    CUDA_CHECK(cudaMemcpyAsync(d->d_in[k], inputs + off * in_b, nb * in_b, cudaMemcpyHostToDevice, s));
+    if (off) CUDA_CHECK(cudaStreamWaitEvent(s, kdone[k ^ 1], 0));
+    launch(d, d->d_in[k], nb, d->d_out[k], status ? d->d_status[k] : nullptr, s);
+    CUDA_CHECK(cudaEventRecord(kdone[k], s));
+    CUDA_CHECK(cudaMemcpyAsync(witness + off * out_b, d->d_out[k], nb * out_b, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_CHECK(cudaMemcpyAsync(status + off, d->d_status[k], nb * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(d->stream[0]));
+  CUDA_CHECK(cudaStreamSynchronize(d->stream[1]));
+  cudaEventDestroy(kdone[0]); cudaEventDestroy(kdone[1]);
+}
+
+void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device) {
+  if (B == 0) return;
+  if (n_gpus <= 1) { run_host_on(first_device, inputs, B, witness, status); return; }
+  // independent input sets: contiguous shards, one host thread per GPU, no collective
+  const size_t in_b = (size_t)plan.n_inputs * 32, out_b = (size_t)plan.n_witness * 32;
+  std::vector<std::thread> th;
+  std::vector<std::string> errs(n_gpus);
+  for (int g = 0; g < n_gpus; g++) {
+    size_t lo = B * g / n_gpus, hi = B * (g + 1) / n_gpus;
+    if (hi == lo) continue;
+    th.emplace_back([=, &errs]() {
+      try { run_host_on(first_device + g, inputs + lo * in_b, hi - lo, witness + lo * out_b, status ? status + lo : nullptr); }
+      catch (const std::exception& e) { errs[g] = e.what(); }
+    });
+  }
+  for (auto& t : th) t.join();
+  for (auto& e : errs) if (!e.empty()) throw Error(e);
+}
+
+int cuda_device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+}  // namespace gw

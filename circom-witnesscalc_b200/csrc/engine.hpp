@@ -1,0 +1,40 @@
+// A loaded witness graph: parsed, compiled to a device plan once, uploaded lazily per GPU.
+// This is the persistent state the reference does not have (it re-parses the graph on every
+// calc_witness call, /root/reference/src/lib.rs:129-130).
+#pragma once
+#include <map>
+#include <mutex>
+
+#include "graph.hpp"
+#include "plan.hpp"
+
+namespace gw {
+
+class Engine {
+ public:
+  Engine(const uint8_t* graph_data, size_t len);
+  ~Engine();
+  Engine(const Engine&) = delete;
+
+  Graph graph;
+  Plan plan;
+  int threads = 128;          // witnesses per CTA
+
+  // inputs/witness resident on `device`: inputs [B][I][32 B LE], witness [B][W][32 B LE]; asynchronous on `stream`
+  void run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
+  // host buffers; shards the batch over n_gpus devices starting at first_device (no collective)
+  void run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device);
+
+ private:
+  struct Dev;
+  Dev* dev(int device);
+  void launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
+  void run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status);
+  std::map<int, Dev*> devs;
+  std::mutex mu;
+};
+
+int cuda_device_count();
+double imad_microbench(int device, int which);
+
+}  // namespace gw

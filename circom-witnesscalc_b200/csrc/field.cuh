@@ -1,0 +1,476 @@
+// BN254 scalar-field and 256-bit integer arithmetic on 8 x 32-bit limbs (little-endian limbs).
+//
+// Replaces, on the device, what the reference gets from ark-ff / ruint behind
+// /root/reference/src/graph.rs:102-144 (Operation::eval_fr), :188-197, :221-225 and the helpers
+// :621-769 (shl, shr, bit_and/or/xor, u_lt/u_gt/u_lte/u_gte), modulus from src/field.rs:3-4.
+//
+// Design choice (see DESIGN.md "value domain"): graph values are kept CANONICAL in [0, M), not in
+// Montgomery form.  Multiplication is schoolbook 8x8 + Barrett reduction (q = floor(ab/M) estimated
+// from the top 256 bits with mu = floor(2^509/M); the estimate is never more than 1 too small).
+// The integer-domain ops (shifts, bitwise, comparisons, Idiv/Mod) and the .wtns output then need no
+// Montgomery<->canonical conversion at all, which is where the reference spends most of its time on
+// bit-heavy graphs.  Montgomery multiplication (fe_mont_mul) is provided for chains that stay in the
+// field (inversion, pow).
+//
+// Every function is __host__ __device__: the device path uses PTX carry chains
+// (mad.lo.cc / madc.hi.cc pairs that ptxas fuses into IMAD.WIDE.U32 with carry), the host path is
+// plain C used only by the unit tests of this header (tests/csrc/test_field_host.cpp).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GW_HD __host__ __device__ __forceinline__
+#define GW_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define GW_HD inline
+#define GW_HD_NOINLINE
+#endif
+
+namespace gw {
+
+struct fe { uint32_t l[8]; };
+
+// ---- constants (constexpr selectors so that unrolled device code sees immediates) ---------------
+GW_HD constexpr uint32_t MOD_L(int i) {   // M
+  return i == 0 ? 0xf0000001u : i == 1 ? 0x43e1f593u : i == 2 ? 0x79b97091u : i == 3 ? 0x2833e848u :
+         i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+}
+GW_HD constexpr uint32_t MU_L(int i) {    // floor(2^509 / M)
+  return i == 0 ? 0x7c3bd24bu : i == 1 ? 0xc40e074du : i == 2 ? 0x13d1015cu : i == 3 ? 0xe2890a40u :
+         i == 4 ? 0xd00e6028u : i == 5 ? 0x560e94b0u : i == 6 ? 0xc474094fu : 0xa948e8c4u;
+}
+GW_HD constexpr uint32_t HALF_L(int i) {  // floor(M / 2), graph.rs:720
+  return i == 0 ? 0xf8000000u : i == 1 ? 0xa1f0fac9u : i == 2 ? 0x3cdcb848u : i == 3 ? 0x9419f424u :
+         i == 4 ? 0x40c0ac2eu : i == 5 ? 0xdc2822dbu : i == 6 ? 0x7098d014u : 0x18322739u;
+}
+GW_HD constexpr uint32_t MM2_L(int i) {   // M - 2 (Fermat exponent)
+  return i == 0 ? 0xefffffffu : MOD_L(i);
+}
+GW_HD constexpr uint32_t R2_L(int i) {    // 2^512 mod M
+  return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u :
+         i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+}
+static const uint32_t MONT_INV32 = 0xefffffffu;   // -M^-1 mod 2^32
+
+GW_HD fe fe_zero() { fe r; for (int i = 0; i < 8; i++) r.l[i] = 0; return r; }
+GW_HD fe fe_small(uint32_t v) { fe r = fe_zero(); r.l[0] = v; return r; }
+GW_HD fe fe_modulus() { fe r; for (int i = 0; i < 8; i++) r.l[i] = MOD_L(i); return r; }
+
+// ---- carry-chain primitives ----------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define GW_ASM asm volatile
+__device__ __forceinline__ uint32_t ptx_add_cc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t ptx_addc_cc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t ptx_addc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t ptx_sub_cc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t ptx_subc_cc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t ptx_subc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t ptx_mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t ptx_madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t ptx_madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t ptx_madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#endif
+
+// r = a + b (mod 2^256); returns the carry out
+GW_HD uint32_t u256_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__)
+  r[0] = ptx_add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r[i] = ptx_addc_cc(a[i], b[i]);
+  return ptx_addc(0, 0);
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (uint64_t)a[i] + b[i]; r[i] = (uint32_t)c; c >>= 32; }
+  return (uint32_t)c;
+#endif
+}
+
+// r = a - b (mod 2^256); returns the borrow out (1 if a < b)
+GW_HD uint32_t u256_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__)
+  r[0] = ptx_sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r[i] = ptx_subc_cc(a[i], b[i]);
+  return ptx_subc(0, 0) & 1u;     // 0 - 0 - borrow = 0xFFFFFFFF when borrow
+#else
+  int64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (int64_t)a[i] - b[i]; r[i] = (uint32_t)c; c >>= 32; }
+  return (uint32_t)(c & 1);
+#endif
+}
+
+GW_HD bool u256_is_zero(const uint32_t* a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a[i];
+  return o == 0;
+}
+GW_HD bool u256_eq(const uint32_t* a, const uint32_t* b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a[i] ^ b[i];
+  return o == 0;
+}
+// a < b (unsigned)
+GW_HD bool u256_lt(const uint32_t* a, const uint32_t* b) {
+  uint32_t t[8];
+  return u256_sub(t, a, b) != 0;
+}
+
+// if a >= M then a -= M
+GW_HD void fe_cond_sub_m(fe& a) {
+  fe m = fe_modulus();
+  uint32_t t[8];
+  uint32_t borrow = u256_sub(t, a.l, m.l);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.l[i] = borrow ? a.l[i] : t[i];
+}
+GW_HD bool fe_is_zero(const fe& a) { return u256_is_zero(a.l); }
+GW_HD bool fe_geq_m(const fe& a) { fe m = fe_modulus(); return !u256_lt(a.l, m.l); }
+
+// any 256-bit integer -> [0, M)   (Fr::new / from_le_bytes_mod_order on load, graph.rs:376, storage.rs:28)
+GW_HD fe fe_reduce256(fe a) {
+#pragma unroll 1
+  for (int k = 0; k < 5; k++) fe_cond_sub_m(a);   // 2^256 / M < 5.3
+  return a;
+}
+
+GW_HD fe fe_add(const fe& a, const fe& b) {          // graph.rs:110
+  fe r; u256_add(r.l, a.l, b.l);                     // a + b < 2M < 2^256: no carry out
+  fe_cond_sub_m(r); return r;
+}
+GW_HD fe fe_sub(const fe& a, const fe& b) {          // graph.rs:111
+  fe r; uint32_t borrow = u256_sub(r.l, a.l, b.l);
+  fe m = fe_modulus(); uint32_t t[8]; u256_add(t, r.l, m.l);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = borrow ? t[i] : r.l[i];
+  return r;
+}
+GW_HD fe fe_neg(const fe& a) {                       // graph.rs:190-194
+  fe m = fe_modulus(); fe r; u256_sub(r.l, m.l, a.l);
+  bool z = fe_is_zero(a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = z ? 0u : r.l[i];
+  return r;
+}
+
+// ---- 8x8 -> 16 limb product ----------------------------------------------------------------------
+// Device: the partial products a_j*b_i are split by the parity of (i+j).  Products of one parity
+// never overlap inside a row, so every row is one carry chain of (mad.lo.cc, madc.hi.cc) pairs that
+// accumulate a full 32x32+64 result per pair (IMAD.WIDE.U32 with carry in SASS).  e[] collects the
+// even columns, o[] the odd ones (o[k] is column k+1); they are merged once at the end.
+GW_HD void u256_mul_wide(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t e[18], o[18];
+#pragma unroll
+  for (int i = 0; i < 18; i++) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t bi = b[i];
+    const int p = i & 1;
+    // same-parity limbs a_j (j = p, p+2, ..): column i+j is even -> e[i+j], e[i+j+1]
+    {
+      const int c0 = i + p;
+      e[c0] = ptx_mad_lo_cc(a[p], bi, e[c0]);
+      e[c0 + 1] = ptx_madc_hi_cc(a[p], bi, e[c0 + 1]);
+#pragma unroll
+      for (int j = p + 2; j < 8; j += 2) {
+        e[i + j] = ptx_madc_lo_cc(a[j], bi, e[i + j]);
+        e[i + j + 1] = ptx_madc_hi_cc(a[j], bi, e[i + j + 1]);
+      }
+      e[c0 + 8] = ptx_addc(e[c0 + 8], 0);
+    }
+    // opposite-parity limbs a_j (j = 1-p, ..): column i+j is odd -> o[i+j-1], o[i+j]
+    {
+      const int q = 1 - p;
+      const int c0 = i + q - 1;
+      o[c0] = ptx_mad_lo_cc(a[q], bi, o[c0]);
+      o[c0 + 1] = ptx_madc_hi_cc(a[q], bi, o[c0 + 1]);
+#pragma unroll
+      for (int j = q + 2; j < 8; j += 2) {
+        o[i + j - 1] = ptx_madc_lo_cc(a[j], bi, o[i + j - 1]);
+        o[i + j] = ptx_madc_hi_cc(a[j], bi, o[i + j]);
+      }
+      o[c0 + 8] = ptx_addc(o[c0 + 8], 0);
+    }
+  }
+  out[0] = e[0];
+  out[1] = ptx_add_cc(e[1], o[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) out[k] = ptx_addc_cc(e[k], o[k - 1]);
+  out[15] = ptx_addc(e[15], o[14]);
+#else
+  uint32_t t[16];
+  for (int i = 0; i < 16; i++) t[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) { c += (uint64_t)a[j] * b[i] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32; }
+    t[i + 8] = (uint32_t)c;
+  }
+  for (int i = 0; i < 16; i++) out[i] = t[i];
+#endif
+}
+
+// low 8 limbs of a*b
+GW_HD void u256_mul_lo(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t e[10], o[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t bi = b[i];
+    const int p = i & 1;
+    {
+      const int c0 = i + p;           // even columns c0, c0+2, .. <= 7 (its high word may be column 8: dropped)
+      if (c0 < 8) {
+        e[c0] = ptx_mad_lo_cc(a[p], bi, e[c0]);
+        e[c0 + 1] = ptx_madc_hi_cc(a[p], bi, e[c0 + 1]);
+#pragma unroll
+        for (int j = p + 2; j < 8; j += 2) {
+          if (i + j < 8) {
+            e[i + j] = ptx_madc_lo_cc(a[j], bi, e[i + j]);
+            e[i + j + 1] = ptx_madc_hi_cc(a[j], bi, e[i + j + 1]);
+          }
+        }
+      }
+    }
+    {
+      const int q = 1 - p;
+      const int c0 = i + q - 1;       // o index of the odd column i+q
+      if (c0 + 1 < 8) {
+        o[c0] = ptx_mad_lo_cc(a[q], bi, o[c0]);
+        o[c0 + 1] = ptx_madc_hi_cc(a[q], bi, o[c0 + 1]);
+#pragma unroll
+        for (int j = q + 2; j < 8; j += 2) {
+          if (i + j < 8) {
+            o[i + j - 1] = ptx_madc_lo_cc(a[j], bi, o[i + j - 1]);
+            o[i + j] = ptx_madc_hi_cc(a[j], bi, o[i + j]);
+          }
+        }
+      }
+    }
+  }
+  out[0] = e[0];
+  out[1] = ptx_add_cc(e[1], o[0]);
+#pragma unroll
+  for (int k = 2; k < 7; k++) out[k] = ptx_addc_cc(e[k], o[k - 1]);
+  out[7] = ptx_addc(e[7], o[6]);
+#else
+  uint32_t t[16];
+  u256_mul_wide(t, a, b);
+  for (int i = 0; i < 8; i++) out[i] = t[i];
+#endif
+}
+
+GW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {   // low 32 bits of (hi:lo) >> s, 0 <= s < 32
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
+  return s == 0 ? lo : (lo >> s) | (hi << (32 - s));
+#endif
+}
+
+// 512-bit product (< 2^508) -> [0, M) by Barrett reduction
+GW_HD fe fe_barrett(const uint32_t* P) {
+  uint32_t q1[8], mu[8], Q[16], qh[8], m[8], T[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { q1[k] = funnel_r(P[7 + k], P[8 + k], 28); mu[k] = MU_L(k); m[k] = MOD_L(k); }  // P >> 252
+  u256_mul_wide(Q, q1, mu);
+#pragma unroll
+  for (int k = 0; k < 7; k++) qh[k] = funnel_r(Q[8 + k], Q[9 + k], 1);                                         // Q >> 257
+  qh[7] = Q[15] >> 1;
+  u256_mul_lo(T, qh, m);
+  fe r; u256_sub(r.l, P, T);      // 0 <= P - qh*M < 3M < 2^256, so the low 256 bits are exact
+  fe_cond_sub_m(r); fe_cond_sub_m(r);
+  return r;
+}
+
+GW_HD fe fe_mul(const fe& a, const fe& b) {          // graph.rs:105
+  uint32_t P[16];
+  u256_mul_wide(P, a.l, b.l);
+  return fe_barrett(P);
+}
+GW_HD fe fe_sqr(const fe& a) { return fe_mul(a, a); }
+// out-of-line copy for the long chains (inversion, pow): keeps the interpreter's code size down
+GW_HD_NOINLINE fe fe_mul_ni(const fe& a, const fe& b) { return fe_mul(a, b); }
+
+// Montgomery product a*b*2^-256 mod M (operands < M), CIOS on 32-bit limbs.
+GW_HD fe fe_mont_mul(const fe& a, const fe& b) {
+  uint32_t t[10];
+  for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { c += (uint64_t)a.l[j] * b.l[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+    c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+    uint32_t mq = t[0] * MONT_INV32;
+    c = ((uint64_t)mq * MOD_L(0) + t[0]) >> 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) { c += (uint64_t)mq * MOD_L(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+    c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+  }
+  fe r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = t[i];
+  fe_cond_sub_m(r);
+  return r;
+}
+GW_HD fe fe_to_mont(const fe& a) { fe r2; for (int i = 0; i < 8; i++) r2.l[i] = R2_L(i); return fe_mont_mul(a, r2); }
+GW_HD fe fe_from_mont(const fe& a) { return fe_mont_mul(a, fe_small(1)); }
+
+// a^e for a 256-bit exponent held per lane (square and multiply, msb first, 254 bits are enough:
+// exponents are canonical field values).  Pow is unimplemented! at run time in the reference
+// (graph.rs:141-142); build-time meaning a.pow_mod(b, M) (graph.rs:79).
+GW_HD_NOINLINE fe fe_pow(const fe& a, const fe& e) {
+  fe r = fe_small(1);
+#pragma unroll 1
+  for (int i = 253; i >= 0; i--) {
+    r = fe_mul_ni(r, r);
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) w = (k == (i >> 5)) ? e.l[k] : w;
+    fe t = fe_mul_ni(r, a);
+    bool bit = (w >> (i & 31)) & 1u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.l[k] = bit ? t.l[k] : r.l[k];
+  }
+  return r;
+}
+
+// a^(M-2): inverse, 0 -> 0 (Div by zero yields 0, graph.rs:109).  The exponent is a compile-time
+// constant, so the multiply branch is uniform across the warp.
+GW_HD_NOINLINE fe fe_inv_fermat(const fe& a) {
+  fe r = fe_small(1);
+#pragma unroll 1
+  for (int i = 253; i >= 0; i--) {
+    r = fe_mul_ni(r, r);
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) w = (k == (i >> 5)) ? MM2_L(k) : w;
+    if ((w >> (i & 31)) & 1u) r = fe_mul_ni(r, a);
+  }
+  return r;
+}
+
+// ---- integer-domain ops ---------------------------------------------------------------------------
+// logical right shift of a 256-bit value by n in [0, 255] with static register indexing
+GW_HD fe u256_shr(fe a, uint32_t n) {
+  uint32_t ws = n >> 5, bs = n & 31;
+  if (ws & 4) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.l[i] = (i + 4 < 8) ? a.l[i + 4] : 0u;
+  }
+  if (ws & 2) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.l[i] = (i + 2 < 8) ? a.l[i + 2] : 0u;
+  }
+  if (ws & 1) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.l[i] = (i + 1 < 8) ? a.l[i + 1] : 0u;
+  }
+  fe r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = funnel_r(a.l[i], (i + 1 < 8) ? a.l[i + 1] : 0u, bs);
+  return r;
+}
+// left shift truncated to 256 bits, n in [0, 255]
+GW_HD fe u256_shl(fe a, uint32_t n) {
+  uint32_t ws = n >> 5, bs = n & 31;
+  if (ws & 4) {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) a.l[i] = (i >= 4) ? a.l[i - 4] : 0u;
+  }
+  if (ws & 2) {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) a.l[i] = (i >= 2) ? a.l[i - 2] : 0u;
+  }
+  if (ws & 1) {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) a.l[i] = (i >= 1) ? a.l[i - 1] : 0u;
+  }
+  fe r;
+#pragma unroll
+  for (int i = 7; i >= 0; i--) {
+    uint32_t lo = (i >= 1) ? a.l[i - 1] : 0u;
+    r.l[i] = bs == 0 ? a.l[i] : ((a.l[i] << bs) | (lo >> (32 - bs)));
+  }
+  return r;
+}
+// shift amount as the reference reads it: b == 0 -> 0, b >= 254 -> 254 (meaning "result is 0"), else b
+GW_HD uint32_t shift_amount(const fe& b) {
+  uint32_t hi = 0;
+#pragma unroll
+  for (int i = 1; i < 8; i++) hi |= b.l[i];
+  return (hi != 0 || b.l[0] >= 254u) ? 254u : b.l[0];
+}
+GW_HD fe fe_shr(const fe& a, const fe& b) {          // graph.rs:637-672
+  uint32_t n = shift_amount(b);
+  fe r = u256_shr(a, n & 255u);
+  if (n >= 254u) r = fe_zero();
+  return r;
+}
+// graph.rs:621-635; *overflow is set where the reference panics (result >= M), in which case the
+// circom semantics ((a << b) & (2^254 - 1)) mod M are returned.
+GW_HD fe fe_shl(const fe& a, const fe& b, bool* overflow) {
+  uint32_t n = shift_amount(b);
+  fe r = u256_shl(a, n & 255u);
+  if (n >= 254u) r = fe_zero();
+  *overflow = fe_geq_m(r);
+  r.l[7] &= 0x3FFFFFFFu;
+  fe_cond_sub_m(r);
+  return r;
+}
+// graph.rs:674-717; which: 0 = and, 1 = or, 2 = xor.  *eq_m is set where the reference panics.
+GW_HD fe fe_bitop(const fe& a, const fe& b, int which, bool* eq_m) {
+  fe d;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d.l[i] = which == 0 ? (a.l[i] & b.l[i]) : which == 1 ? (a.l[i] | b.l[i]) : (a.l[i] ^ b.l[i]);
+  fe m = fe_modulus();
+  *eq_m = u256_eq(d.l, m.l);
+  fe_cond_sub_m(d);
+  return d;
+}
+GW_HD fe fe_bnot(const fe& a) {                      // circom: (~a & (2^254 - 1)) mod M  (extension)
+  fe d;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d.l[i] = ~a.l[i];
+  d.l[7] &= 0x3FFFFFFFu;
+  fe_cond_sub_m(d);
+  return d;
+}
+// circom signed comparison, graph.rs:723-769.  which: 0 = lt, 1 = gt, 2 = leq, 3 = geq
+GW_HD bool fe_cmp(const fe& a, const fe& b, int which) {
+  uint32_t half[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) half[i] = HALF_L(i);
+  bool an = u256_lt(half, a.l), bn = u256_lt(half, b.l);
+  bool lt = u256_lt(a.l, b.l), gt = u256_lt(b.l, a.l);
+  if (an != bn) return (which == 0 || which == 2) ? an : bn;
+  return which == 0 ? lt : which == 1 ? gt : which == 2 ? !gt : !lt;
+}
+// unsigned 256-bit division (b != 0): binary long division, 254 uniform steps (a < 2^254)
+GW_HD_NOINLINE void u256_divrem(const fe& a, const fe& b, fe* q, fe* r) {
+  fe quo = fe_zero(), rem = fe_zero();
+#pragma unroll 1
+  for (int i = 253; i >= 0; i--) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) w = (k == (i >> 5)) ? a.l[k] : w;
+    uint32_t bit = (w >> (i & 31)) & 1u;
+#pragma unroll
+    for (int k = 7; k >= 1; k--) rem.l[k] = (rem.l[k] << 1) | (rem.l[k - 1] >> 31);
+    rem.l[0] = (rem.l[0] << 1) | bit;
+    uint32_t t[8];
+    uint32_t borrow = u256_sub(t, rem.l, b.l);
+#pragma unroll
+    for (int k = 0; k < 8; k++) rem.l[k] = borrow ? rem.l[k] : t[k];
+    uint32_t qb = (borrow ? 0u : 1u) << (i & 31);
+#pragma unroll
+    for (int k = 0; k < 8; k++) quo.l[k] |= (k == (i >> 5)) ? qb : 0u;
+  }
+  *q = quo; *r = rem;
+}
+
+}  // namespace gw

@@ -1,0 +1,112 @@
+/* C ABI of the B200 witness evaluator.
+ *
+ * Part 1 is the reference's header verbatim in meaning: /root/reference/include/graph_witness.h:7-28
+ * (GW_ERROR_CODE, gw_status_t, gw_calc_witness, gw_free_status), implemented by the reference in
+ * src/lib.rs:28-111.  examples/calc_witness.c of the reference compiles against this file unchanged.
+ * Part 2 is the batch extension: load a graph once, evaluate many input sets.
+ *
+ * Every entry point is backed by CUDA kernels; there is no CPU fallback: without a usable GPU the
+ * calls return 1 with an error message.
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#ifndef RUST_GRAPH_WITNESS_H
+#define RUST_GRAPH_WITNESS_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- part 1: drop-in (reference include/graph_witness.h:7-28) ---------------------------------- */
+
+typedef enum {
+  OK = 0,
+  ERROR = 1
+} GW_ERROR_CODE;
+
+typedef struct {
+  GW_ERROR_CODE code;
+  char *error_msg;
+} gw_status_t;
+
+/* inputs: NUL-terminated UTF-8 JSON; graph_data: a wtns.graph.001 file; on success *wtns_data is a
+ * malloc'ed .wtns file of *wtns_len bytes that the caller frees.  Returns 0 on success, 1 on error
+ * (status->code = ERROR, status->error_msg malloc'ed).  Deviation from src/lib.rs:106-108: on
+ * success status is {OK, NULL} (the reference writes {ERROR, "test error"}) and nothing is printed. */
+int
+gw_calc_witness(const char *inputs,
+                const void *graph_data, const size_t graph_data_len,
+                void **wtns_data, size_t *wtns_len,
+                const gw_status_t *status);
+
+/* reference include/graph_witness.h:23-28 defines this function in the header; kept, but static
+ * inline so that the header can be included from more than one translation unit. */
+static inline void
+gw_free_status(gw_status_t *status) {
+  if (status->error_msg != NULL) {
+    free(status->error_msg);
+  }
+}
+
+/* ---- part 2: batch extension ---------------------------------------------------------------------- */
+
+typedef struct gw_graph gw_graph_t;
+
+typedef struct {
+  uint64_t n_nodes;       /* nodes in the graph file */
+  uint64_t n_ops;         /* Op + UnoOp + TresOp nodes (unit of the node-ops/s metric) */
+  uint32_t n_inputs;      /* I: input buffer length including slot 0 (the constant 1) */
+  uint32_t n_witness;     /* W: witness length */
+  uint32_t n_input_signals;
+  uint32_t n_instrs;      /* device instructions per witness */
+  uint32_t n_regs;        /* per-witness registers in shared memory */
+  uint32_t n_spill;       /* per-witness spill slots in HBM */
+  uint64_t n_mul;         /* field multiplications per witness (Mul) */
+  uint64_t n_div;         /* field divisions per witness (Div) */
+  uint64_t n_spill_ld;    /* spill loads per witness */
+  uint64_t n_spill_st;    /* spill stores per witness */
+} gw_graph_info_t;
+
+/* replaces storage::deserialize_witnesscalc_graph (src/storage.rs:214-249) + upload; parse once */
+int gw_graph_load(const void *graph_data, size_t graph_data_len, gw_graph_t **graph, gw_status_t *status);
+void gw_graph_free(gw_graph_t *graph);
+int gw_graph_info(const gw_graph_t *graph, gw_graph_info_t *info);
+/* i-th input signal of the graph's input map (InputSignalsInfo, src/lib.rs:19); name is owned by the graph */
+int gw_graph_input_signal(const gw_graph_t *graph, uint32_t i, const char **name, uint32_t *offset, uint32_t *len);
+
+/* calc_witness (src/lib.rs:125-136) + wtns_from_witness (:114-123) on a pre-loaded graph */
+int gw_graph_calc_witness(gw_graph_t *graph, const char *inputs_json, void **wtns_data, size_t *wtns_len,
+                          gw_status_t *status);
+
+/* graph::evaluate (src/graph.rs:367-391) for n_sets independent input sets, HOST buffers.
+ *   inputs : n_sets x n_inputs x 32 bytes, little-endian 256-bit values, row-major; slot 0 of every
+ *            row is ignored (it is the constant 1); values >= M are reduced mod M like Fr::new.
+ *   witness: n_sets x n_witness x 32 bytes, canonical little-endian (the .wtns payload of each set).
+ *   flags  : optional (may be NULL) n_sets x uint32: per-set bits for cases where the reference
+ *            panics (1 Shl overflow, 2 Bor/Bxor == M, 4 Pow, 8 Id, 16 Lnot/Bnot).
+ *   n_gpus : the sets are split into n_gpus contiguous shards, one per device, no collective. */
+int gw_calc_witness_batch(gw_graph_t *graph, const uint8_t *inputs, size_t n_sets, uint8_t *witness,
+                          uint32_t *flags, int n_gpus, gw_status_t *status);
+
+/* same, buffers already resident on CUDA device `device`; enqueued on `cuda_stream` (a cudaStream_t,
+ * NULL = default stream) and asynchronous with respect to the host. */
+int gw_calc_witness_batch_device(gw_graph_t *graph, int device, const void *d_inputs, size_t n_sets,
+                                 void *d_witness, uint32_t *d_flags, void *cuda_stream, gw_status_t *status);
+
+/* writes the 76-byte .wtns header for n_witness values (src/lib.rs:114-123) */
+void gw_wtns_header(uint32_t n_witness, uint8_t *dst76);
+
+/* diagnostics */
+int gw_device_count(void);
+/* integer-pipe microbenchmark: executed multiply-add instructions per second on `device`;
+ * which = 0 IMAD.WIDE.U32 carry rows (32x32+64, the form the field multiplier uses), 1 mad.lo.u32,
+ * 2 mad.hi.u32, 3 add.u32 */
+double gw_microbench_imad(int device, int which);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RUST_GRAPH_WITNESS_H */

@@ -1,0 +1,82 @@
+// TEST-ONLY host simulator of the device plan: executes the instruction stream that plan.cpp emits
+// with the host path of csrc/alu.cuh, one witness at a time.  It exists so that the graph codec, the
+// inputs parser, the register allocator / spill logic and the op semantics can be checked against the
+// oracle on a machine without a GPU.  It is NOT part of libcircom_witnesscalc.so (the product has no
+// CPU fallback); the same alu_exec() runs on the device inside eval_batch_kernel.
+#include <string.h>
+
+#include <memory>
+
+#include "../../circom-witnesscalc_b200/csrc/alu.cuh"
+#include "../../circom-witnesscalc_b200/csrc/graph.hpp"
+#include "../../circom-witnesscalc_b200/csrc/inputs.hpp"
+#include "../../circom-witnesscalc_b200/csrc/plan.hpp"
+#include "../../circom-witnesscalc_b200/csrc/wtns.hpp"
+
+using namespace gw;
+
+struct SimGraph { Graph g; Plan plan; std::string err; };
+
+static fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
+
+extern "C" {
+
+SimGraph* sim_load(const uint8_t* data, size_t len, uint32_t n_regs, char* err, size_t errlen) {
+  try {
+    std::unique_ptr<SimGraph> s(new SimGraph());
+    s->g = deserialize_witnesscalc_graph(data, len);
+    PlanOptions o; o.n_regs = n_regs;
+    s->plan = compile_plan(s->g, o);
+    return s.release();
+  } catch (const std::exception& e) { if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; } return nullptr; }
+}
+void sim_free(SimGraph* s) { delete s; }
+void sim_info(SimGraph* s, uint64_t* out) {
+  out[0] = s->g.nodes.size(); out[1] = s->plan.n_inputs; out[2] = s->plan.n_witness; out[3] = s->plan.code.size();
+  out[4] = s->plan.n_regs; out[5] = s->plan.n_spill; out[6] = s->plan.stats.spill_ld; out[7] = s->plan.stats.spill_st;
+  out[8] = s->plan.stats.max_live; out[9] = s->plan.consts.size(); out[10] = s->plan.stats.live_ops; out[11] = s->plan.stats.graph_ops;
+}
+// inputs: I x 32 B, witness: W x 32 B; returns status bits, or -1 on a malformed plan
+int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
+  const Plan& p = s->plan;
+  std::vector<fe> rf(p.n_regs, fe_zero()), spill(p.n_spill, fe_zero());
+  uint32_t st = 0;
+  for (const Instr& ins : p.code) {
+    uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
+    fe A = fe_zero(), B = fe_zero(), C = fe_zero(), R;
+    if (op == OP_SPILL_ST) { if (ins.y >= p.n_regs || ins.z >= p.n_spill) return -1; spill[ins.z] = rf[ins.y]; continue; }
+    if (op == OP_SPILL_LD) { if (dst >= p.n_regs || ins.y >= p.n_spill) return -1; rf[dst] = spill[ins.y]; continue; }
+    if (op == OP_INPUT) {
+      if (ins.y >= p.n_inputs) return -1;
+      fe v; memcpy(v.l, inputs + 32 * (size_t)ins.y, 32);
+      R = fe_reduce256(v);
+    } else {
+      auto load = [&](uint32_t idx, bool is_const, fe* o) { if (is_const) { if (idx >= p.consts.size()) return false; *o = to_fe(p.consts[idx]); } else { if (idx >= p.n_regs) return false; *o = rf[idx]; } return true; };
+      if (!load(ins.y, ins.x & F_A_CONST, &A)) return -1;
+      if (op == OP_OUT) { if (ins.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, A.l, 32); continue; }
+      if (op_has_b(op) && !load(ins.z, ins.x & F_B_CONST, &B)) return -1;
+      if (op == OP_TERN && !load(ins.w, ins.x & F_C_CONST, &C)) return -1;
+      R = alu_exec(op, A, B, C, st);
+    }
+    if (dst != NO_DST) { if (dst >= p.n_regs) return -1; rf[dst] = R; }
+    if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
+  }
+  return st;
+}
+// inputs JSON -> I x 32 B buffer; returns 0 ok / 1 error (message in err)
+int sim_inputs(SimGraph* s, const char* json, uint8_t* buf, char* err, size_t errlen) {
+  try {
+    InputList in = deserialize_inputs(json, strlen(json));
+    std::vector<U256> b = build_inputs_buffer(s->g, in);
+    memcpy(buf, b.data(), b.size() * 32);
+    return 0;
+  } catch (const std::exception& e) { if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; } return 1; }
+}
+// re-serialise the parsed graph (codec round trip); returns the size, copies up to cap bytes
+size_t sim_reserialize(SimGraph* s, uint8_t* out, size_t cap) {
+  std::vector<uint8_t> v = serialize_witnesscalc_graph(s->g);
+  if (out && cap >= v.size()) memcpy(out, v.data(), v.size());
+  return v.size();
+}
+void sim_wtns_header(uint32_t n, uint8_t* dst) { wtns_write_header(dst, n); }
+}

@@ -1,0 +1,94 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the Python oracle and the
+committed golden .wtns files.  Bit-exact comparison everywhere (integer arithmetic)."""
+import importlib
+import random
+
+import numpy as np
+import pytest
+
+from tests import util
+from tests.util import po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cwc():
+    mod = importlib.import_module("circom-witnesscalc_b200")
+    assert mod.device_count() >= 1, "no CUDA device visible"
+    return mod
+
+
+GOLDEN = ["circuit1", "circuit2", "circuit3", "circuit4", "circuit5_poseidon", "circuit6_num2bits",
+          "circuit7_poseidon4", "poseidon2", "circuit11_key_expansion", "circuit8_sha256_512", "circuit9_authV2"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_wtns_drop_in(cwc, name):
+    """gw_calc_witness(inputs.json, graph.bin) == committed .wtns, byte for byte (test_circuits.sh:81 `cmp`)."""
+    got = cwc.calc_witness_wtns(util.golden_inputs(name), util.golden_graph(name))
+    assert got == util.golden_wtns(name)
+
+
+def test_random_graphs_all_ops(cwc):
+    rnd = random.Random(1234)
+    for t in range(12):
+        nodes, wit, imap = util.random_graph(rnd, n_ops=400)
+        g = cwc.Graph(po.serialize_graph(nodes, wit, imap))
+        B = 96 + t            # not a multiple of the CTA size: ragged last tile
+        rows = [[1] + [util.random_value(rnd) if rnd.random() < 0.8 else rnd.randrange(1 << 256) for _ in range(6)]
+                for _ in range(B)]
+        inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(B, 7, 32)
+        out = g.calc_witness_batch(inp)
+        for b in range(0, B, 7):
+            want = po.evaluate(nodes, rows[b], wit, "circom")
+            assert util.unpack_u256(out[b].tobytes()) == want, (t, b)
+
+
+def test_reference_undefined_flags(cwc):
+    """cases where the reference panics get the circom value and a per-set flag"""
+    nodes = [(po.K_INPUT, 0), (po.K_INPUT, 1), (po.K_INPUT, 2),
+             (po.K_DUO, po.DUO["Shl"], 1, 2), (po.K_DUO, po.DUO["Bxor"], 1, 2), (po.K_DUO, po.DUO["Pow"], 1, 2)]
+    g = cwc.Graph(po.serialize_graph(nodes, [0, 3, 4, 5], {"a": (1, 1), "b": (2, 1)}))
+    M = po.M
+    rows = [[1, 5, 3], [1, M - 1, 200], [1, M, 0], [1, (1 << 253), (1 << 253) ^ M]]
+    inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(4, 3, 32)
+    out, flags = g.calc_witness_batch(inp, want_flags=True)
+    for b, r in enumerate(rows):
+        assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, r, [0, 3, 4, 5], "circom")
+    assert flags[0] == 4 and flags[1] & 1 and flags[3] & 2
+
+
+def test_batch_matches_single_and_properties(cwc):
+    """batch of random inputs on Poseidon(2): every row equals the oracle; duplicated rows give
+    duplicated witnesses (purity); size-independent check on a larger batch via row sampling."""
+    name = "poseidon2"
+    data = util.golden_graph(name)
+    nodes, wit, imap = po.deserialize_graph(data)
+    g = cwc.Graph(data)
+    rng = np.random.default_rng(7)
+    B = 4096 + 37
+    vals = util.random_field_batch(rng, (B, g.n_inputs))
+    vals[:, 0, :] = 0
+    vals[:, 0, 0] = 1
+    vals[B - 1] = vals[0]
+    inp = vals.view(np.uint8).reshape(B, g.n_inputs, 32)
+    out = g.calc_witness_batch(inp)
+    assert (out[B - 1] == out[0]).all()
+    for b in [0, 1, 31, 32, 127, 128, 4095, 4096, B - 2]:
+        row = util.limbs_to_ints(vals[b])
+        assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, row, wit)
+
+
+def test_bad_inputs_return_errors(cwc):
+    data = util.golden_graph("circuit1")
+    with pytest.raises(cwc.WitnessCalcError):
+        cwc.calc_witness_wtns('{"a": "1", "zzz": "2"}', data)          # unknown key (reference: panic)
+    with pytest.raises(cwc.WitnessCalcError):
+        cwc.calc_witness_wtns('{"a": ["1", "2"]}', data)                # wrong length (reference: panic)
+    with pytest.raises(cwc.WitnessCalcError):
+        cwc.calc_witness_wtns('{"a": -1}', data)                        # lib.rs:211-214
+    with pytest.raises(cwc.WitnessCalcError):
+        cwc.calc_witness_wtns('{"a": "1"', data)                        # invalid JSON (reference: panic)
+    with pytest.raises(cwc.WitnessCalcError):
+        cwc.calc_witness_wtns('{"a": "1"}', b"not a graph file at all....")

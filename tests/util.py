@@ -1,0 +1,200 @@
+"""Shared helpers of the test-suite: golden fixtures, random graphs, ctypes bindings of the
+test-only host libraries (tests/csrc) and of the product library."""
+import ctypes
+import json
+import lzma
+import os
+import random
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BUILD = os.path.join(ROOT, "tests", "_build")
+CSRC = os.path.join(ROOT, "circom-witnesscalc_b200", "csrc")
+
+from oracle import pyoracle as po  # noqa: E402
+
+M = po.M
+
+
+# ---- fixtures -------------------------------------------------------------------------------------
+def manifest():
+    return json.load(open(os.path.join(GOLDEN, "manifest.json")))
+
+
+def golden_graph(name) -> bytes:
+    return lzma.decompress(open(os.path.join(GOLDEN, "graphs", name + ".bin.xz"), "rb").read())
+
+
+def golden_inputs(name) -> str:
+    return open(os.path.join(GOLDEN, "inputs", name + "_inputs.json")).read()
+
+
+def golden_wtns(name) -> bytes:
+    return lzma.decompress(open(os.path.join(GOLDEN, "wtns", name + ".wtns.xz"), "rb").read())
+
+
+# ---- packing ----------------------------------------------------------------------------------------
+def pack_u256(vals) -> bytes:
+    return b"".join(int(v).to_bytes(32, "little") for v in vals)
+
+
+def unpack_u256(buf) -> list:
+    buf = bytes(buf)
+    return [int.from_bytes(buf[i:i + 32], "little") for i in range(0, len(buf), 32)]
+
+
+def random_field_batch(rng: np.random.Generator, shape):
+    """uniform values in [0, M) as a uint64 array [..., 4] (little-endian limbs) by rejection sampling"""
+    n = int(np.prod(shape))
+    out = np.empty((n, 4), dtype=np.uint64)
+    top = M >> 192
+    filled = 0
+    while filled < n:
+        cand = rng.integers(0, 1 << 64, size=(2 * (n - filled) + 16, 4), dtype=np.uint64)
+        cand[:, 3] &= np.uint64((1 << 62) - 1)      # 254 bits
+        hi = cand[:, 3]
+        ok = hi < np.uint64(top)                      # strictly below the top limb of M: always < M
+        eq = hi == np.uint64(top)
+        if eq.any():
+            for i in np.nonzero(eq)[0]:
+                v = sum(int(cand[i, k]) << (64 * k) for k in range(4))
+                ok[i] = v < M
+        good = cand[ok]
+        take = min(len(good), n - filled)
+        out[filled:filled + take] = good[:take]
+        filled += take
+    return out.reshape(tuple(shape) + (4,))
+
+
+def limbs_to_ints(a):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1, 4)
+    return [int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192) for r in a]
+
+
+# ---- random graphs ----------------------------------------------------------------------------------
+EDGE = [0, 1, 2, 3, M - 1, M - 2, M >> 1, (M >> 1) + 1, (M >> 1) - 1, 1 << 253, (1 << 253) - 1, (1 << 254) - 1 - M,
+        0xFFFFFFFF, 1 << 32, (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 253, 254, 255, 256, 31, 32, 33, 64]
+
+
+def random_value(rnd: random.Random):
+    r = rnd.random()
+    if r < 0.3:
+        return rnd.choice(EDGE) % M
+    if r < 0.45:
+        return rnd.randrange(1 << rnd.randrange(1, 254))
+    return rnd.randrange(M)
+
+
+def random_graph(rnd: random.Random, n_inputs=6, n_ops=200, ops=None, n_consts=12):
+    """A graph in the layout build-circuit produces: Input run first, then constants and ops.
+    Returns (nodes, witness_signals, input_map)."""
+    duo = ops if ops is not None else list(range(20))
+    nodes = [(po.K_INPUT, i) for i in range(n_inputs + 1)]
+    for _ in range(n_consts):
+        nodes.append((po.K_CONST, random_value(rnd)))
+    small = [len(nodes) + i for i in range(6)]
+    for v in (0, 1, 5, 31, 32, 200):
+        nodes.append((po.K_CONST, v))
+    for _ in range(n_ops):
+        n = len(nodes)
+        pick = lambda: rnd.randrange(n) if rnd.random() < 0.7 else rnd.randrange(max(0, n - 8), n)
+        r = rnd.random()
+        if r < 0.08:
+            nodes.append((po.K_UNO, 0, pick()))
+        elif r < 0.16:
+            nodes.append((po.K_TRES, 0, pick(), pick(), pick()))
+        else:
+            op = rnd.choice(duo)
+            a, b = pick(), pick()
+            if op in (15, 16) and rnd.random() < 0.7:
+                b = rnd.choice(small)
+            if op == 0 and rnd.random() < 0.2:
+                b = a
+            nodes.append((po.K_DUO, op, a, b))
+    n = len(nodes)
+    wit = [0] + [rnd.randrange(n) for _ in range(min(n, 40))] + list(range(n - 10, n))
+    return nodes, wit, {"x": (1, n_inputs)}
+
+
+# ---- test-only host libraries -------------------------------------------------------------------------
+def _build(name, sources, extra=()):
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, name)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [s for s in sources]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", out,
+                               *sources, *extra])
+    return out
+
+
+_libs = {}
+
+
+def field_host_lib():
+    if "field" not in _libs:
+        _libs["field"] = ctypes.CDLL(_build("libfieldhost.so", [os.path.join(ROOT, "tests/csrc/field_host_api.cpp")]))
+    return _libs["field"]
+
+
+def sim_lib():
+    if "sim" not in _libs:
+        src = [os.path.join(ROOT, "tests/csrc/plan_host_sim.cpp")] + [os.path.join(CSRC, f) for f in
+                                                                      ("graph.cpp", "plan.cpp", "inputs.cpp", "wtns.cpp")]
+        L = ctypes.CDLL(_build("libgwsim.so", src))
+        L.sim_load.restype = ctypes.c_void_p
+        L.sim_load.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t]
+        L.sim_free.argtypes = [ctypes.c_void_p]
+        L.sim_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        L.sim_eval.restype = ctypes.c_int64
+        L.sim_eval.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+        L.sim_inputs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.sim_reserialize.restype = ctypes.c_size_t
+        L.sim_reserialize.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        _libs["sim"] = L
+    return _libs["sim"]
+
+
+class SimGraph:
+    """ctypes wrapper over tests/csrc/plan_host_sim.cpp"""
+
+    def __init__(self, data: bytes, n_regs=24):
+        self.L = sim_lib()
+        err = ctypes.create_string_buffer(512)
+        self.h = self.L.sim_load(data, len(data), n_regs, err, 512)
+        if not self.h:
+            raise ValueError(err.value.decode())
+        info = (ctypes.c_uint64 * 12)()
+        self.L.sim_info(self.h, info)
+        keys = ["n_nodes", "I", "W", "n_instrs", "n_regs", "n_spill", "spill_ld", "spill_st", "max_live", "n_consts",
+                "live_ops", "graph_ops"]
+        self.info = dict(zip(keys, [int(x) for x in info]))
+
+    def eval(self, inputs):
+        """inputs: list of I ints -> (witness list, status bits)"""
+        assert len(inputs) == self.info["I"]
+        out = ctypes.create_string_buffer(32 * self.info["W"])
+        st = self.L.sim_eval(self.h, pack_u256(inputs), out)
+        assert st >= 0, "malformed plan"
+        return unpack_u256(out.raw), int(st)
+
+    def inputs_from_json(self, js: str):
+        buf = ctypes.create_string_buffer(32 * self.info["I"])
+        err = ctypes.create_string_buffer(512)
+        r = self.L.sim_inputs(self.h, js.encode(), buf, err, 512)
+        if r:
+            raise ValueError(err.value.decode())
+        return unpack_u256(buf.raw)
+
+    def reserialize(self) -> bytes:
+        n = self.L.sim_reserialize(self.h, None, 0)
+        buf = ctypes.create_string_buffer(n)
+        self.L.sim_reserialize(self.h, buf, n)
+        return buf.raw
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.sim_free(self.h)
+            self.h = None
