@@ -4,6 +4,7 @@
 // plan simulator used in the CPU unit tests (tests/csrc/plan_host_sim.cpp).
 #pragma once
 #include "field.cuh"
+#include "inv_safegcd.cuh"
 #include "isa.h"
 
 namespace gw {
@@ -12,7 +13,7 @@ namespace gw {
 GW_HD fe alu_exec(uint32_t op, const fe& A, fe Bv, const fe& C, uint32_t& st) {
   fe R;
   if (op == OP_SQR) { Bv = A; op = OP_MUL; }
-  if (op == OP_DIV) { Bv = fe_inv_fermat(Bv); op = OP_MUL; }                 // graph.rs:109 (b == 0 -> 0)
+  if (op == OP_DIV) { Bv = fe_inv(Bv); op = OP_MUL; }                        // graph.rs:109 (b == 0 -> 0)
   else if (op == OP_POW) { R = fe_pow(A, Bv); st |= ST_POW; }
   switch (op) {
     case OP_MUL: R = fe_mul(A, Bv); break;                                   // graph.rs:105

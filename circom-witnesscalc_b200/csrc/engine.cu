@@ -42,6 +42,16 @@ __device__ __forceinline__ fe fe_from(uint4 lo, uint4 hi) {
 __device__ __forceinline__ uint4 fe_lo(const fe& a) { return make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]); }
 __device__ __forceinline__ uint4 fe_hi(const fe& a) { return make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]); }
 
+__device__ __forceinline__ uint4 shfl4(const uint4& v, int src) {
+  uint4 r;
+  r.x = __shfl_sync(0xffffffffu, v.x, src);
+  r.y = __shfl_sync(0xffffffffu, v.y, src);
+  r.z = __shfl_sync(0xffffffffu, v.z, src);
+  r.w = __shfl_sync(0xffffffffu, v.w, src);
+  return r;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int T>
 __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
   extern __shared__ uint4 rf[];
@@ -53,6 +63,7 @@ __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
   auto rf_load = [&](uint32_t r) { return fe_from(rf[(r * 2) * T + tid], rf[(r * 2 + 1) * T + tid]); };
   auto rf_store = [&](uint32_t r, const fe& v) { rf[(r * 2) * T + tid] = fe_lo(v); rf[(r * 2 + 1) * T + tid] = fe_hi(v); };
   auto const_load = [&](uint32_t c) { return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1)); };
+  auto operand = [&](uint32_t is_const, uint32_t idx) { return is_const ? const_load(idx) : rf_load(idx); };
 
   for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const unsigned long long w = (unsigned long long)tile * T + tid;
@@ -61,51 +72,91 @@ __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
     const uint4* in = p.inputs + wl * p.I * 2;
     uint4* out = p.out + wl * p.W * 2;
     uint32_t st = 0;
+    auto out_store = [&](uint32_t j, const fe& v) { if (active) { out[2 * (size_t)j] = fe_lo(v); out[2 * (size_t)j + 1] = fe_hi(v); } };
 
-    uint4 nxt = __ldg(p.code + min((uint32_t)lane, n - 1));
-    for (uint32_t base = 0; base < n; base += 32) {
-      const uint4 cur = nxt;
-      if (base + 32 < n) nxt = __ldg(p.code + min(base + 32 + lane, n - 1));
-      const int cnt = min(32u, n - base);
-      for (int k = 0; k < cnt; k++) {
-        uint4 ins;
-        ins.x = __shfl_sync(0xffffffffu, cur.x, k);
-        ins.y = __shfl_sync(0xffffffffu, cur.y, k);
-        ins.z = __shfl_sync(0xffffffffu, cur.z, k);
-        ins.w = __shfl_sync(0xffffffffu, cur.w, k);
-        uint32_t op = ins.x & 0xFFu;
-        const uint32_t dst = ins.x >> 16;
-        fe A, Bv, R;
-        Bv = fe_zero();
+    // Instruction stream: blk holds instructions [base, base+32) one per lane, nblk the following 32.
+    // q0/q1/q2 are the next three instructions, already broadcast: the shuffles (and the L1 prefetch of
+    // constant operands) for an instruction are issued two instructions before it executes, so their
+    // latency hides behind the arithmetic of the instructions in front of it.
+    uint32_t base = 0;
+    uint4 blk = __ldg(p.code + min((uint32_t)lane, n - 1));
+    uint4 nblk = __ldg(p.code + min(32u + lane, n - 1));
+    auto fetch = [&](uint32_t pcx) {
+      uint4 r = shfl4((pcx - base) < 32u ? blk : nblk, (int)(pcx & 31u));
+      if (r.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)r.y);
+      if (r.x & F_B_CONST) prefetch_l1(p.consts + 2 * (size_t)r.z);
+      return r;
+    };
+    uint4 q0 = fetch(0), q1 = fetch(min(1u, n - 1)), q2 = fetch(min(2u, n - 1));
+    uint32_t pc = 0;
+    while (pc < n) {
+      const uint4 ins = q0;
+      const uint32_t op = ins.x & 0xFFu;
+      const uint32_t dst = ins.x >> 16;
+      uint32_t adv = 1;
 
-        if (op == OP_SPILL_ST) {
-          fe v = rf_load(ins.y);
-          p.spill[((size_t)ins.z * 2) * p.spill_threads + gthread] = fe_lo(v);
-          p.spill[((size_t)ins.z * 2 + 1) * p.spill_threads + gthread] = fe_hi(v);
-          continue;
-        }
-        if (op == OP_SPILL_LD) {
-          R = fe_from(p.spill[((size_t)ins.y * 2) * p.spill_threads + gthread],
-                      p.spill[((size_t)ins.y * 2 + 1) * p.spill_threads + gthread]);
-          rf_store(dst, R);
-          continue;
-        }
+      if (ins.x & F_PAIR) {
+        // two independent multiplications issued together: all four operands are read before either
+        // result is written, and the two products give the scheduler twice the independent work
+        const uint4 in2 = q1;
+        adv = 2;
+        fe A1 = operand(ins.x & F_A_CONST, ins.y);
+        fe B1 = (op == OP_SQR) ? A1 : operand(ins.x & F_B_CONST, ins.z);
+        fe A2 = operand(in2.x & F_A_CONST, in2.y);
+        fe B2 = ((in2.x & 0xFFu) == OP_SQR) ? A2 : operand(in2.x & F_B_CONST, in2.z);
+        fe R1, R2;
+        fe_mul2(A1, B1, A2, B2, R1, R2);
+        const uint32_t dst2 = in2.x >> 16;
+        if (dst != NO_DST) rf_store(dst, R1);
+        if (dst2 != NO_DST) rf_store(dst2, R2);
+        if (ins.x & F_OUT) out_store(ins.w, R1);
+        if (in2.x & F_OUT) out_store(in2.w, R2);
+      } else if (op == OP_ADD || op == OP_SUB) {
+        fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
+        fe R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);
+        if (dst != NO_DST) rf_store(dst, R);
+        if (ins.x & F_OUT) out_store(ins.w, R);
+      } else if (op == OP_MUL || op == OP_SQR) {
+        fe A = operand(ins.x & F_A_CONST, ins.y);
+        fe Bv = (op == OP_SQR) ? A : operand(ins.x & F_B_CONST, ins.z);
+        fe R = fe_mul(A, Bv);
+        if (dst != NO_DST) rf_store(dst, R);
+        if (ins.x & F_OUT) out_store(ins.w, R);
+      } else if (op == OP_SPILL_ST) {
+        fe v = rf_load(ins.y);
+        p.spill[((size_t)ins.z * 2) * p.spill_threads + gthread] = fe_lo(v);
+        p.spill[((size_t)ins.z * 2 + 1) * p.spill_threads + gthread] = fe_hi(v);
+      } else if (op == OP_SPILL_LD) {
+        rf_store(dst, fe_from(p.spill[((size_t)ins.y * 2) * p.spill_threads + gthread],
+                              p.spill[((size_t)ins.y * 2 + 1) * p.spill_threads + gthread]));
+      } else if (op == OP_OUT) {
+        out_store(ins.w, operand(ins.x & F_A_CONST, ins.y));
+      } else if (op != OP_NOP) {
+        // everything else (rare ops, out-of-line helpers): kept apart so that the hot paths above never
+        // have their operands forced into local memory by the calls in here
+        fe R;
         if (op == OP_INPUT) {
           R = fe_reduce256(fe_from(__ldg(in + 2 * (size_t)ins.y), __ldg(in + 2 * (size_t)ins.y + 1)));
         } else {
-          A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
-          if (op == OP_OUT) {
-            if (active) { out[2 * (size_t)ins.w] = fe_lo(A); out[2 * (size_t)ins.w + 1] = fe_hi(A); }
-            continue;
-          }
-          fe C;
-          if (op_has_b(op)) Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z);
-          if (op == OP_TERN) C = (ins.x & F_C_CONST) ? const_load(ins.w) : rf_load(ins.w);
+          fe A = operand(ins.x & F_A_CONST, ins.y), Bv = fe_zero(), C = fe_zero();
+          if (op_has_b(op)) Bv = operand(ins.x & F_B_CONST, ins.z);
+          if (op == OP_TERN) C = operand(ins.x & F_C_CONST, ins.w);
           R = alu_exec(op, A, Bv, C, st);
         }
         if (dst != NO_DST) rf_store(dst, R);
-        if ((ins.x & F_OUT) && active) { out[2 * (size_t)ins.w] = fe_lo(R); out[2 * (size_t)ins.w + 1] = fe_hi(R); }
+        if (ins.x & F_OUT) out_store(ins.w, R);
       }
+
+      // advance the instruction queue by adv (1 or 2) and refill it
+      const uint32_t npc = pc + adv;
+      if ((npc - base) >= 32u && npc < n) {            // entered the next block of 32
+        base += 32;
+        blk = nblk;
+        nblk = __ldg(p.code + min(base + 32u + lane, n - 1));
+      }
+      if (adv == 1) { q0 = q1; q1 = q2; q2 = fetch(min(npc + 2, n - 1)); }
+      else { q0 = q2; q1 = fetch(min(npc + 1, n - 1)); q2 = fetch(min(npc + 2, n - 1)); }
+      pc = npc;
     }
     if (p.status != nullptr && active) p.status[w] = st;
   }
@@ -206,6 +257,8 @@ Engine::Engine(const uint8_t* graph_data, size_t len) {
   threads = env_int("GW_THREADS", 128);
   if (threads != 64 && threads != 128 && threads != 256) throw Error("GW_THREADS must be 64, 128 or 256");
   PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", 24);
+  opt.pair_muls = env_int("GW_PAIR", 1) != 0;
+  opt.pair_window = (uint32_t)env_int("GW_PAIR_WINDOW", 24);
   plan = compile_plan(graph, opt);
 }
 
@@ -286,10 +339,16 @@ void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* w
   CUDA_CHECK(cudaSetDevice(device));
   std::lock_guard<std::mutex> lk(d->mu);
   const size_t in_b = (size_t)plan.n_inputs * 32, out_b = (size_t)plan.n_witness * 32;
-  // chunk: enough witnesses to fill the chip a few times, bounded by a memory budget per buffer
-  size_t budget = (size_t)env_int("GW_CHUNK_MB", 4096) << 20;
-  size_t chunk = std::max<size_t>(threads, std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 4 * d->spill_threads));
-  chunk = std::min(chunk, std::max<size_t>(B, 1));
+  // chunk size: bounded by a device-memory budget per staging buffer (two of them), at most two full
+  // waves of resident threads, and small enough to give the copy/compute pipeline >= 4 stages when the
+  // batch is large.  GW_CHUNK_MB overrides the budget.
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = (size_t)env_int("GW_CHUNK_MB", 24576) << 20;
+  budget = std::min(budget, (free_b + 2 * d->chunk * (in_b + out_b)) / 5);
+  size_t chunk = std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 2 * d->spill_threads);
+  if (B >= 4 * 2048) chunk = std::min(chunk, (B + 3) / 4);
+  chunk = std::max<size_t>(std::min(chunk, B), 1);
   if (chunk > d->chunk) {
     for (int i = 0; i < 2; i++) {
       cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]);

@@ -263,6 +263,72 @@ GW_HD void u256_mul_lo(uint32_t* out, const uint32_t* a, const uint32_t* b) {
 #endif
 }
 
+// Upper part of a*b for Barrett's quotient estimate: only partial products a_j*b_i with i+j >= 6
+// are accumulated (43 of the 64), so out[8..15] is below the true value by less than 2^-60 of one
+// unit of out[8]; out[0..5] are not produced (left 0), out[6..7] are partial.
+GW_HD void u256_mul_hi_trunc(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t e[18], o[18];
+#pragma unroll
+  for (int i = 0; i < 18; i++) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t bi = b[i];
+    const int p = i & 1;
+    {
+      // same-parity limbs: first j (>= p, parity p) with i + j >= 6
+      int j0 = p;
+      while (i + j0 < 6) j0 += 2;
+      if (j0 < 8) {
+        e[i + j0] = ptx_mad_lo_cc(a[j0], bi, e[i + j0]);
+        e[i + j0 + 1] = ptx_madc_hi_cc(a[j0], bi, e[i + j0 + 1]);
+#pragma unroll
+        for (int j = j0 + 2; j < 8; j += 2) {
+          e[i + j] = ptx_madc_lo_cc(a[j], bi, e[i + j]);
+          e[i + j + 1] = ptx_madc_hi_cc(a[j], bi, e[i + j + 1]);
+        }
+        e[i + p + 8] = ptx_addc(e[i + p + 8], 0);
+      }
+    }
+    {
+      const int q = 1 - p;
+      int j0 = q;
+      while (i + j0 < 6) j0 += 2;
+      if (j0 < 8) {
+        o[i + j0 - 1] = ptx_mad_lo_cc(a[j0], bi, o[i + j0 - 1]);
+        o[i + j0] = ptx_madc_hi_cc(a[j0], bi, o[i + j0]);
+#pragma unroll
+        for (int j = j0 + 2; j < 8; j += 2) {
+          o[i + j - 1] = ptx_madc_lo_cc(a[j], bi, o[i + j - 1]);
+          o[i + j] = ptx_madc_hi_cc(a[j], bi, o[i + j]);
+        }
+        o[i + q + 7] = ptx_addc(o[i + q + 7], 0);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) out[k] = 0;
+  out[6] = ptx_add_cc(e[6], o[5]);
+#pragma unroll
+  for (int k = 7; k < 15; k++) out[k] = ptx_addc_cc(e[k], o[k - 1]);
+  out[15] = ptx_addc(e[15], o[14]);
+#else
+  uint32_t t[17];
+  for (int i = 0; i < 17; i++) t[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    int jf = 8;
+    for (int j = 0; j < 8; j++) {
+      if (i + j < 6) continue;
+      if (jf == 8) jf = j;
+      c += (uint64_t)a[j] * b[i] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32;
+    }
+    if (jf < 8) { c += t[i + 8]; t[i + 8] = (uint32_t)c; if (i + 9 < 17) t[i + 9] += (uint32_t)(c >> 32); }
+  }
+  for (int i = 0; i < 16; i++) out[i] = t[i];
+#endif
+}
+
 GW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {   // low 32 bits of (hi:lo) >> s, 0 <= s < 32
 #if defined(__CUDA_ARCH__)
   return __funnelshift_r(lo, hi, s);
@@ -276,13 +342,16 @@ GW_HD fe fe_barrett(const uint32_t* P) {
   uint32_t q1[8], mu[8], Q[16], qh[8], m[8], T[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) { q1[k] = funnel_r(P[7 + k], P[8 + k], 28); mu[k] = MU_L(k); m[k] = MOD_L(k); }  // P >> 252
-  u256_mul_wide(Q, q1, mu);
+  u256_mul_hi_trunc(Q, q1, mu);
 #pragma unroll
   for (int k = 0; k < 7; k++) qh[k] = funnel_r(Q[8 + k], Q[9 + k], 1);                                         // Q >> 257
   qh[7] = Q[15] >> 1;
   u256_mul_lo(T, qh, m);
-  fe r; u256_sub(r.l, P, T);      // 0 <= P - qh*M < 3M < 2^256, so the low 256 bits are exact
-  fe_cond_sub_m(r); fe_cond_sub_m(r);
+  // Quotient estimate: qh = floor(floor(P/2^252) * mu / 2^257) with mu = floor(2^509/M).  With
+  // x = P/M:  qh > x - 2^252/M - P/(2^509) - (truncation < 2^-50) - 1 > x - 0.33 - 0.29 - 1, and qh <= x,
+  // so floor(x) - 1 <= qh <= floor(x):  0 <= P - qh*M < 2M and ONE conditional subtraction finishes.
+  fe r; u256_sub(r.l, P, T);      // P - qh*M < 2M < 2^256, so the low 256 bits are exact
+  fe_cond_sub_m(r);
   return r;
 }
 
@@ -292,6 +361,14 @@ GW_HD fe fe_mul(const fe& a, const fe& b) {          // graph.rs:105
   return fe_barrett(P);
 }
 GW_HD fe fe_sqr(const fe& a) { return fe_mul(a, a); }
+// two independent products in one basic block (instruction-level parallelism for the scheduler)
+GW_HD void fe_mul2(const fe& a1, const fe& b1, const fe& a2, const fe& b2, fe& r1, fe& r2) {
+  uint32_t P1[16], P2[16];
+  u256_mul_wide(P1, a1.l, b1.l);
+  u256_mul_wide(P2, a2.l, b2.l);
+  r1 = fe_barrett(P1);
+  r2 = fe_barrett(P2);
+}
 // out-of-line copy for the long chains (inversion, pow): keeps the interpreter's code size down
 GW_HD_NOINLINE fe fe_mul_ni(const fe& a, const fe& b) { return fe_mul(a, b); }
 

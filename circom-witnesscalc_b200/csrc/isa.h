@@ -32,6 +32,8 @@ enum Flags : uint32_t {
   F_B_CONST = 1u << 9,
   F_C_CONST = 1u << 10,
   F_OUT = 1u << 11,      // also store the result to witness position .w
+  F_PAIR = 1u << 12,     // MUL/SQR only: the next slot is an independent MUL/SQR issued together (both
+                         // read their operands before either writes); never straddles a 32-slot block
 };
 
 static const uint32_t NO_DST = 0xFFFFu;

@@ -110,7 +110,6 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt) {
     for (uint32_t j = 0; j < g.witness_signals.size(); j++) out_list[fill[g.witness_signals[j]]++] = j;
   }
 
-  // use lists of non-constant values, in instruction order (CSR)
   auto operands = [&](const Node& nd, uint32_t* ops) {
     int n = 0;
     if (nd.kind >= N_UNO) ops[n++] = nd.a;
@@ -118,9 +117,42 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt) {
     if (nd.kind == N_TRES) ops[n++] = nd.c;
     return n;
   };
+
+  // schedule: file order (any topological order is valid, graph.rs:343-356), except that an
+  // independent multiplication found within a small window is pulled up next to a multiplication so
+  // that the two can be issued as one pair (instruction-level parallelism inside a thread).
+  std::vector<uint32_t> order; order.reserve(N);
+  std::vector<int32_t> partner(N, -1);       // for the first node of a pair: the second one
+  {
+    std::vector<uint8_t> scheduled(N, 0);
+    auto is_mul = [&](size_t i) { const Node& nd = g.nodes[i]; return needed[i] && nd.kind == N_DUO && nd.op == OP_MUL && const_of[i] < 0; };
+    auto ready = [&](size_t j, size_t first) {
+      const Node& nd = g.nodes[j];
+      for (uint32_t x : {nd.a, nd.b}) {
+        if (x == first) return false;
+        if (const_of[x] < 0 && !scheduled[x]) return false;
+      }
+      return true;
+    };
+    for (size_t i = 0; i < N; i++) {
+      if (!needed[i] || scheduled[i]) continue;
+      scheduled[i] = 1; order.push_back((uint32_t)i);
+      if (!opt.pair_muls || !is_mul(i)) continue;
+      size_t end = std::min(N, i + 1 + (size_t)opt.pair_window);
+      for (size_t j = i + 1; j < end; j++) {
+        if (scheduled[j] || !is_mul(j) || !ready(j, i)) continue;
+        scheduled[j] = 1; order.push_back((uint32_t)j); partner[i] = (int32_t)j;
+        plan.stats.mul_pairs++;
+        break;
+      }
+    }
+  }
+  std::vector<uint32_t> pos(N, 0);
+  for (size_t p = 0; p < order.size(); p++) pos[order[p]] = (uint32_t)p;
+
+  // use lists of non-constant values as schedule positions of their consumers (CSR, ascending)
   std::vector<uint32_t> use_start(N + 1, 0);
-  for (size_t i = 0; i < N; i++) {
-    if (!needed[i]) continue;
+  for (uint32_t i : order) {
     uint32_t ops[3]; int n = operands(g.nodes[i], ops);
     for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) use_start[ops[k] + 1]++;
   }
@@ -128,10 +160,9 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt) {
   std::vector<uint32_t> use_list(use_start[N]);
   {
     std::vector<uint32_t> fill(use_start.begin(), use_start.end() - 1);
-    for (size_t i = 0; i < N; i++) {
-      if (!needed[i]) continue;
+    for (uint32_t i : order) {
       uint32_t ops[3]; int n = operands(g.nodes[i], ops);
-      for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) use_list[fill[ops[k]]++] = (uint32_t)i;
+      for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) use_list[fill[ops[k]]++] = pos[i];
     }
   }
 
@@ -139,23 +170,11 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt) {
   plan.code.reserve(N + N / 4);
   uint32_t live = 0;
 
-  for (size_t i = 0; i < N; i++) {
-    if (!needed[i]) continue;
+  struct Enc { uint32_t op, flags, dst, a, b, w; bool need_reg, has_uses, out_inline; };
+  // phase 1 of one node: operands resident (registers in `pinned` stay put); returns encodings of operands
+  auto load_operands = [&](uint32_t i, uint32_t* enc, uint32_t& flags, uint32_t* pinned, int& n_pin) {
     const Node& nd = g.nodes[i];
-    const uint32_t n_out = out_start[i + 1] - out_start[i];
-    const uint32_t* outs = &out_list[out_start[i]];
-
-    if (const_of[i] >= 0) {                 // constants never occupy a register
-      for (uint32_t k = 0; k < n_out; k++) { al.emit(make_instr(OP_OUT, F_A_CONST, NO_DST, (uint32_t)const_of[i], 0, outs[k])); plan.stats.outs++; }
-      continue;
-    }
-    if (nd.kind == N_CONST) continue;
-
     uint32_t ops[3]; int n_ops = operands(nd, ops);
-    uint32_t enc[3] = {0, 0, 0}; uint32_t flags = 0;
-    uint32_t pinned[3]; int n_pin = 0;
-    if (nd.kind >= N_UNO) plan.stats.live_ops++;
-    // make the operands resident
     for (int k = 0; k < n_ops; k++) {
       uint32_t x = ops[k];
       if (const_of[x] >= 0) { enc[k] = (uint32_t)const_of[x]; flags |= (F_A_CONST << k); continue; }
@@ -169,34 +188,79 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt) {
       enc[k] = (uint32_t)al.reg_of[x];
       pinned[n_pin++] = enc[k];
     }
-    // consume the uses; operands that die here give their register back before dst is chosen
+  };
+  // phase 2: consume the uses up to schedule position `upto`; operands that die give their register back
+  auto retire_operands = [&](uint32_t i, uint32_t upto) {
+    const Node& nd = g.nodes[i];
+    uint32_t ops[3]; int n_ops = operands(nd, ops);
     for (int k = 0; k < n_ops; k++) {
       uint32_t x = ops[k];
       if (const_of[x] >= 0) continue;
-      while (al.use_ptr[x] < use_start[x + 1] && use_list[al.use_ptr[x]] <= i) al.use_ptr[x]++;
+      while (al.use_ptr[x] < use_start[x + 1] && use_list[al.use_ptr[x]] <= upto) al.use_ptr[x]++;
     }
     for (int k = 0; k < n_ops; k++) {
       uint32_t x = ops[k];
       if (const_of[x] >= 0 || al.has_uses(x)) continue;
       if (al.reg_of[x] >= 0 || al.spill_of[x] >= 0) { al.release(x); live--; }
     }
-    const bool has_uses = al.has_uses((uint32_t)i);
-    const bool out_inline = n_out >= 1 && nd.kind != N_TRES;       // .w is operand c for TernCond
-    const bool need_reg = has_uses || n_out > (out_inline ? 1u : 0u);
-    uint32_t dst = NO_DST;
-    if (need_reg) { dst = al.alloc_reg(nullptr, 0); al.bind((uint32_t)i, dst); live++; plan.stats.max_live = std::max(plan.stats.max_live, live); }
-    if (!need_reg && n_out == 0) continue;   // cannot happen for needed nodes, kept for safety
+  };
 
-    uint32_t op;
-    if (nd.kind == N_INPUT) { op = OP_INPUT; enc[0] = nd.a; }
-    else if (nd.kind == N_UNO) op = OP_NEG + nd.op;
-    else if (nd.kind == N_TRES) op = OP_TERN;
-    else op = (nd.op == OP_MUL && nd.a == nd.b && !(flags & F_A_CONST)) ? (uint32_t)OP_SQR : nd.op;
-    uint32_t w = nd.kind == N_TRES ? enc[2] : (out_inline ? outs[0] : 0);
-    if (out_inline) { flags |= F_OUT; plan.stats.outs++; }
-    al.emit(make_instr(op, flags, dst, enc[0], enc[1], w));
-    for (uint32_t k = out_inline ? 1u : 0u; k < n_out; k++) { al.emit(make_instr(OP_OUT, 0, NO_DST, dst, 0, outs[k])); plan.stats.outs++; }
-    if (need_reg && !has_uses) { al.release((uint32_t)i); live--; }
+  for (size_t p = 0; p < order.size(); p++) {
+    const uint32_t i = order[p];
+    const Node& nd = g.nodes[i];
+    const uint32_t n_out = out_start[i + 1] - out_start[i];
+    const uint32_t* outs = &out_list[out_start[i]];
+
+    if (const_of[i] >= 0) {                 // constants never occupy a register
+      for (uint32_t k = 0; k < n_out; k++) { al.emit(make_instr(OP_OUT, F_A_CONST, NO_DST, (uint32_t)const_of[i], 0, outs[k])); plan.stats.outs++; }
+      continue;
+    }
+    if (nd.kind == N_CONST) continue;
+    if (nd.kind >= N_UNO) plan.stats.live_ops++;
+
+    const int n_nodes_here = partner[i] >= 0 ? 2 : 1;
+    uint32_t ids[2] = {i, partner[i] >= 0 ? (uint32_t)partner[i] : 0u};
+    if (n_nodes_here == 2) { plan.stats.live_ops++; p++; }       // the partner is order[p + 1]
+    uint32_t enc[2][3] = {{0, 0, 0}, {0, 0, 0}}; uint32_t flags[2] = {0, 0};
+    uint32_t pinned[8]; int n_pin = 0;
+    for (int s = 0; s < n_nodes_here; s++) load_operands(ids[s], enc[s], flags[s], pinned, n_pin);
+    for (int s = 0; s < n_nodes_here; s++) retire_operands(ids[s], pos[ids[n_nodes_here - 1]]);
+
+    uint32_t dsts[2] = {NO_DST, NO_DST}; bool need_reg[2], has_uses[2], out_inline[2];
+    uint32_t dpin[2]; int n_dpin = 0;
+    for (int s = 0; s < n_nodes_here; s++) {
+      const uint32_t id = ids[s];
+      const uint32_t no = out_start[id + 1] - out_start[id];
+      has_uses[s] = al.has_uses(id);
+      out_inline[s] = no >= 1 && g.nodes[id].kind != N_TRES;       // .w is operand c for TernCond
+      need_reg[s] = has_uses[s] || no > (out_inline[s] ? 1u : 0u);
+      if (need_reg[s]) {
+        dsts[s] = al.alloc_reg(dpin, n_dpin); al.bind(id, dsts[s]); dpin[n_dpin++] = dsts[s];
+        live++; plan.stats.max_live = std::max(plan.stats.max_live, live);
+      }
+    }
+    if (n_nodes_here == 2 && (plan.code.size() & 31) == 31) al.emit(make_instr(OP_NOP, 0, NO_DST, 0, 0, 0));
+    for (int s = 0; s < n_nodes_here; s++) {
+      const uint32_t id = ids[s];
+      const Node& n2 = g.nodes[id];
+      const uint32_t* o2 = &out_list[out_start[id]];
+      uint32_t op;
+      if (n2.kind == N_INPUT) { op = OP_INPUT; enc[s][0] = n2.a; }
+      else if (n2.kind == N_UNO) op = OP_NEG + n2.op;
+      else if (n2.kind == N_TRES) op = OP_TERN;
+      else op = (n2.op == OP_MUL && n2.a == n2.b && !(flags[s] & F_A_CONST)) ? (uint32_t)OP_SQR : n2.op;
+      uint32_t w = n2.kind == N_TRES ? enc[s][2] : (out_inline[s] ? o2[0] : 0);
+      if (out_inline[s]) { flags[s] |= F_OUT; plan.stats.outs++; }
+      if (n_nodes_here == 2 && s == 0) flags[s] |= F_PAIR;
+      al.emit(make_instr(op, flags[s], dsts[s], enc[s][0], enc[s][1], w));
+    }
+    for (int s = 0; s < n_nodes_here; s++) {
+      const uint32_t id = ids[s];
+      const uint32_t no = out_start[id + 1] - out_start[id];
+      const uint32_t* o2 = &out_list[out_start[id]];
+      for (uint32_t k = out_inline[s] ? 1u : 0u; k < no; k++) { al.emit(make_instr(OP_OUT, 0, NO_DST, dsts[s], 0, o2[k])); plan.stats.outs++; }
+      if (need_reg[s] && !has_uses[s]) { al.release(id); live--; }
+    }
   }
   plan.n_spill = al.n_spill;
   plan.stats.instrs = plan.code.size();

@@ -14,12 +14,14 @@ namespace gw {
 
 struct PlanOptions {
   uint32_t n_regs = 24;      // per-witness registers kept in shared memory
+  bool pair_muls = true;     // schedule independent multiplications next to each other and issue them as pairs
+  uint32_t pair_window = 24; // how far ahead (in nodes) a partner is searched
 };
 
 struct PlanStats {
   uint64_t graph_nodes = 0, graph_ops = 0;   // ops = Op + UnoOp + TresOp nodes of the file (node-ops/s metric)
   uint64_t live_ops = 0;                     // ops reachable from the witness
-  uint64_t instrs = 0, spill_st = 0, spill_ld = 0, outs = 0;
+  uint64_t instrs = 0, spill_st = 0, spill_ld = 0, outs = 0, mul_pairs = 0;
   uint64_t op_count[64] = {0};               // executed instructions by opcode
   uint32_t max_live = 0;                     // peak number of simultaneously live values
 };

@@ -26,3 +26,6 @@ void t_divrem(const uint32_t* a, const uint32_t* b, uint32_t* q, uint32_t* r) { 
 void t_pow(const uint32_t* a, const uint32_t* e, uint32_t* r) { st(r, fe_pow(ld(a), ld(e))); }
 void t_inv(const uint32_t* a, uint32_t* r) { st(r, fe_inv_fermat(ld(a))); }
 }
+#include "../../circom-witnesscalc_b200/csrc/inv_safegcd.cuh"
+extern "C" void t_inv_safegcd(const uint32_t* a, uint32_t* r) { st(r, gw::fe_inv(ld(a))); }
+extern "C" void t_mul_hi_trunc(const uint32_t* a, const uint32_t* b, uint32_t* r16) { gw::u256_mul_hi_trunc(r16, a, b); }

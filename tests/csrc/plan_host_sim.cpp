@@ -21,11 +21,15 @@ static fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 
 extern "C" {
 
+SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int pair, char* err, size_t errlen);
 SimGraph* sim_load(const uint8_t* data, size_t len, uint32_t n_regs, char* err, size_t errlen) {
+  return sim_load2(data, len, n_regs, 1, err, errlen);
+}
+SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int pair, char* err, size_t errlen) {
   try {
     std::unique_ptr<SimGraph> s(new SimGraph());
     s->g = deserialize_witnesscalc_graph(data, len);
-    PlanOptions o; o.n_regs = n_regs;
+    PlanOptions o; o.n_regs = n_regs; o.pair_muls = pair != 0;
     s->plan = compile_plan(s->g, o);
     return s.release();
   } catch (const std::exception& e) { if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; } return nullptr; }
@@ -35,14 +39,34 @@ void sim_info(SimGraph* s, uint64_t* out) {
   out[0] = s->g.nodes.size(); out[1] = s->plan.n_inputs; out[2] = s->plan.n_witness; out[3] = s->plan.code.size();
   out[4] = s->plan.n_regs; out[5] = s->plan.n_spill; out[6] = s->plan.stats.spill_ld; out[7] = s->plan.stats.spill_st;
   out[8] = s->plan.stats.max_live; out[9] = s->plan.consts.size(); out[10] = s->plan.stats.live_ops; out[11] = s->plan.stats.graph_ops;
+  out[12] = s->plan.stats.mul_pairs;
 }
 // inputs: I x 32 B, witness: W x 32 B; returns status bits, or -1 on a malformed plan
 int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
   const Plan& p = s->plan;
   std::vector<fe> rf(p.n_regs, fe_zero()), spill(p.n_spill, fe_zero());
   uint32_t st = 0;
-  for (const Instr& ins : p.code) {
+  for (size_t pc = 0; pc < p.code.size(); pc++) {
+    const Instr& ins = p.code[pc];
     uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
+    if (op == OP_NOP) continue;
+    if (ins.x & F_PAIR) {                       // pair semantics: read all four operands, then write
+      if (pc + 1 >= p.code.size() || (pc & 31) == 31) return -1;
+      const Instr& in2 = p.code[++pc];
+      auto ld = [&](uint32_t idx, bool is_const, fe* o) { if (is_const) { if (idx >= p.consts.size()) return false; *o = to_fe(p.consts[idx]); } else { if (idx >= p.n_regs) return false; *o = rf[idx]; } return true; };
+      fe A1, B1, A2, B2, R1, R2;
+      uint32_t op2 = in2.x & 0xFF, dst2 = in2.x >> 16;
+      if ((op != OP_MUL && op != OP_SQR) || (op2 != OP_MUL && op2 != OP_SQR)) return -1;
+      if (!ld(ins.y, ins.x & F_A_CONST, &A1) || !ld(in2.y, in2.x & F_A_CONST, &A2)) return -1;
+      if (op == OP_SQR) B1 = A1; else if (!ld(ins.z, ins.x & F_B_CONST, &B1)) return -1;
+      if (op2 == OP_SQR) B2 = A2; else if (!ld(in2.z, in2.x & F_B_CONST, &B2)) return -1;
+      fe_mul2(A1, B1, A2, B2, R1, R2);
+      if (dst != NO_DST) { if (dst >= p.n_regs) return -1; rf[dst] = R1; }
+      if (dst2 != NO_DST) { if (dst2 >= p.n_regs) return -1; rf[dst2] = R2; }
+      if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, R1.l, 32); }
+      if (in2.x & F_OUT) { if (in2.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)in2.w, R2.l, 32); }
+      continue;
+    }
     fe A = fe_zero(), B = fe_zero(), C = fe_zero(), R;
     if (op == OP_SPILL_ST) { if (ins.y >= p.n_regs || ins.z >= p.n_spill) return -1; spill[ins.z] = rf[ins.y]; continue; }
     if (op == OP_SPILL_LD) { if (dst >= p.n_regs || ins.y >= p.n_spill) return -1; rf[dst] = spill[ins.y]; continue; }

@@ -146,6 +146,8 @@ def sim_lib():
         L = ctypes.CDLL(_build("libgwsim.so", src))
         L.sim_load.restype = ctypes.c_void_p
         L.sim_load.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t]
+        L.sim_load2.restype = ctypes.c_void_p
+        L.sim_load2.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
         L.sim_free.argtypes = [ctypes.c_void_p]
         L.sim_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.sim_eval.restype = ctypes.c_int64
@@ -160,16 +162,16 @@ def sim_lib():
 class SimGraph:
     """ctypes wrapper over tests/csrc/plan_host_sim.cpp"""
 
-    def __init__(self, data: bytes, n_regs=24):
+    def __init__(self, data: bytes, n_regs=24, pair=True):
         self.L = sim_lib()
         err = ctypes.create_string_buffer(512)
-        self.h = self.L.sim_load(data, len(data), n_regs, err, 512)
+        self.h = self.L.sim_load2(data, len(data), n_regs, int(pair), err, 512)
         if not self.h:
             raise ValueError(err.value.decode())
-        info = (ctypes.c_uint64 * 12)()
+        info = (ctypes.c_uint64 * 13)()
         self.L.sim_info(self.h, info)
         keys = ["n_nodes", "I", "W", "n_instrs", "n_regs", "n_spill", "spill_ld", "spill_st", "max_live", "n_consts",
-                "live_ops", "graph_ops"]
+                "live_ops", "graph_ops", "mul_pairs"]
         self.info = dict(zip(keys, [int(x) for x in info]))
 
     def eval(self, inputs):

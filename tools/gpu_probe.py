@@ -30,7 +30,7 @@ if not a.no_imad:
 for name in a.circuits.split(","):
     g = cwc.Graph(util.golden_graph(name))
     I, W = g.n_inputs, g.n_witness
-    B = a.batch or max(1024, min(148 * 256 * 2, int(40e9 // (32 * W))))
+    B = a.batch or max(1024, min(148 * 256 * 2, int(110e9 // (32 * W))))
     rng = np.random.default_rng(9)
     vals = util.random_field_batch(rng, (min(B, 4096), I))
     if "sha256" in name:
