@@ -194,8 +194,17 @@ def main():
     I, W = g.n_inputs, g.n_witness
     B = a.batch
     free_b, _ = torch.cuda.mem_get_info()
-    chunk = a.chunk or int(min(B, max(1024, (free_b * 0.55 - B * I * 32) // (W * 32))))
-    chunk = max(128, (chunk // 128) * 128) if chunk >= 128 else chunk
+    threads = int(os.environ.get("GW_THREADS", "64"))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    wave = sms * threads                                     # one CTA per SM
+    max_chunk = int(max(wave, (free_b * 0.85 - B * I * 32) // (W * 32)))
+    if a.chunk:
+        chunk = a.chunk
+    elif B <= max_chunk:
+        chunk = B
+    else:
+        chunk = max_chunk // wave * wave                     # whole CTAs on every SM: no ragged last wave
+    n_chunks = (B + chunk - 1) // chunk
     n_unique = min(a.unique, B)
     host_in = synth_inputs(a.circuit, n_unique, I, g.input_signals, seed=9 + rank)
     d_unique = torch.from_numpy(host_in.reshape(n_unique, I * 32)).to(dev)
@@ -287,7 +296,9 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     imad_lo = cwc.microbench_imad(local_rank, 1)
     imad_wide = cwc.microbench_imad(local_rank, 0)
-    mul_per_div = float(os.environ.get("GW_MUL_PER_DIV", "381"))     # Fermat a^(M-2): 253 squarings + 126 + 2
+    # Div = one multiplication + one safegcd inversion: 20 rounds x 92 signed 32x32->64 multiply-adds
+    # (update_de 56 + update_fg 36) = 3680 IMAD-equivalents; the 600 divsteps themselves use no multiplier.
+    mul_per_div = 1.0 + 20 * 92 * 2 / 264.0
     mul_equiv = info["n_mul"] + info["n_div"] * mul_per_div
     imad_per_witness = 264.0 * mul_equiv
     per_launch_sets = B / len(chunks)

@@ -51,13 +51,14 @@ _L.gw_graph_input_signal.argtypes = [_vp, ctypes.c_uint32, ctypes.POINTER(ctypes
 _L.gw_graph_calc_witness.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_vp), ctypes.POINTER(_sz), ctypes.POINTER(gw_status_t)]
 _L.gw_calc_witness_batch.argtypes = [_vp, _vp, _sz, _vp, _vp, ctypes.c_int, ctypes.POINTER(gw_status_t)]
 _L.gw_calc_witness_batch_device.argtypes = [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, ctypes.POINTER(gw_status_t)]
+_L.gw_calc_witness_latency.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(gw_status_t)]
 _L.gw_wtns_header.argtypes = [ctypes.c_uint32, _vp]
 _L.gw_device_count.restype = ctypes.c_int
 _L.gw_microbench_imad.restype = ctypes.c_double
 _L.gw_microbench_imad.argtypes = [ctypes.c_int, ctypes.c_int]
 
 EXPORTS = ["gw_calc_witness", "gw_graph_load", "gw_graph_free", "gw_graph_info", "gw_graph_input_signal",
-           "gw_graph_calc_witness", "gw_calc_witness_batch", "gw_calc_witness_batch_device", "gw_wtns_header",
+           "gw_graph_calc_witness", "gw_calc_witness_batch", "gw_calc_witness_batch_device", "gw_calc_witness_latency", "gw_wtns_header",
            "gw_device_count", "gw_microbench_imad"]
 
 
@@ -174,6 +175,18 @@ class Graph:
                                       flags.ctypes.data if want_flags else None, n_gpus, ctypes.byref(st))
         _check(rc, st)
         return (out, flags) if want_flags else out
+
+    def calc_witness_latency(self, inputs_row: np.ndarray, device=0):
+        """ONE input set uint8 [I, 32] -> (witness uint8 [W, 32], kernel milliseconds): gw_calc_witness_latency."""
+        inputs_row = np.ascontiguousarray(inputs_row, dtype=np.uint8)
+        assert inputs_row.shape == (self.n_inputs, 32), inputs_row.shape
+        out = np.empty((self.n_witness, 32), dtype=np.uint8)
+        ms = ctypes.c_float(0)
+        st = gw_status_t()
+        rc = _L.gw_calc_witness_latency(self._h, device, inputs_row.ctypes.data, out.ctypes.data, None, ctypes.byref(ms),
+                                        ctypes.byref(st))
+        _check(rc, st)
+        return out, float(ms.value)
 
     def calc_witness_batch_ptr(self, inputs_ptr, n_sets, witness_ptr, flags_ptr=None, n_gpus=1):
         """HOST pointers (e.g. pinned torch tensors): no allocation, no copies besides the DMA."""

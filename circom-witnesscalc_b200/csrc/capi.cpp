@@ -47,7 +47,11 @@ static void calc_one(Engine& eng, const char* json, void** wtns_data, size_t* wt
   if (!out) throw Error("Failed to allocate memory for wtns_data");
   try {
     wtns_write_header(out, W);
-    eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, 0);
+    // a single witness goes through the latency-mode kernel (intra-level node parallelism) unless
+    // GW_SINGLE_MODE=batch asks for the throughput kernel with a batch of one
+    const char* mode = getenv("GW_SINGLE_MODE");
+    if (mode && !strcmp(mode, "batch")) eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, 0);
+    else eng.run_latency(0, (const uint8_t*)buf.data(), out + WTNS_HEADER_BYTES, nullptr, nullptr);
   } catch (...) { free(out); throw; }
   *wtns_data = out; *wtns_len = n;
 }
@@ -136,6 +140,12 @@ int gw_calc_witness_batch_device(gw_graph_t* graph, int device, const void* d_in
                                  uint32_t* d_flags, void* cuda_stream, gw_status_t* status) {
   if (!graph || (n_sets && (!d_inputs || !d_witness))) { set_status(status, ERROR, "null argument"); return 1; }
   return guarded(status, [&]() { graph->engine->run_device(device, d_inputs, n_sets, d_witness, d_flags, cuda_stream); });
+}
+
+int gw_calc_witness_latency(gw_graph_t* graph, int device, const uint8_t* inputs, uint8_t* witness, uint32_t* flags,
+                            float* kernel_ms, gw_status_t* status) {
+  if (!graph || !inputs || !witness) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() { graph->engine->run_latency(device, inputs, witness, flags, kernel_ms); });
 }
 
 void gw_wtns_header(uint32_t n_witness, uint8_t* dst76) { wtns_write_header(dst76, n_witness); }

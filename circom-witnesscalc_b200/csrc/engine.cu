@@ -162,6 +162,69 @@ __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
   }
 }
 
+// ---- single-witness latency mode ------------------------------------------------------------------------
+// One CTA evaluates ONE witness: the instructions of a dependency level are spread over the threads
+// (intra-level node parallelism), values live in one shared-memory slot file, a CTA barrier separates
+// levels.  Each thread prefetches its instruction of the next level while it executes the current one.
+struct LParams {
+  const uint4* code; const uint32_t* level_count; uint32_t n_levels;
+  const uint4* consts;
+  const uint4* inputs;     // [I][2]
+  uint4* out;              // [W][2]
+  uint32_t* status;        // [1] or null
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) eval_latency_kernel(const LParams p) {
+  extern __shared__ uint4 slots[];     // [n_slots][2]
+  const uint32_t tid = threadIdx.x;
+  auto slot_load = [&](uint32_t r) { return fe_from(slots[2 * r], slots[2 * r + 1]); };
+  auto const_load = [&](uint32_t c) { return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1)); };
+  auto operand = [&](uint32_t is_const, uint32_t idx) { return is_const ? const_load(idx) : slot_load(idx); };
+  uint32_t st = 0;
+  auto exec = [&](const uint4 ins) {
+    const uint32_t op = ins.x & 0xFFu, dst = ins.x >> 16;
+    fe R;
+    if (op == OP_NOP) return;
+    if (op == OP_OUT) { fe v = operand(ins.x & F_A_CONST, ins.y); p.out[2 * (size_t)ins.w] = fe_lo(v); p.out[2 * (size_t)ins.w + 1] = fe_hi(v); return; }
+    if (op == OP_INPUT) {
+      R = fe_reduce256(fe_from(__ldg(p.inputs + 2 * (size_t)ins.y), __ldg(p.inputs + 2 * (size_t)ins.y + 1)));
+    } else if (op == OP_MUL || op == OP_SQR) {
+      fe A = operand(ins.x & F_A_CONST, ins.y);
+      fe Bv = (op == OP_SQR) ? A : operand(ins.x & F_B_CONST, ins.z);
+      R = fe_mul(A, Bv);
+    } else if (op == OP_ADD || op == OP_SUB) {
+      fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
+      R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);
+    } else {
+      fe A = operand(ins.x & F_A_CONST, ins.y), Bv = fe_zero(), C = fe_zero();
+      if (op_has_b(op)) Bv = operand(ins.x & F_B_CONST, ins.z);
+      if (op == OP_TERN) C = operand(ins.x & F_C_CONST, ins.w);
+      R = alu_exec(op, A, Bv, C, st);
+    }
+    if (dst != NO_DST) { slots[2 * dst] = fe_lo(R); slots[2 * dst + 1] = fe_hi(R); }
+    if (ins.x & F_OUT) { p.out[2 * (size_t)ins.w] = fe_lo(R); p.out[2 * (size_t)ins.w + 1] = fe_hi(R); }
+  };
+  const uint4 nop = make_uint4(OP_NOP, 0, 0, 0);
+  const uint32_t nl = p.n_levels;
+  uint32_t pos = 0;
+  uint32_t c0 = __ldg(p.level_count), c1 = nl > 1 ? __ldg(p.level_count + 1) : 0, c2 = nl > 2 ? __ldg(p.level_count + 2) : 0;
+  uint4 nxt = tid < c0 ? __ldg(p.code + tid) : nop;
+  for (uint32_t L = 0; L < nl; L++) {
+    const uint4 ins = nxt;
+    const uint32_t c = c0, npos = pos + c;
+    nxt = tid < c1 ? __ldg(p.code + npos + tid) : nop;                    // next level's instruction
+    const uint32_t c3 = (L + 3 < nl) ? __ldg(p.level_count + L + 3) : 0;
+    if (tid < c) exec(ins);
+    for (uint32_t i = tid + T; i < c; i += T) exec(__ldg(p.code + pos + i));   // wide levels
+    if (nxt.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)nxt.y);
+    if ((nxt.x & F_B_CONST) && (nxt.x & 0xFFu) < 32) prefetch_l1(p.consts + 2 * (size_t)nxt.z);
+    __syncthreads();
+    pos = npos; c0 = c1; c1 = c2; c2 = c3;
+  }
+  if (p.status != nullptr && st) atomicOr(p.status, st);
+}
+
 // ---- integer-pipe microbenchmark (roofline denominator for multiplication-heavy graphs) ---------
 // WHICH = 0: rows of (mad.lo.cc, madc.hi.cc) pairs exactly as in u256_mul_wide -> IMAD.WIDE.U32(.X)
 //            with carry predicates; counts one op per 32x32+64 multiply-accumulate,
@@ -247,6 +310,9 @@ struct Engine::Dev {
   uint4* d_in[2] = {nullptr, nullptr}; uint4* d_out[2] = {nullptr, nullptr};
   uint32_t* d_status[2] = {nullptr, nullptr};
   size_t chunk = 0;
+  // single-witness latency mode
+  uint4* lat_code = nullptr; uint32_t* lat_levels = nullptr; uint4* lat_consts = nullptr;
+  uint4* lat_in = nullptr; uint4* lat_out = nullptr; uint32_t* lat_status = nullptr;
   std::mutex mu;
 };
 
@@ -254,9 +320,9 @@ static int env_int(const char* name, int dflt) { const char* s = getenv(name); r
 
 Engine::Engine(const uint8_t* graph_data, size_t len) {
   graph = deserialize_witnesscalc_graph(graph_data, len);
-  threads = env_int("GW_THREADS", 128);
+  threads = env_int("GW_THREADS", 64);
   if (threads != 64 && threads != 128 && threads != 256) throw Error("GW_THREADS must be 64, 128 or 256");
-  PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", 24);
+  PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", 12);
   opt.pair_muls = env_int("GW_PAIR", 1) != 0;
   opt.pair_window = (uint32_t)env_int("GW_PAIR_WINDOW", 24);
   plan = compile_plan(graph, opt);
@@ -267,6 +333,7 @@ Engine::~Engine() {
     Dev* d = kv.second;
     cudaSetDevice(d->device);
     cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
+    cudaFree(d->lat_code); cudaFree(d->lat_levels); cudaFree(d->lat_consts); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
     for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
     delete d;
   }
@@ -395,6 +462,52 @@ void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_
   }
   for (auto& t : th) t.join();
   for (auto& e : errs) if (!e.empty()) throw Error(e);
+}
+
+static const int LAT_THREADS = 128;
+
+// one witness, host buffers: inputs I x 32 B, witness W x 32 B; returns the kernel time in ms if asked
+void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms) {
+  Dev* d = dev(device);
+  CUDA_CHECK(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(d->mu);
+  {
+    std::lock_guard<std::mutex> lk2(mu);
+    if (!lat_ready) {
+      cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+      lat_plan = compile_latency_plan(graph, (uint32_t)(prop.sharedMemPerBlockOptin / 32));
+      lat_ready = true;
+    }
+  }
+  const LatencyPlan& lp = lat_plan;
+  const size_t in_b = (size_t)lp.n_inputs * 32, out_b = std::max<size_t>((size_t)lp.n_witness * 32, 32);
+  if (!d->lat_code) {
+    CUDA_CHECK(cudaMalloc(&d->lat_code, std::max<size_t>(lp.code.size(), 1) * sizeof(Instr)));
+    CUDA_CHECK(cudaMemcpy(d->lat_code, lp.code.data(), lp.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->lat_levels, std::max<size_t>(lp.level_count.size(), 1) * 4));
+    CUDA_CHECK(cudaMemcpy(d->lat_levels, lp.level_count.data(), lp.level_count.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->lat_consts, lp.consts.size() * 32));
+    CUDA_CHECK(cudaMemcpy(d->lat_consts, lp.consts.data(), lp.consts.size() * 32, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->lat_in, in_b));
+    CUDA_CHECK(cudaMalloc(&d->lat_out, out_b));
+    CUDA_CHECK(cudaMalloc(&d->lat_status, 4));
+    CUDA_CHECK(cudaFuncSetAttribute(eval_latency_kernel<LAT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)lp.n_slots * 32)));
+  }
+  if (lp.level_count.empty()) return;
+  LParams p;
+  p.code = d->lat_code; p.level_count = d->lat_levels; p.n_levels = (uint32_t)lp.level_count.size();
+  p.consts = d->lat_consts; p.inputs = d->lat_in; p.out = d->lat_out; p.status = status ? d->lat_status : nullptr;
+  CUDA_CHECK(cudaMemcpyAsync(d->lat_in, inputs, in_b, cudaMemcpyHostToDevice, 0));
+  if (status) CUDA_CHECK(cudaMemsetAsync(d->lat_status, 0, 4, 0));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (kernel_ms) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventRecord(e0, 0)); }
+  eval_latency_kernel<LAT_THREADS><<<1, LAT_THREADS, (size_t)lp.n_slots * 32, 0>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+  if (kernel_ms) CUDA_CHECK(cudaEventRecord(e1, 0));
+  CUDA_CHECK(cudaMemcpyAsync(witness, d->lat_out, (size_t)lp.n_witness * 32, cudaMemcpyDeviceToHost, 0));
+  if (status) CUDA_CHECK(cudaMemcpyAsync(status, d->lat_status, 4, cudaMemcpyDeviceToHost, 0));
+  CUDA_CHECK(cudaStreamSynchronize(0));
+  if (kernel_ms) { CUDA_CHECK(cudaEventElapsedTime(kernel_ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
 }
 
 int cuda_device_count() {

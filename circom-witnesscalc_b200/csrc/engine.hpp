@@ -18,12 +18,16 @@ class Engine {
 
   Graph graph;
   Plan plan;
-  int threads = 128;          // witnesses per CTA
+  int threads = 64;           // witnesses per CTA (GW_THREADS)
 
   // inputs/witness resident on `device`: inputs [B][I][32 B LE], witness [B][W][32 B LE]; asynchronous on `stream`
   void run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
   // host buffers; shards the batch over n_gpus devices starting at first_device (no collective)
   void run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device);
+  // single witness, latency mode (one CTA, intra-level node parallelism); host buffers
+  void run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms);
+  LatencyPlan lat_plan;
+  bool lat_ready = false;
 
  private:
   struct Dev;

@@ -269,3 +269,136 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt) {
 }
 
 }  // namespace gw
+
+namespace gw {
+
+LatencyPlan compile_latency_plan(const Graph& g, uint32_t max_slots) {
+  const size_t N = g.nodes.size();
+  LatencyPlan lp;
+  lp.n_inputs = g.inputs_size;
+  lp.n_witness = (uint32_t)g.witness_signals.size();
+
+  std::vector<uint8_t> needed(N, 0);
+  for (uint32_t s : g.witness_signals) needed[s] = 1;
+  for (size_t i = N; i-- > 0;) {
+    if (!needed[i]) continue;
+    const Node& nd = g.nodes[i];
+    if (nd.kind >= N_UNO) needed[nd.a] = 1;
+    if (nd.kind >= N_DUO) needed[nd.b] = 1;
+    if (nd.kind == N_TRES) needed[nd.c] = 1;
+  }
+  std::vector<int32_t> const_of(N, -1);
+  std::map<U256, uint32_t> cix;
+  auto intern = [&](const U256& v) {
+    auto it = cix.find(v);
+    if (it == cix.end()) { it = cix.emplace(v, (uint32_t)lp.consts.size()).first; lp.consts.push_back(v); }
+    return (int32_t)it->second;
+  };
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i]) continue;
+    const Node& nd = g.nodes[i];
+    if (nd.kind == N_CONST) const_of[i] = intern(g.constants.at(nd.a));
+    else if (nd.kind == N_INPUT && nd.a == 0) const_of[i] = intern(u256_from_u64(1));
+    else if (nd.kind == N_INPUT && nd.a >= g.inputs_size) throw Error("plan: input index out of range");
+  }
+  auto operands = [&](const Node& nd, uint32_t* ops) {
+    int n = 0;
+    if (nd.kind >= N_UNO) ops[n++] = nd.a;
+    if (nd.kind >= N_DUO) ops[n++] = nd.b;
+    if (nd.kind == N_TRES) ops[n++] = nd.c;
+    return n;
+  };
+  // dependency levels (inputs are level 0), last level at which every value is read
+  std::vector<uint32_t> level(N, 0), last_use(N, 0);
+  uint32_t n_levels = 1;
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i] || const_of[i] >= 0) continue;
+    const Node& nd = g.nodes[i];
+    uint32_t ops[3]; int n = operands(nd, ops);
+    uint32_t lv = 0;
+    for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) lv = std::max(lv, level[ops[k]] + 1);
+    if (nd.kind >= N_UNO && lv == 0) lv = 1;            // constant-only operands: still after the input level
+    level[i] = lv;
+    for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) last_use[ops[k]] = std::max(last_use[ops[k]], lv);
+    n_levels = std::max(n_levels, lv + 1);
+  }
+  // witness positions per node
+  std::vector<uint32_t> out_start(N + 1, 0), out_list(g.witness_signals.size());
+  for (uint32_t s : g.witness_signals) out_start[s + 1]++;
+  for (size_t i = 0; i < N; i++) out_start[i + 1] += out_start[i];
+  {
+    std::vector<uint32_t> fill(out_start.begin(), out_start.end() - 1);
+    for (uint32_t j = 0; j < g.witness_signals.size(); j++) out_list[fill[g.witness_signals[j]]++] = j;
+  }
+  // extra OUT instructions (second and later witness positions, TernCond results) run one level later
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i] || const_of[i] >= 0) continue;
+    uint32_t n_out = out_start[i + 1] - out_start[i];
+    bool inline_out = n_out >= 1 && g.nodes[i].kind != N_TRES;
+    if (n_out > (inline_out ? 1u : 0u)) { last_use[i] = std::max(last_use[i], level[i] + 1); n_levels = std::max(n_levels, level[i] + 2); }
+  }
+  // bucket nodes by level, inside a level by opcode (keeps warps uniform)
+  std::vector<std::vector<uint32_t>> by_level(n_levels);
+  for (size_t i = 0; i < N; i++) if (needed[i] && const_of[i] < 0) by_level[level[i]].push_back((uint32_t)i);
+  auto opkey = [&](uint32_t i) { const Node& nd = g.nodes[i]; return (uint32_t)nd.kind * 64u + nd.op; };
+  for (auto& v : by_level) std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return opkey(a) < opkey(b); });
+
+  std::vector<int32_t> slot_of(N, -1);
+  std::vector<uint32_t> free_slots;
+  std::vector<std::vector<uint32_t>> dying(n_levels + 1);       // values whose last read happens at this level
+  uint32_t n_slots = 0;
+  std::vector<Instr> pending_outs;                              // OUT instructions for the next level
+  for (uint32_t L = 0; L < n_levels; L++) {
+    uint32_t count = 0;
+    for (const Instr& in : pending_outs) { lp.code.push_back(in); count++; }
+    pending_outs.clear();
+    if (L == 0) {
+      for (size_t i = 0; i < N; i++) {
+        if (!needed[i] || const_of[i] < 0) continue;
+        for (uint32_t k = out_start[i]; k < out_start[i + 1]; k++) { lp.code.push_back(make_instr(OP_OUT, F_A_CONST, NO_DST, (uint32_t)const_of[i], 0, out_list[k])); count++; }
+      }
+    }
+    for (uint32_t i : by_level[L]) {
+      const Node& nd = g.nodes[i];
+      uint32_t ops[3]; int n = operands(nd, ops);
+      uint32_t enc[3] = {0, 0, 0}, flags = 0;
+      for (int k = 0; k < n; k++) {
+        if (const_of[ops[k]] >= 0) { enc[k] = (uint32_t)const_of[ops[k]]; flags |= (F_A_CONST << k); }
+        else { if (slot_of[ops[k]] < 0) throw Error("latency plan: operand without a slot"); enc[k] = (uint32_t)slot_of[ops[k]]; }
+      }
+      const uint32_t n_out = out_start[i + 1] - out_start[i];
+      const uint32_t* outs = &out_list[out_start[i]];
+      const bool inline_out = n_out >= 1 && nd.kind != N_TRES;
+      uint32_t dst = NO_DST;
+      if (last_use[i] > L) {
+        if (!free_slots.empty()) { dst = free_slots.back(); free_slots.pop_back(); }
+        else { dst = n_slots++; if (n_slots > max_slots) throw Error("latency plan: graph is too wide for the shared-memory value file"); }
+        slot_of[i] = (int32_t)dst;
+        dying[last_use[i]].push_back(i);
+      }
+      uint32_t op;
+      if (nd.kind == N_INPUT) { op = OP_INPUT; enc[0] = nd.a; }
+      else if (nd.kind == N_UNO) op = OP_NEG + nd.op;
+      else if (nd.kind == N_TRES) op = OP_TERN;
+      else op = (nd.op == OP_MUL && nd.a == nd.b && !(flags & F_A_CONST)) ? (uint32_t)OP_SQR : nd.op;
+      uint32_t w = nd.kind == N_TRES ? enc[2] : (inline_out ? outs[0] : 0);
+      if (inline_out) flags |= F_OUT;
+      lp.code.push_back(make_instr(op, flags, dst, enc[0], enc[1], w));
+      count++;
+      for (uint32_t k = inline_out ? 1u : 0u; k < n_out; k++) pending_outs.push_back(make_instr(OP_OUT, 0, NO_DST, dst, 0, outs[k]));
+    }
+    // slots read for the last time in this level become reusable from the next level on
+    for (uint32_t v : dying[L]) { free_slots.push_back((uint32_t)slot_of[v]); }
+    lp.level_count.push_back(count);
+    lp.max_level_width = std::max(lp.max_level_width, count);
+  }
+  if (!pending_outs.empty()) {
+    for (const Instr& in : pending_outs) lp.code.push_back(in);
+    lp.level_count.push_back((uint32_t)pending_outs.size());
+  }
+  lp.n_slots = std::max(n_slots, 1u);
+  if (lp.consts.empty()) lp.consts.push_back(u256_from_u64(0));
+  return lp;
+}
+
+}  // namespace gw

@@ -13,7 +13,7 @@
 namespace gw {
 
 struct PlanOptions {
-  uint32_t n_regs = 24;      // per-witness registers kept in shared memory
+  uint32_t n_regs = 12;      // per-witness registers kept in shared memory (12 x 32 B x 128 threads = 48 KB per CTA: 4 CTAs/SM)
   bool pair_muls = true;     // schedule independent multiplications next to each other and issue them as pairs
   uint32_t pair_window = 24; // how far ahead (in nodes) a partner is searched
 };
@@ -36,5 +36,18 @@ struct Plan {
 };
 
 Plan compile_plan(const Graph& g, const PlanOptions& opt);
+
+// Single-witness ("latency") mode: the same instruction format, but instructions are grouped into
+// dependency levels; all instructions of a level are independent and are executed by different threads
+// of ONE CTA, with a CTA barrier between levels.  Operands name slots of one shared-memory value file
+// (slots are recycled only at level boundaries, so there are no hazards inside a level).
+struct LatencyPlan {
+  std::vector<Instr> code;            // level after level
+  std::vector<uint32_t> level_count;  // instructions per level
+  std::vector<U256> consts;
+  uint32_t n_slots = 0, n_inputs = 0, n_witness = 0;
+  uint32_t max_level_width = 0;
+};
+LatencyPlan compile_latency_plan(const Graph& g, uint32_t max_slots);
 
 }  // namespace gw

@@ -103,4 +103,40 @@ size_t sim_reserialize(SimGraph* s, uint8_t* out, size_t cap) {
   return v.size();
 }
 void sim_wtns_header(uint32_t n, uint8_t* dst) { wtns_write_header(dst, n); }
+
+// latency plan: level by level; inside a level every instruction reads its operands before ANY
+// instruction of the level writes (the kernel runs them concurrently), which exposes slot hazards.
+// out5: n_levels, n_slots, n_instrs, max level width, status
+int64_t sim_eval_latency(SimGraph* s, const uint8_t* inputs, uint8_t* witness, uint64_t* out5) {
+  LatencyPlan lp;
+  try { lp = compile_latency_plan(s->g, 7264); } catch (const std::exception&) { return -2; }
+  std::vector<fe> slots(lp.n_slots, fe_zero());
+  uint32_t st = 0;
+  size_t pos = 0;
+  struct W { uint32_t dst; fe v; };
+  for (uint32_t cnt : lp.level_count) {
+    std::vector<W> writes;
+    for (size_t k = pos; k < pos + cnt; k++) {
+      const Instr& ins = lp.code[k];
+      uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
+      if (op == OP_NOP) continue;
+      auto load = [&](uint32_t idx, bool is_const, fe* o) { if (is_const) { if (idx >= lp.consts.size()) return false; *o = to_fe(lp.consts[idx]); } else { if (idx >= lp.n_slots) return false; *o = slots[idx]; } return true; };
+      fe A = fe_zero(), B = fe_zero(), C = fe_zero(), R;
+      if (op == OP_INPUT) { if (ins.y >= lp.n_inputs) return -1; fe v; memcpy(v.l, inputs + 32 * (size_t)ins.y, 32); R = fe_reduce256(v); }
+      else {
+        if (!load(ins.y, ins.x & F_A_CONST, &A)) return -1;
+        if (op == OP_OUT) { if (ins.w >= lp.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, A.l, 32); continue; }
+        if (op_has_b(op) && !load(ins.z, ins.x & F_B_CONST, &B)) return -1;
+        if (op == OP_TERN && !load(ins.w, ins.x & F_C_CONST, &C)) return -1;
+        R = alu_exec(op, A, B, C, st);
+      }
+      if (dst != NO_DST) { if (dst >= lp.n_slots) return -1; writes.push_back({dst, R}); }
+      if (ins.x & F_OUT) { if (ins.w >= lp.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
+    }
+    for (const W& w : writes) slots[w.dst] = w.v;
+    pos += cnt;
+  }
+  out5[0] = lp.level_count.size(); out5[1] = lp.n_slots; out5[2] = lp.code.size(); out5[3] = lp.max_level_width; out5[4] = st;
+  return 0;
+}
 }

@@ -92,3 +92,28 @@ def test_bad_inputs_return_errors(cwc):
         cwc.calc_witness_wtns('{"a": "1"', data)                        # invalid JSON (reference: panic)
     with pytest.raises(cwc.WitnessCalcError):
         cwc.calc_witness_wtns('{"a": "1"}', b"not a graph file at all....")
+
+
+def test_latency_mode_random_graphs_and_golden(cwc):
+    """single-witness latency mode (one CTA, level-parallel): gw_calc_witness_latency"""
+    rnd = random.Random(4321)
+    for t in range(10):
+        nodes, wit, imap = util.random_graph(rnd, n_ops=500)
+        g = cwc.Graph(po.serialize_graph(nodes, wit, imap))
+        row = [1] + [util.random_value(rnd) if rnd.random() < 0.8 else rnd.randrange(1 << 256) for _ in range(6)]
+        out, ms = g.calc_witness_latency(np.frombuffer(util.pack_u256(row), dtype=np.uint8).reshape(7, 32))
+        assert util.unpack_u256(out.tobytes()) == po.evaluate(nodes, row, wit, "circom"), t
+    for name in ("circuit8_sha256_512", "circuit9_authV2"):
+        data = util.golden_graph(name)
+        nodes, wit, imap = po.deserialize_graph(data)
+        g = cwc.Graph(data)
+        buf = po.build_input_buffer(nodes, imap, po.deserialize_inputs(util.golden_inputs(name)))
+        out, ms = g.calc_witness_latency(np.frombuffer(util.pack_u256(buf), dtype=np.uint8).reshape(g.n_inputs, 32))
+        assert po.wtns_from_witness(util.unpack_u256(out.tobytes())) == util.golden_wtns(name)
+        print(f"latency mode {name}: {ms:.2f} ms kernel")
+
+
+def test_single_witness_through_batch_kernel(cwc, monkeypatch):
+    monkeypatch.setenv("GW_SINGLE_MODE", "batch")
+    for name in ("circuit2", "circuit5_poseidon", "circuit9_authV2"):
+        assert cwc.calc_witness_wtns(util.golden_inputs(name), util.golden_graph(name)) == util.golden_wtns(name)

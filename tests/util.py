@@ -152,6 +152,8 @@ def sim_lib():
         L.sim_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.sim_eval.restype = ctypes.c_int64
         L.sim_eval.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+        L.sim_eval_latency.restype = ctypes.c_int64
+        L.sim_eval_latency.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)]
         L.sim_inputs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
         L.sim_reserialize.restype = ctypes.c_size_t
         L.sim_reserialize.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
@@ -181,6 +183,14 @@ class SimGraph:
         st = self.L.sim_eval(self.h, pack_u256(inputs), out)
         assert st >= 0, "malformed plan"
         return unpack_u256(out.raw), int(st)
+
+    def eval_latency(self, inputs):
+        """latency-mode plan on the host simulator -> (witness list, info dict)"""
+        out = ctypes.create_string_buffer(32 * self.info["W"])
+        o5 = (ctypes.c_uint64 * 5)()
+        rc = self.L.sim_eval_latency(self.h, pack_u256(inputs), out, o5)
+        assert rc == 0, f"latency plan failed ({rc})"
+        return unpack_u256(out.raw), dict(zip(["n_levels", "n_slots", "n_instrs", "max_width", "status"], [int(x) for x in o5]))
 
     def inputs_from_json(self, js: str):
         buf = ctypes.create_string_buffer(32 * self.info["I"])
