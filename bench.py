@@ -194,9 +194,8 @@ def main():
     I, W = g.n_inputs, g.n_witness
     B = a.batch
     free_b, _ = torch.cuda.mem_get_info()
-    threads = int(os.environ.get("GW_THREADS", "64"))
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    wave = sms * threads                                     # one CTA per SM
+    wave = sms * info["threads"] * info["sets_per_thread"]   # one CTA per SM
     max_chunk = int(max(wave, (free_b * 0.85 - B * I * 32) // (W * 32)))
     if a.chunk:
         chunk = a.chunk

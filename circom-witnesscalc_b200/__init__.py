@@ -36,7 +36,10 @@ class gw_graph_info_t(ctypes.Structure):
     _fields_ = [("n_nodes", ctypes.c_uint64), ("n_ops", ctypes.c_uint64), ("n_inputs", ctypes.c_uint32),
                 ("n_witness", ctypes.c_uint32), ("n_input_signals", ctypes.c_uint32), ("n_instrs", ctypes.c_uint32),
                 ("n_regs", ctypes.c_uint32), ("n_spill", ctypes.c_uint32), ("n_mul", ctypes.c_uint64),
-                ("n_div", ctypes.c_uint64), ("n_spill_ld", ctypes.c_uint64), ("n_spill_st", ctypes.c_uint64)]
+                ("n_div", ctypes.c_uint64), ("n_spill_ld", ctypes.c_uint64), ("n_spill_st", ctypes.c_uint64),
+                ("n_slots", ctypes.c_uint32), ("n_dot", ctypes.c_uint32), ("n_dot_mac", ctypes.c_uint32),
+                ("n_mul_instr", ctypes.c_uint32), ("n_inversions", ctypes.c_uint32), ("threads", ctypes.c_uint32),
+                ("sets_per_thread", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 _libc = ctypes.CDLL(None)

@@ -46,6 +46,8 @@ GW_HD fe alu_exec(uint32_t op, const fe& A, fe Bv, const fe& C, uint32_t& st) {
     case OP_ID: R = A; st |= ST_ID; break;
     case OP_LNOT: R = fe_small(fe_is_zero(A) ? 1u : 0u); st |= ST_LNOT_BNOT; break;
     case OP_BNOT: R = fe_bnot(A); st |= ST_LNOT_BNOT; break;
+    case OP_INV: R = fe_inv(A); break;                                       // plan compiler only (batched Div)
+    case OP_NZ1: { bool z = fe_is_zero(A); R = A; R.l[0] = z ? 1u : A.l[0]; break; }
     case OP_TERN: {                                                          // graph.rs:221-225
       bool z = fe_is_zero(A);
 #pragma unroll
@@ -58,5 +60,14 @@ GW_HD fe alu_exec(uint32_t op, const fe& A, fe Bv, const fe& C, uint32_t& st) {
 }
 
 GW_HD bool op_has_b(uint32_t op) { return op < 32 || op == OP_TERN; }
+
+// OP_SHRAND: (a >> k) & c for a shift amount 0 < k < 254 known at plan time (graph.rs:637-672 then :674-687; the
+// result of the AND is <= c < M, so bit_and's reduction never fires)
+GW_HD fe fe_shr_and(const fe& a, uint32_t k, const fe& c) {
+  fe r = u256_shr(a, k);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] &= c.l[i];
+  return r;
+}
 
 }  // namespace gw

@@ -24,16 +24,17 @@
 namespace gw {
 
 struct KParams {
-  const uint4* code; uint32_t n_instr;
+  const uint4* code; uint32_t n_slots;
   const uint4* consts;
   const uint4* inputs;     // [B][I][2]
   uint4* out;              // [B][W][2]
-  uint4* spill;            // [n_spill][2][spill_threads]
+  uint4* spill;            // [n_spill][2][V][spill_threads]
   uint32_t* status;        // [B] or null
   unsigned long long B;
   uint32_t I, W;
   uint32_t n_tiles;
   unsigned long long spill_threads;
+  unsigned long long out_wrap;   // profiling aid (GW_DEBUG_OUT_WRAP): witness rows wrap modulo this many rows; 0 = off
 };
 
 __device__ __forceinline__ fe fe_from(uint4 lo, uint4 hi) {
@@ -41,124 +42,324 @@ __device__ __forceinline__ fe fe_from(uint4 lo, uint4 hi) {
 }
 __device__ __forceinline__ uint4 fe_lo(const fe& a) { return make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]); }
 __device__ __forceinline__ uint4 fe_hi(const fe& a) { return make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]); }
-
-__device__ __forceinline__ uint4 shfl4(const uint4& v, int src) {
-  uint4 r;
-  r.x = __shfl_sync(0xffffffffu, v.x, src);
-  r.y = __shfl_sync(0xffffffffu, v.y, src);
-  r.z = __shfl_sync(0xffffffffu, v.z, src);
-  r.w = __shfl_sync(0xffffffffu, v.w, src);
-  return r;
-}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <int T>
+static const int RING = 64;     // instruction slots staged per warp in shared memory (two blocks of 32)
+
+// T threads per CTA, V input sets per thread.  Shared memory: [T/32 warps][RING] instruction slots, then the
+// register file [n_regs][2 halves][V][T] of uint4.
+template <int T, int V>
 __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
-  extern __shared__ uint4 rf[];
+  extern __shared__ uint4 smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  uint4* ring = smem + (tid >> 5) * RING;
+  uint4* rf = smem + (T / 32) * RING;
   const unsigned long long gthread = (unsigned long long)blockIdx.x * T + tid;
-  const uint32_t n = p.n_instr;
+  const uint32_t n = p.n_slots;
 
-  auto rf_load = [&](uint32_t r) { return fe_from(rf[(r * 2) * T + tid], rf[(r * 2 + 1) * T + tid]); };
-  auto rf_store = [&](uint32_t r, const fe& v) { rf[(r * 2) * T + tid] = fe_lo(v); rf[(r * 2 + 1) * T + tid] = fe_hi(v); };
+  auto rf_load = [&](uint32_t r, int v) { return fe_from(rf[((r * 2) * V + v) * T + tid], rf[((r * 2 + 1) * V + v) * T + tid]); };
+  auto rf_store = [&](uint32_t r, int v, const fe& x) { rf[((r * 2) * V + v) * T + tid] = fe_lo(x); rf[((r * 2 + 1) * V + v) * T + tid] = fe_hi(x); };
   auto const_load = [&](uint32_t c) { return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1)); };
-  auto operand = [&](uint32_t is_const, uint32_t idx) { return is_const ? const_load(idx) : rf_load(idx); };
 
   for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const unsigned long long w = (unsigned long long)tile * T + tid;
-    const bool active = w < p.B;
-    const unsigned long long wl = active ? w : p.B - 1;
-    const uint4* in = p.inputs + wl * p.I * 2;
-    uint4* out = p.out + wl * p.W * 2;
-    uint32_t st = 0;
-    auto out_store = [&](uint32_t j, const fe& v) { if (active) { out[2 * (size_t)j] = fe_lo(v); out[2 * (size_t)j + 1] = fe_hi(v); } };
+    const uint4* in[V]; uint4* out[V]; bool active[V]; unsigned long long wv[V];
+    uint32_t st[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      wv[v] = ((unsigned long long)tile * V + v) * T + tid;
+      active[v] = wv[v] < p.B;
+      const unsigned long long wl = active[v] ? wv[v] : p.B - 1;
+      in[v] = p.inputs + wl * p.I * 2;
+      out[v] = p.out + (p.out_wrap ? wl % p.out_wrap : wl) * p.W * 2;
+      st[v] = 0;
+    }
+    auto out_store = [&](uint32_t j, int v, const fe& x) { if (active[v]) { out[v][2 * (size_t)j] = fe_lo(x); out[v][2 * (size_t)j + 1] = fe_hi(x); } };
 
-    // Instruction stream: blk holds instructions [base, base+32) one per lane, nblk the following 32.
-    // q0/q1/q2 are the next three instructions, already broadcast: the shuffles (and the L1 prefetch of
-    // constant operands) for an instruction are issued two instructions before it executes, so their
-    // latency hides behind the arithmetic of the instructions in front of it.
-    uint32_t base = 0;
-    uint4 blk = __ldg(p.code + min((uint32_t)lane, n - 1));
-    uint4 nblk = __ldg(p.code + min(32u + lane, n - 1));
-    auto fetch = [&](uint32_t pcx) {
-      uint4 r = shfl4((pcx - base) < 32u ? blk : nblk, (int)(pcx & 31u));
-      if (r.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)r.y);
-      if (r.x & F_B_CONST) prefetch_l1(p.consts + 2 * (size_t)r.z);
-      return r;
+    // pull what the NEXT instruction reads from global memory (table constants, spilled values) towards L1 while
+    // the current instruction computes; its header (and term slots) are already in the ring
+    auto prefetch_one = [&](const uint4& h, uint32_t at) {
+      const uint32_t o = h.x & 0xFFu;
+      if (o == OP_DOT) {
+        const uint32_t nt = h.y & 0xFFu;
+#pragma unroll 1
+        for (uint32_t t = 0; t < nt; t += 2) {
+          const uint4 sl = ring[(at + 1 + (t >> 1)) & (RING - 1)];
+          if ((sl.x & 0xFu) != T_ADDHI && (sl.x & 0xFu) != T_SUBHI) prefetch_l1(p.consts + 2 * (size_t)sl.y);
+          if (t + 1 < nt && (sl.z & 0xFu) != T_ADDHI && (sl.z & 0xFu) != T_SUBHI) prefetch_l1(p.consts + 2 * (size_t)sl.w);
+        }
+      } else if (o == OP_SPILL_LD) {
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          prefetch_l1(p.spill + (((size_t)h.y * 2) * V + v) * p.spill_threads + gthread);
+          prefetch_l1(p.spill + (((size_t)h.y * 2 + 1) * V + v) * p.spill_threads + gthread);
+        }
+      } else if (o == OP_SHRAND) {
+        prefetch_l1(p.consts + 2 * (size_t)(h.z >> 8));
+      } else if (o < 48u) {
+        if (h.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)h.y);
+        if ((h.x & F_B_CONST) && o < 32u) prefetch_l1(p.consts + 2 * (size_t)h.z);
+      }
     };
-    uint4 q0 = fetch(0), q1 = fetch(min(1u, n - 1)), q2 = fetch(min(2u, n - 1));
+
+    auto prefetch_operands = [&](const uint4& h, uint32_t at) {
+      prefetch_one(h, at);
+      if ((V == 1) && (h.x & F_PAIR)) {
+        const uint32_t at2 = at + (((h.x & 0xFFu) == OP_DOT) ? 1u + (((h.y & 0xFFu) + 1u) >> 1) : 1u);
+        prefetch_one(ring[at2 & (RING - 1)], at2);
+      }
+    };
+
+    // instruction ring: blocks 0 and 1 staged, block 2 in flight in nblk
+    __syncwarp();
+    ring[lane] = __ldg(p.code + min((uint32_t)lane, n - 1));
+    ring[32 + lane] = __ldg(p.code + min(32u + lane, n - 1));
+    uint4 nblk = __ldg(p.code + min(64u + lane, n - 1));
+    __syncwarp();
     uint32_t pc = 0;
+    uint4 nxt = ring[0];
     while (pc < n) {
-      const uint4 ins = q0;
+      const uint4 ins = nxt;
       const uint32_t op = ins.x & 0xFFu;
       const uint32_t dst = ins.x >> 16;
-      uint32_t adv = 1;
+      const uint32_t len = (op == OP_DOT) ? 1u + (((ins.y & 0xFFu) + 1u) >> 1) : 1u;
+      uint32_t npc = pc + len;
+      uint4 ins2 = ins;
+      const bool paired = (V == 1) && (ins.x & F_PAIR);
+      if (paired) {                                   // bundle: the partner follows immediately
+        ins2 = ring[npc & (RING - 1)];
+        npc += ((ins2.x & 0xFFu) == OP_DOT) ? 1u + (((ins2.y & 0xFFu) + 1u) >> 1) : 1u;
+      }
+      const bool cross = (npc >> 5) != (pc >> 5);
+      if (!cross) { nxt = ring[npc & (RING - 1)]; if (npc < n) prefetch_operands(nxt, npc); }
 
-      if (ins.x & F_PAIR) {
-        // two independent multiplications issued together: all four operands are read before either
-        // result is written, and the two products give the scheduler twice the independent work
-        const uint4 in2 = q1;
-        adv = 2;
-        fe A1 = operand(ins.x & F_A_CONST, ins.y);
-        fe B1 = (op == OP_SQR) ? A1 : operand(ins.x & F_B_CONST, ins.z);
-        fe A2 = operand(in2.x & F_A_CONST, in2.y);
-        fe B2 = ((in2.x & 0xFFu) == OP_SQR) ? A2 : operand(in2.x & F_B_CONST, in2.z);
+      fe R[V];
+      bool have_result = true;
+      if (paired) {
+        // ---- two independent instructions of the same class as one bundle (V == 1): their carry chains sit in the
+        // same basic block, so the scheduler interleaves them; every operand is read before either result is stored
         fe R1, R2;
-        fe_mul2(A1, B1, A2, B2, R1, R2);
-        const uint32_t dst2 = in2.x >> 16;
-        if (dst != NO_DST) rf_store(dst, R1);
-        if (dst2 != NO_DST) rf_store(dst2, R2);
-        if (ins.x & F_OUT) out_store(ins.w, R1);
-        if (in2.x & F_OUT) out_store(in2.w, R2);
-      } else if (op == OP_ADD || op == OP_SUB) {
-        fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
-        fe R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);
-        if (dst != NO_DST) rf_store(dst, R);
-        if (ins.x & F_OUT) out_store(ins.w, R);
-      } else if (op == OP_MUL || op == OP_SQR) {
-        fe A = operand(ins.x & F_A_CONST, ins.y);
-        fe Bv = (op == OP_SQR) ? A : operand(ins.x & F_B_CONST, ins.z);
-        fe R = fe_mul(A, Bv);
-        if (dst != NO_DST) rf_store(dst, R);
-        if (ins.x & F_OUT) out_store(ins.w, R);
-      } else if (op == OP_SPILL_ST) {
-        fe v = rf_load(ins.y);
-        p.spill[((size_t)ins.z * 2) * p.spill_threads + gthread] = fe_lo(v);
-        p.spill[((size_t)ins.z * 2 + 1) * p.spill_threads + gthread] = fe_hi(v);
-      } else if (op == OP_SPILL_LD) {
-        rf_store(dst, fe_from(p.spill[((size_t)ins.y * 2) * p.spill_threads + gthread],
-                              p.spill[((size_t)ins.y * 2 + 1) * p.spill_threads + gthread]));
-      } else if (op == OP_OUT) {
-        out_store(ins.w, operand(ins.x & F_A_CONST, ins.y));
-      } else if (op != OP_NOP) {
-        // everything else (rare ops, out-of-line helpers): kept apart so that the hot paths above never
-        // have their operands forced into local memory by the calls in here
-        fe R;
-        if (op == OP_INPUT) {
-          R = fe_reduce256(fe_from(__ldg(in + 2 * (size_t)ins.y), __ldg(in + 2 * (size_t)ins.y + 1)));
-        } else {
-          fe A = operand(ins.x & F_A_CONST, ins.y), Bv = fe_zero(), C = fe_zero();
-          if (op_has_b(op)) Bv = operand(ins.x & F_B_CONST, ins.z);
-          if (op == OP_TERN) C = operand(ins.x & F_C_CONST, ins.w);
-          R = alu_exec(op, A, Bv, C, st);
+        if (op == OP_DOT) {
+          const uint32_t nt1 = ins.y & 0xFFu, nt2 = ins2.y & 0xFFu;
+          const uint32_t base1 = pc + 1, base2 = pc + len + 1;
+          const uint32_t tmin = min(nt1, nt2);
+          uint32_t P1[16], P2[16];
+#pragma unroll
+          for (int k = 0; k < 16; k++) { P1[k] = 0; P2[k] = 0; }
+          auto term_at = [&](uint32_t base, uint32_t t, uint32_t& kind, uint32_t& reg, uint32_t& ci) {
+            const uint4 sl = ring[(base + (t >> 1)) & (RING - 1)];
+            const uint32_t lo = (t & 1) ? sl.z : sl.x;
+            ci = (t & 1) ? sl.w : sl.y; kind = lo & 0xFu; reg = lo >> 16;
+          };
+          auto one_term = [&](uint32_t* P, uint32_t kind, uint32_t reg, uint32_t ci) {
+            if (kind == T_MAC) { const fe c = const_load(ci); const fe x = rf_load(reg, 0); uint32_t Q[16]; u256_mul_wide(Q, x.l, c.l); u512_add(P, Q); }
+            else if (kind == T_CONST) { const fe c = const_load(ci); u512_add256(P, c.l, 0); }
+            else dot_term(P, kind, rf_load(reg, 0), fe_zero());
+          };
+#pragma unroll 1
+          for (uint32_t t = 0; t < tmin; t++) {
+            uint32_t k1, r1, c1, k2, r2, c2;
+            term_at(base1, t, k1, r1, c1); term_at(base2, t, k2, r2, c2);
+            if (k1 == T_MAC && k2 == T_MAC) {
+              const fe cv1 = const_load(c1), cv2 = const_load(c2);
+              const fe x1 = rf_load(r1, 0), x2 = rf_load(r2, 0);
+              uint32_t Q1[16], Q2[16];
+              u256_mul_wide(Q1, x1.l, cv1.l); u256_mul_wide(Q2, x2.l, cv2.l);
+              u512_add(P1, Q1); u512_add(P2, Q2);
+            } else { one_term(P1, k1, r1, c1); one_term(P2, k2, r2, c2); }
+          }
+#pragma unroll 1
+          for (uint32_t t = tmin; t < nt1; t++) { uint32_t k1, r1, c1; term_at(base1, t, k1, r1, c1); one_term(P1, k1, r1, c1); }
+#pragma unroll 1
+          for (uint32_t t = tmin; t < nt2; t++) { uint32_t k2, r2, c2; term_at(base2, t, k2, r2, c2); one_term(P2, k2, r2, c2); }
+          R1 = fe_mont_reduce_core(P1); R2 = fe_mont_reduce_core(P2);
+          fe_cond_sub_n(R1, (int)((ins.y >> 8) & 0xFFu)); fe_cond_sub_n(R2, (int)((ins2.y >> 8) & 0xFFu));
+        } else {                                       // MUL / SQR x MUL / SQR
+          const uint32_t op2 = ins2.x & 0xFFu;
+          const fe A1 = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y, 0);
+          const fe B1 = (op == OP_SQR) ? A1 : ((ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z, 0));
+          const fe A2 = (ins2.x & F_A_CONST) ? const_load(ins2.y) : rf_load(ins2.y, 0);
+          const fe B2 = (op2 == OP_SQR) ? A2 : ((ins2.x & F_B_CONST) ? const_load(ins2.z) : rf_load(ins2.z, 0));
+          uint32_t Pm1[16], Pm2[16];
+          u256_mul_wide(Pm1, A1.l, B1.l); u256_mul_wide(Pm2, A2.l, B2.l);
+          R1 = fe_barrett(Pm1); R2 = fe_barrett(Pm2);
         }
-        if (dst != NO_DST) rf_store(dst, R);
-        if (ins.x & F_OUT) out_store(ins.w, R);
+        const uint32_t dst2 = ins2.x >> 16;
+        if (dst != NO_DST) rf_store(dst, 0, R1);
+        if (dst2 != NO_DST) rf_store(dst2, 0, R2);
+        if (ins.x & F_OUT) out_store(ins.w, 0, R1);
+        if (ins2.x & F_OUT) out_store(ins2.w, 0, R2);
+        have_result = false;
+      } else if (op == OP_DOT) {
+        // fused linear combination: 512-bit accumulators, one Montgomery reduction per input set
+        const uint32_t nt = ins.y & 0xFFu, ncs = (ins.y >> 8) & 0xFFu;
+        uint32_t P[V][16];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) P[v][k] = 0;
+        }
+#pragma unroll 1
+        for (uint32_t t = 0; t < nt; t++) {
+          const uint4 sl = ring[(pc + 1 + (t >> 1)) & (RING - 1)];
+          const uint32_t lo = (t & 1) ? sl.z : sl.x, ci = (t & 1) ? sl.w : sl.y;
+          const uint32_t kind = lo & 0xFu, reg = lo >> 16;
+          if (kind == T_MAC) {
+            const fe c = const_load(ci);
+            uint32_t Q[V][16];
+#pragma unroll
+            for (int v = 0; v < V; v++) { const fe x = rf_load(reg, v); u256_mul_wide(Q[v], x.l, c.l); }
+#pragma unroll
+            for (int v = 0; v < V; v++) u512_add(P[v], Q[v]);
+          } else if (kind == T_CONST) {
+            const fe c = const_load(ci);
+#pragma unroll
+            for (int v = 0; v < V; v++) u512_add256(P[v], c.l, 0);
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; v++) dot_term(P[v], kind, rf_load(reg, v), fe_zero());
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; v++) R[v] = fe_mont_reduce(P[v], (int)ncs);
+      } else if (op == OP_MUL || op == OP_SQR) {
+        fe A[V], Bv[V];
+        if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
+#pragma unroll
+          for (int v = 0; v < V; v++) A[v] = c;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) A[v] = rf_load(ins.y, v);
+        }
+        if (op == OP_SQR) {
+#pragma unroll
+          for (int v = 0; v < V; v++) Bv[v] = A[v];
+        } else if (ins.x & F_B_CONST) { const fe c = const_load(ins.z);
+#pragma unroll
+          for (int v = 0; v < V; v++) Bv[v] = c;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) Bv[v] = rf_load(ins.z, v);
+        }
+        uint32_t Pm[V][16];
+#pragma unroll
+        for (int v = 0; v < V; v++) u256_mul_wide(Pm[v], A[v].l, Bv[v].l);
+#pragma unroll
+        for (int v = 0; v < V; v++) R[v] = fe_barrett(Pm[v]);
+      } else if (op == OP_ADD || op == OP_SUB) {
+        fe A[V], Bv[V];
+        if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
+#pragma unroll
+          for (int v = 0; v < V; v++) A[v] = c;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) A[v] = rf_load(ins.y, v);
+        }
+        if (ins.x & F_B_CONST) { const fe c = const_load(ins.z);
+#pragma unroll
+          for (int v = 0; v < V; v++) Bv[v] = c;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) Bv[v] = rf_load(ins.z, v);
+        }
+#pragma unroll
+        for (int v = 0; v < V; v++) R[v] = (op == OP_ADD) ? fe_add(A[v], Bv[v]) : fe_sub(A[v], Bv[v]);
+      } else if (op == OP_SPILL_ST) {
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const fe x = rf_load(ins.y, v);
+          p.spill[(((size_t)ins.z * 2) * V + v) * p.spill_threads + gthread] = fe_lo(x);
+          p.spill[(((size_t)ins.z * 2 + 1) * V + v) * p.spill_threads + gthread] = fe_hi(x);
+        }
+        have_result = false;
+      } else if (op == OP_SPILL_LD) {
+#pragma unroll
+        for (int v = 0; v < V; v++)
+          R[v] = fe_from(p.spill[(((size_t)ins.y * 2) * V + v) * p.spill_threads + gthread],
+                         p.spill[(((size_t)ins.y * 2 + 1) * V + v) * p.spill_threads + gthread]);
+      } else if (op == OP_OUT) {
+        if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
+#pragma unroll
+          for (int v = 0; v < V; v++) out_store(ins.w, v, c);
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) out_store(ins.w, v, rf_load(ins.y, v));
+        }
+        have_result = false;
+      } else if (op == OP_INPUT) {
+#pragma unroll
+        for (int v = 0; v < V; v++) R[v] = fe_reduce256(fe_from(__ldg(in[v] + 2 * (size_t)ins.y), __ldg(in[v] + 2 * (size_t)ins.y + 1)));
+      } else if (op == OP_SHRAND) {
+        const fe c = const_load(ins.z >> 8);
+#pragma unroll
+        for (int v = 0; v < V; v++) R[v] = fe_shr_and(rf_load(ins.y, v), ins.z & 0xFFu, c);
+      } else if (op == OP_INV || op == OP_DIV) {
+        // modular inversion for all V input sets at once (interleaved safegcd chains); Div = a * b^-1, b == 0 -> 0
+        fe X[V];
+        const uint32_t src = (op == OP_INV) ? ins.y : ins.z;
+        const uint32_t src_const = (op == OP_INV) ? (ins.x & F_A_CONST) : (ins.x & F_B_CONST);
+        if (src_const) { const fe c = const_load(src);
+#pragma unroll
+          for (int v = 0; v < V; v++) X[v] = c;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) X[v] = rf_load(src, v);
+        }
+        fe_inv_batch<V>(X);
+        if (op == OP_DIV) {
+          uint32_t Pm[V][16];
+          if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
+#pragma unroll
+            for (int v = 0; v < V; v++) u256_mul_wide(Pm[v], c.l, X[v].l);
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; v++) { const fe a = rf_load(ins.y, v); u256_mul_wide(Pm[v], a.l, X[v].l); }
+          }
+#pragma unroll
+          for (int v = 0; v < V; v++) R[v] = fe_barrett(Pm[v]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) R[v] = X[v];
+        }
+      } else if (op != OP_NOP) {
+        // everything else (rare ops, out-of-line helpers), one input set after the other
+#pragma unroll 1
+        for (int v = 0; v < V; v++) {
+          fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y, v), Bv = fe_zero(), C = fe_zero();
+          if (op_has_b(op)) Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z, v);
+          if (op == OP_TERN) C = (ins.x & F_C_CONST) ? const_load(ins.w) : rf_load(ins.w, v);
+          uint32_t s = 0;
+          const fe r = alu_exec(op, A, Bv, C, s);
+#pragma unroll
+          for (int u = 0; u < V; u++) if (u == v) { R[u] = r; st[u] |= s; }
+        }
+      } else {
+        have_result = false;
+      }
+      if (have_result) {
+        if (dst != NO_DST) {
+#pragma unroll
+          for (int v = 0; v < V; v++) rf_store(dst, v, R[v]);
+        }
+        if (ins.x & F_OUT) {
+#pragma unroll
+          for (int v = 0; v < V; v++) out_store(ins.w, v, R[v]);
+        }
       }
 
-      // advance the instruction queue by adv (1 or 2) and refill it
-      const uint32_t npc = pc + adv;
-      if ((npc - base) >= 32u && npc < n) {            // entered the next block of 32
-        base += 32;
-        blk = nblk;
-        nblk = __ldg(p.code + min(base + 32u + lane, n - 1));
+      if (cross) {
+        // block (pc >> 5) is consumed: stage block (pc >> 5) + 2 in its half, start loading the one after it
+        __syncwarp();
+        ring[((pc >> 5) & 1u) * 32u + lane] = nblk;
+        nblk = __ldg(p.code + min(((pc >> 5) + 3u) * 32u + lane, n - 1));
+        __syncwarp();
+        nxt = ring[npc & (RING - 1)];
+        if (npc < n) prefetch_operands(nxt, npc);
       }
-      if (adv == 1) { q0 = q1; q1 = q2; q2 = fetch(min(npc + 2, n - 1)); }
-      else { q0 = q2; q1 = fetch(min(npc + 1, n - 1)); q2 = fetch(min(npc + 2, n - 1)); }
       pc = npc;
     }
-    if (p.status != nullptr && active) p.status[w] = st;
+#pragma unroll
+    for (int v = 0; v < V; v++) if (p.status != nullptr && active[v]) p.status[wv[v]] = st[v];
   }
 }
 
@@ -300,6 +501,15 @@ double imad_microbench(int device, int which) {
 }
 
 // ---- engine ------------------------------------------------------------------------------------------
+typedef void (*BatchKernel)(const KParams);
+static BatchKernel batch_kernel(int T, int V) {
+  if (T == 32 && V == 1) return eval_batch_kernel<32, 1>;
+  if (T == 32 && V == 2) return eval_batch_kernel<32, 2>;
+  if (T == 64 && V == 1) return eval_batch_kernel<64, 1>;
+  if (T == 64 && V == 2) return eval_batch_kernel<64, 2>;
+  throw Error("GW_THREADS must be 32 or 64 and GW_V 1 or 2");
+}
+
 struct Engine::Dev {
   int device = -1;
   int sms = 0, ctas_per_sm = 0;
@@ -321,11 +531,18 @@ static int env_int(const char* name, int dflt) { const char* s = getenv(name); r
 Engine::Engine(const uint8_t* graph_data, size_t len) {
   graph = deserialize_witnesscalc_graph(graph_data, len);
   threads = env_int("GW_THREADS", 64);
-  if (threads != 64 && threads != 128 && threads != 256) throw Error("GW_THREADS must be 64, 128 or 256");
-  PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", 12);
-  opt.pair_muls = env_int("GW_PAIR", 1) != 0;
-  opt.pair_window = (uint32_t)env_int("GW_PAIR_WINDOW", 24);
+  sets_per_thread = env_int("GW_V", 1);
+  batch_kernel(threads, sets_per_thread);      // validates the combination
+  PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", (int)opt.n_regs);
+  opt.div_batch = (uint32_t)env_int("GW_DIV_BATCH", (int)opt.div_batch);
+  opt.fuse_dot = env_int("GW_FUSE_DOT", 1) != 0;
+  opt.max_terms = (uint32_t)env_int("GW_MAX_TERMS", (int)opt.max_terms);
+  opt.pair = env_int("GW_PAIR", 0) != 0 && sets_per_thread == 1;   // bundles are the V == 1 source of ILP
   plan = compile_plan(graph, opt);
+}
+
+size_t Engine::smem_bytes() const {
+  return (size_t)(threads / 32) * RING * 16 + (size_t)plan.n_regs * 32 * sets_per_thread * threads;
 }
 
 Engine::~Engine() {
@@ -337,16 +554,6 @@ Engine::~Engine() {
     for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
     delete d;
   }
-}
-
-template <int T> static void launch_t(const KParams& p, int grid, size_t smem, cudaStream_t s) {
-  eval_batch_kernel<T><<<grid, T, smem, s>>>(p);
-}
-template <int T> static int setup_t(size_t smem) {
-  CUDA_CHECK(cudaFuncSetAttribute(eval_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int nb = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, eval_batch_kernel<T>, T, smem));
-  return nb;
 }
 
 Engine::Dev* Engine::dev(int device) {
@@ -362,16 +569,18 @@ Engine::Dev* Engine::dev(int device) {
   d->device = device;
   cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   d->sms = prop.multiProcessorCount;
-  size_t smem = (size_t)plan.n_regs * 32 * threads;
+  const size_t smem = smem_bytes();
   if (smem > (size_t)prop.sharedMemPerBlockOptin) throw Error("register file does not fit shared memory: lower GW_REGS or GW_THREADS");
-  d->ctas_per_sm = threads == 64 ? setup_t<64>(smem) : threads == 128 ? setup_t<128>(smem) : setup_t<256>(smem);
+  BatchKernel k = batch_kernel(threads, sets_per_thread);
+  CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->ctas_per_sm, k, threads, smem));
   if (d->ctas_per_sm < 1) throw Error("kernel cannot be resident with this register-file size");
   CUDA_CHECK(cudaMalloc(&d->code, plan.code.size() * sizeof(Instr)));
   CUDA_CHECK(cudaMemcpy(d->code, plan.code.data(), plan.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMalloc(&d->consts, plan.consts.size() * 32));
   CUDA_CHECK(cudaMemcpy(d->consts, plan.consts.data(), plan.consts.size() * 32, cudaMemcpyHostToDevice));
   d->spill_threads = (size_t)d->sms * d->ctas_per_sm * threads;
-  if (plan.n_spill) CUDA_CHECK(cudaMalloc(&d->spill, (size_t)plan.n_spill * 32 * d->spill_threads));
+  if (plan.n_spill) CUDA_CHECK(cudaMalloc(&d->spill, (size_t)plan.n_spill * 32 * sets_per_thread * d->spill_threads));
   devs[device] = d;
   return d;
 }
@@ -379,17 +588,17 @@ Engine::Dev* Engine::dev(int device) {
 void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
   if (B == 0 || plan.code.empty()) return;
   KParams p;
-  p.code = d->code; p.n_instr = (uint32_t)plan.code.size(); p.consts = d->consts;
+  p.code = d->code; p.n_slots = (uint32_t)plan.code.size(); p.consts = d->consts;
   p.inputs = (const uint4*)d_inputs; p.out = (uint4*)d_witness; p.spill = d->spill; p.status = d_status;
   p.B = B; p.I = plan.n_inputs; p.W = plan.n_witness;
-  size_t n_tiles = (B + threads - 1) / threads;
+  const size_t tile = (size_t)threads * sets_per_thread;
+  size_t n_tiles = (B + tile - 1) / tile;
   if (n_tiles > 0xFFFFFFFFull) throw Error("batch too large");
   p.n_tiles = (uint32_t)n_tiles;
   p.spill_threads = d->spill_threads;
+  p.out_wrap = (unsigned long long)env_int("GW_DEBUG_OUT_WRAP", 0);
   int grid = (int)std::min<size_t>(n_tiles, (size_t)d->sms * d->ctas_per_sm);
-  size_t smem = (size_t)plan.n_regs * 32 * threads;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (threads == 64) launch_t<64>(p, grid, smem, s); else if (threads == 128) launch_t<128>(p, grid, smem, s); else launch_t<256>(p, grid, smem, s);
+  batch_kernel(threads, sets_per_thread)<<<grid, threads, smem_bytes(), (cudaStream_t)stream>>>(p);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -413,7 +622,7 @@ void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* w
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   size_t budget = (size_t)env_int("GW_CHUNK_MB", 24576) << 20;
   budget = std::min(budget, (free_b + 2 * d->chunk * (in_b + out_b)) / 5);
-  size_t chunk = std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 2 * d->spill_threads);
+  size_t chunk = std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 2 * d->spill_threads * sets_per_thread);
   if (B >= 4 * 2048) chunk = std::min(chunk, (B + 3) / 4);
   chunk = std::max<size_t>(std::min(chunk, B), 1);
   if (chunk > d->chunk) {

@@ -23,7 +23,7 @@
 #define GW_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define GW_HD inline
-#define GW_HD_NOINLINE
+#define GW_HD_NOINLINE inline __attribute__((noinline))
 #endif
 
 namespace gw {
@@ -49,6 +49,13 @@ GW_HD constexpr uint32_t MM2_L(int i) {   // M - 2 (Fermat exponent)
 GW_HD constexpr uint32_t R2_L(int i) {    // 2^512 mod M
   return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u :
          i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+}
+GW_HD constexpr uint32_t R1_L(int i) {    // 2^256 mod M
+  return i == 0 ? 0x4ffffffbu : i == 1 ? 0xac96341cu : i == 2 ? 0x9f60cd29u : i == 3 ? 0x36fc7695u :
+         i == 4 ? 0x7879462eu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+}
+GW_HD constexpr uint32_t MODS_L(int i, int s) {   // limb i of M << s, s in {0, 1, 2}  (4M < 2^256)
+  return s == 0 ? MOD_L(i) : ((MOD_L(i) << s) | (i > 0 ? (MOD_L(i - 1) >> (32 - s)) : 0u));
 }
 static const uint32_t MONT_INV32 = 0xefffffffu;   // -M^-1 mod 2^32
 
@@ -122,6 +129,15 @@ GW_HD void fe_cond_sub_m(fe& a) {
   fe m = fe_modulus();
   uint32_t t[8];
   uint32_t borrow = u256_sub(t, a.l, m.l);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.l[i] = borrow ? a.l[i] : t[i];
+}
+// if a >= (M << S) then a -= (M << S)
+template <int S> GW_HD void fe_cond_sub_ms(fe& a) {
+  uint32_t m[8], t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = MODS_L(i, S);
+  uint32_t borrow = u256_sub(t, a.l, m);
 #pragma unroll
   for (int i = 0; i < 8; i++) a.l[i] = borrow ? a.l[i] : t[i];
 }
@@ -371,6 +387,112 @@ GW_HD void fe_mul2(const fe& a1, const fe& b1, const fe& a2, const fe& b2, fe& r
 }
 // out-of-line copy for the long chains (inversion, pow): keeps the interpreter's code size down
 GW_HD_NOINLINE fe fe_mul_ni(const fe& a, const fe& b) { return fe_mul(a, b); }
+
+// ---- fused linear combinations (OP_DOT): 512-bit accumulator + ONE Montgomery reduction -----------------
+// P (16 limbs) += Q (16 limbs); the caller guarantees the sum stays below 2^512
+GW_HD void u512_add(uint32_t* P, const uint32_t* Q) {
+#if defined(__CUDA_ARCH__)
+  P[0] = ptx_add_cc(P[0], Q[0]);
+#pragma unroll
+  for (int i = 1; i < 15; i++) P[i] = ptx_addc_cc(P[i], Q[i]);
+  P[15] = ptx_addc(P[15], Q[15]);
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 16; i++) { c += (uint64_t)P[i] + Q[i]; P[i] = (uint32_t)c; c >>= 32; }
+#endif
+}
+// P += v (8 limbs) at limb offset `off` (0 or 8), carry propagated to the top
+GW_HD void u512_add256(uint32_t* P, const uint32_t* v, int off) {
+#if defined(__CUDA_ARCH__)
+  P[off] = ptx_add_cc(P[off], v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) P[off + i] = ptx_addc_cc(P[off + i], v[i]);
+  if (off == 0) {
+#pragma unroll
+    for (int i = 8; i < 15; i++) P[i] = ptx_addc_cc(P[i], 0);
+    P[15] = ptx_addc(P[15], 0);
+  }
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (uint64_t)P[off + i] + v[i]; P[off + i] = (uint32_t)c; c >>= 32; }
+  for (int i = off + 8; i < 16; i++) { c += P[i]; P[i] = (uint32_t)c; c >>= 32; }
+#endif
+}
+// t = P * 2^-256 mod M for P < 2^512 with t_before_subtraction = (P + m*M) / 2^256 < 2^(n_cond_sub) * M and < 2^256
+// (the plan compiler bounds P term by term, see plan.cpp).  Word-serial Montgomery reduction: 8 rounds of
+// m = P[i] * (-M^-1) mod 2^32; P += m * M << 32 i, as two carry chains per round (even / odd limbs of M) whose
+// carry-outs are collected lazily in K (columns 8..16 are never read by a later round).  P is clobbered.
+GW_HD fe fe_mont_reduce_core(uint32_t* P) {
+  fe r;
+#if defined(__CUDA_ARCH__)
+  uint32_t K[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) K[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t m = P[i] * MONT_INV32;
+    P[i] = ptx_mad_lo_cc(m, MOD_L(0), P[i]);
+    P[i + 1] = ptx_madc_hi_cc(m, MOD_L(0), P[i + 1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      P[i + j] = ptx_madc_lo_cc(m, MOD_L(j), P[i + j]);
+      P[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), P[i + j + 1]);
+    }
+    K[i] = ptx_addc(K[i], 0);
+    P[i + 1] = ptx_mad_lo_cc(m, MOD_L(1), P[i + 1]);
+    P[i + 2] = ptx_madc_hi_cc(m, MOD_L(1), P[i + 2]);
+#pragma unroll
+    for (int j = 3; j < 8; j += 2) {
+      P[i + j] = ptx_madc_lo_cc(m, MOD_L(j), P[i + j]);
+      P[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), P[i + j + 1]);
+    }
+    K[i + 1] = ptx_addc(K[i + 1], 0);
+  }
+  r.l[0] = ptx_add_cc(P[8], K[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.l[i] = ptx_addc_cc(P[8 + i], K[i]);
+  r.l[7] = ptx_addc(P[15], K[7]);
+#else
+  uint64_t top = 0;                                    // carries out of column 15
+  for (int i = 0; i < 8; i++) {
+    const uint32_t m = P[i] * MONT_INV32;
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) { c += (uint64_t)m * MOD_L(j) + P[i + j]; P[i + j] = (uint32_t)c; c >>= 32; }
+    for (int k = i + 8; k < 16 && c; k++) { c += P[k]; P[k] = (uint32_t)c; c >>= 32; }
+    top += c;
+  }
+  (void)top;                                           // 0 by the caller's bound
+  for (int i = 0; i < 8; i++) r.l[i] = P[8 + i];
+#endif
+  return r;
+}
+// r < 2^n * M (n = n_cond_sub in 1..3)  ->  [0, M)
+GW_HD void fe_cond_sub_n(fe& r, int n_cond_sub) {
+  if (n_cond_sub >= 3) fe_cond_sub_ms<2>(r);
+  if (n_cond_sub >= 2) fe_cond_sub_ms<1>(r);
+  fe_cond_sub_m(r);
+}
+GW_HD fe fe_mont_reduce(uint32_t* P, int n_cond_sub) {
+  fe r = fe_mont_reduce_core(P);
+  fe_cond_sub_n(r, n_cond_sub);
+  return r;
+}
+// one OP_DOT term (isa.h TermKind) accumulated into P; x = register value, c = table constant (pre-scaled)
+GW_HD void dot_term(uint32_t* P, uint32_t kind, const fe& x, const fe& c) {
+  if (kind == 0) {                                     // T_MAC
+    uint32_t Q[16];
+    u256_mul_wide(Q, x.l, c.l);
+    u512_add(P, Q);
+  } else if (kind == 1) {                              // T_ADDHI
+    u512_add256(P, x.l, 8);
+  } else if (kind == 2) {                              // T_SUBHI: + (M - x)
+    fe m = fe_modulus(); uint32_t t[8];
+    u256_sub(t, m.l, x.l);
+    u512_add256(P, t, 8);
+  } else {                                             // T_CONST
+    u512_add256(P, c.l, 0);
+  }
+}
 
 // Montgomery product a*b*2^-256 mod M (operands < M), CIOS on 32-bit limbs.
 GW_HD fe fe_mont_mul(const fe& a, const fe& b) {

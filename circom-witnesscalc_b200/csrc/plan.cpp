@@ -4,10 +4,139 @@
 
 #include <algorithm>
 #include <map>
+#include <set>
+
+#include "field.cuh"
 
 namespace gw {
 
 namespace {
+
+inline int n_operands(const Node& nd) { return nd.kind == N_TRES ? 3 : nd.kind == N_DUO ? 2 : nd.kind == N_UNO ? 1 : 0; }
+inline uint32_t operand(const Node& nd, int k) { return k == 0 ? nd.a : k == 1 ? nd.b : nd.c; }
+
+std::vector<uint8_t> liveness(const Graph& g) {
+  // dead nodes are unobservable: evaluate() is pure (graph.rs:367)
+  const size_t N = g.nodes.size();
+  std::vector<uint8_t> needed(N, 0);
+  for (uint32_t s : g.witness_signals) needed[s] = 1;
+  for (size_t i = N; i-- > 0;) {
+    if (!needed[i]) continue;
+    const Node& nd = g.nodes[i];
+    for (int k = 0; k < n_operands(nd); k++) needed[operand(nd, k)] = 1;
+  }
+  return needed;
+}
+
+fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
+U256 to_u256(const fe& v) { U256 r; memcpy(r.l, v.l, 32); return r; }
+// c * 2^256 mod M (or (M - c) * 2^256 mod M): the form OP_DOT constants are stored in
+U256 prescale(const U256& c, bool neg) {
+  fe r1; for (int i = 0; i < 8; i++) r1.l[i] = R1_L(i);
+  fe v = to_fe(c);
+  if (neg) v = fe_neg(v);
+  return to_u256(fe_mul(v, r1));
+}
+
+// ---- Div batching -----------------------------------------------------------------------------------
+// dl(n) = number of Div nodes on the longest operand path ending at n (n itself excluded).  Div nodes with
+// equal dl are mutually independent.  The graph is re-emitted level by level (file order inside a level:
+// still topological), and the Div nodes of a level are replaced, in groups of <= kmax, by
+//   nz_i = NZ1(b_i); p_i = nz_1 .. nz_i; t = INV(p_k); inv_i = t_i * p_(i-1), t_(i-1) = t_i * nz_i;
+//   r_i = b_i != 0 ? a_i * inv_i : 0                                    (Div semantics graph.rs:109)
+Graph rewrite_div_batches(const Graph& g, uint32_t kmax) {
+  const size_t N = g.nodes.size();
+  std::vector<uint8_t> needed = liveness(g);
+  auto is_div = [&](uint32_t i) { return g.nodes[i].kind == N_DUO && g.nodes[i].op == OP_DIV; };
+  std::vector<uint32_t> dl(N, 0);
+  uint32_t max_l = 0; size_t n_div = 0;
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i]) continue;
+    const Node& nd = g.nodes[i];
+    uint32_t d = 0;
+    for (int k = 0; k < n_operands(nd); k++) { uint32_t o = operand(nd, k); d = std::max(d, dl[o] + (is_div(o) ? 1u : 0u)); }
+    dl[i] = d; max_l = std::max(max_l, d);
+    n_div += is_div((uint32_t)i);
+  }
+  if (n_div < 2) return g;
+  std::vector<std::vector<uint32_t>> plain(max_l + 1), divs(max_l + 1);
+  for (size_t i = 0; i < N; i++) if (needed[i]) (is_div((uint32_t)i) ? divs : plain)[dl[i]].push_back((uint32_t)i);
+
+  Graph ng;
+  ng.constants = g.constants; ng.inputs = g.inputs; ng.inputs_size = g.inputs_size;
+  ng.nodes.reserve(N + 6 * n_div);
+  std::vector<uint32_t> map(N, 0xFFFFFFFFu);
+  auto push = [&](uint8_t kind, uint8_t op, uint32_t a, uint32_t b, uint32_t c) {
+    Node nd; nd.kind = kind; nd.op = op; nd.a = a; nd.b = b; nd.c = c;
+    ng.nodes.push_back(nd);
+    return (uint32_t)ng.nodes.size() - 1;
+  };
+  int32_t zero_node = -1;
+  auto const_node = [&](uint64_t v) {
+    U256 c = u256_from_u64(v);
+    uint32_t ci = 0;
+    for (; ci < ng.constants.size(); ci++) if (ng.constants[ci] == c) break;
+    if (ci == ng.constants.size()) ng.constants.push_back(c);
+    return push(N_CONST, 0, ci, 0, 0);
+  };
+  auto is_const_one = [&](uint32_t old) {
+    const Node& nd = g.nodes[old];
+    return nd.kind == N_CONST && g.constants[nd.a] == u256_from_u64(1);
+  };
+  for (uint32_t L = 0; L <= max_l; L++) {
+    for (uint32_t i : plain[L]) {
+      const Node& nd = g.nodes[i];
+      uint32_t a = nd.a, b = nd.b, c = nd.c;
+      if (nd.kind >= N_UNO) a = map[nd.a];
+      if (nd.kind >= N_DUO) b = map[nd.b];
+      if (nd.kind == N_TRES) c = map[nd.c];
+      map[i] = push(nd.kind, nd.op, a, b, c);
+    }
+    const std::vector<uint32_t>& dv = divs[L];
+    for (size_t lo = 0; lo < dv.size(); lo += kmax) {
+      const size_t k = std::min<size_t>(kmax, dv.size() - lo);
+      if (k == 1) { const Node& nd = g.nodes[dv[lo]]; map[dv[lo]] = push(N_DUO, OP_DIV, map[nd.a], map[nd.b], 0); continue; }
+      if (zero_node < 0) zero_node = (int32_t)const_node(0);
+      std::vector<uint32_t> nz(k), p(k), inv(k);
+      for (size_t i = 0; i < k; i++) nz[i] = push(N_UNO, (uint8_t)(OP_NZ1 - OP_NEG), map[g.nodes[dv[lo + i]].b], 0, 0);
+      p[0] = nz[0];
+      for (size_t i = 1; i < k; i++) p[i] = push(N_DUO, OP_MUL, p[i - 1], nz[i], 0);
+      uint32_t t = push(N_UNO, (uint8_t)(OP_INV - OP_NEG), p[k - 1], 0, 0);
+      for (size_t i = k - 1; i >= 1; i--) {
+        inv[i] = push(N_DUO, OP_MUL, t, p[i - 1], 0);
+        t = push(N_DUO, OP_MUL, t, nz[i], 0);
+      }
+      inv[0] = t;
+      for (size_t i = 0; i < k; i++) {
+        const Node& nd = g.nodes[dv[lo + i]];
+        uint32_t q = is_const_one(nd.a) ? inv[i] : push(N_DUO, OP_MUL, map[nd.a], inv[i], 0);
+        map[dv[lo + i]] = push(N_TRES, 0, map[nd.b], q, (uint32_t)zero_node);
+      }
+    }
+  }
+  ng.witness_signals.reserve(g.witness_signals.size());
+  for (uint32_t s : g.witness_signals) ng.witness_signals.push_back(map[s]);
+  return ng;
+}
+
+// ---- macro ops -----------------------------------------------------------------------------------------
+struct PTerm { uint8_t kind; bool neg; uint32_t node; U256 c; };   // kind: 0 value*const, 1 value, 2 const
+struct MOp {
+  uint32_t node = 0;              // graph node whose value this op defines
+  uint32_t opc = OP_NOP;
+  uint32_t in[3] = {0, 0, 0}; int n_in = 0;   // operand nodes of a regular op (constants included)
+  std::vector<PTerm> terms;       // OP_DOT
+  uint32_t ncs = 1;
+  uint32_t shift = 0; U256 mask;  // OP_SHRAND
+};
+
+// bound of the Montgomery-reduced sum before the conditional subtractions, in units of M:
+// (P + mM) / 2^256 < M * (1 + nmac * M / 2^256 + nhi) (+ < 1 for constant terms)
+double dot_bound(const std::vector<PTerm>& t) {
+  double b = 1.0 + 1e-6;
+  for (const PTerm& x : t) b += x.kind == 0 ? 0.18906 : x.kind == 1 ? 1.0 : 1e-9;
+  return b;
+}
 
 struct Allocator {
   const std::vector<uint32_t>& use_start;
@@ -29,15 +158,14 @@ struct Allocator {
   void emit(const Instr& in) {
     plan.code.push_back(in);
     plan.stats.op_count[in.x & 0x3F]++;
+    plan.stats.instrs++;
   }
   // a free register; `pin` = registers that must stay resident for the instruction being built
-  uint32_t alloc_reg(const uint32_t* pin, int n_pin) {
+  uint32_t alloc_reg(const std::vector<uint32_t>& pin) {
     if (!free_regs.empty()) { uint32_t r = free_regs.back(); free_regs.pop_back(); return r; }
     int best = -1; uint32_t best_use = 0;
     for (uint32_t r = 0; r < reg_val.size(); r++) {
-      bool pinned = false;
-      for (int k = 0; k < n_pin; k++) pinned |= (pin[k] == r);
-      if (pinned) continue;
+      if (std::find(pin.begin(), pin.end(), r) != pin.end()) continue;
       uint32_t nu = next_use((uint32_t)reg_val[r]);
       if (best < 0 || nu > best_use) { best = (int)r; best_use = nu; }
     }
@@ -64,44 +192,49 @@ struct Allocator {
 
 }  // namespace
 
-Plan compile_plan(const Graph& g, const PlanOptions& opt) {
-  const size_t N = g.nodes.size();
+Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
   if (opt.n_regs < 4 || opt.n_regs > 4096) throw Error("plan: n_regs out of range");
   Plan plan;
   plan.n_regs = opt.n_regs;
-  plan.n_inputs = g.inputs_size;
-  plan.n_witness = (uint32_t)g.witness_signals.size();
-  plan.stats.graph_nodes = N;
-  plan.stats.graph_ops = g.n_ops();
+  plan.n_inputs = g0.inputs_size;
+  plan.n_witness = (uint32_t)g0.witness_signals.size();
+  plan.stats.graph_nodes = g0.nodes.size();
+  plan.stats.graph_ops = g0.n_ops();
+  {
+    std::vector<uint8_t> nd0 = liveness(g0);
+    for (size_t i = 0; i < g0.nodes.size(); i++) {
+      if (!nd0[i]) continue;
+      plan.stats.live_ops += g0.nodes[i].kind >= N_UNO;
+      plan.stats.div_nodes += g0.nodes[i].kind == N_DUO && g0.nodes[i].op == OP_DIV;
+      plan.stats.mul_nodes += g0.nodes[i].kind == N_DUO && g0.nodes[i].op == OP_MUL;
+    }
+  }
+  Graph rewritten;
+  const bool batch = opt.div_batch > 1 && plan.stats.div_nodes >= 2;
+  if (batch) rewritten = rewrite_div_batches(g0, opt.div_batch);
+  const Graph& g = batch ? rewritten : g0;
+  const size_t N = g.nodes.size();
+  const std::vector<uint8_t> needed = liveness(g);
 
-  // liveness from the witness backwards (dead nodes are unobservable: evaluate() is pure, graph.rs:367)
-  std::vector<uint8_t> needed(N, 0);
-  for (uint32_t s : g.witness_signals) needed[s] = 1;
-  for (size_t i = N; i-- > 0;) {
+  // constants: N_CONST nodes, and Input(0) which get_inputs_buffer forces to 1 (lib.rs:177-181).  const_val is the
+  // canonical value; table entries are interned on first use (raw for ordinary operands, pre-scaled for OP_DOT).
+  std::vector<uint8_t> is_const(N, 0);
+  std::vector<U256> const_val(N);
+  for (size_t i = 0; i < N; i++) {
     if (!needed[i]) continue;
     const Node& nd = g.nodes[i];
-    if (nd.kind >= N_UNO) needed[nd.a] = 1;
-    if (nd.kind >= N_DUO) needed[nd.b] = 1;
-    if (nd.kind == N_TRES) needed[nd.c] = 1;
+    if (nd.kind == N_CONST) { is_const[i] = 1; const_val[i] = g.constants.at(nd.a); }
+    else if (nd.kind == N_INPUT && nd.a == 0) { is_const[i] = 1; const_val[i] = u256_from_u64(1); }
+    else if (nd.kind == N_INPUT && nd.a >= g.inputs_size) throw Error("plan: input index out of range");
   }
-
-  // constants: N_CONST nodes, and Input(0) which get_inputs_buffer forces to 1 (lib.rs:177-181)
-  std::vector<int32_t> const_of(N, -1);
   std::map<U256, uint32_t> cix;
   auto intern = [&](const U256& v) {
     auto it = cix.find(v);
     if (it == cix.end()) { it = cix.emplace(v, (uint32_t)plan.consts.size()).first; plan.consts.push_back(v); }
-    return (int32_t)it->second;
+    return it->second;
   };
-  for (size_t i = 0; i < N; i++) {
-    if (!needed[i]) continue;
-    const Node& nd = g.nodes[i];
-    if (nd.kind == N_CONST) const_of[i] = intern(g.constants.at(nd.a));
-    else if (nd.kind == N_INPUT && nd.a == 0) const_of[i] = intern(u256_from_u64(1));
-    else if (nd.kind == N_INPUT && nd.a >= g.inputs_size) throw Error("plan: input index out of range");
-  }
 
-  // witness positions per node (CSR)
+  // witness positions per node (CSR), use counts and the single consumer of single-use values
   std::vector<uint32_t> out_start(N + 1, 0), out_list(g.witness_signals.size());
   for (uint32_t s : g.witness_signals) out_start[s + 1]++;
   for (size_t i = 0; i < N; i++) out_start[i + 1] += out_start[i];
@@ -109,161 +242,306 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt) {
     std::vector<uint32_t> fill(out_start.begin(), out_start.end() - 1);
     for (uint32_t j = 0; j < g.witness_signals.size(); j++) out_list[fill[g.witness_signals[j]]++] = j;
   }
+  std::vector<uint32_t> uses(N, 0), consumer(N, 0);
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i]) continue;
+    const Node& nd = g.nodes[i];
+    for (int k = 0; k < n_operands(nd); k++) { uses[operand(nd, k)]++; consumer[operand(nd, k)] = (uint32_t)i; }
+  }
+  auto n_out = [&](uint32_t i) { return out_start[i + 1] - out_start[i]; };
+  auto is_addsub = [&](uint32_t i) { const Node& nd = g.nodes[i]; return nd.kind == N_DUO && (nd.op == OP_ADD || nd.op == OP_SUB); };
 
-  auto operands = [&](const Node& nd, uint32_t* ops) {
-    int n = 0;
-    if (nd.kind >= N_UNO) ops[n++] = nd.a;
-    if (nd.kind >= N_DUO) ops[n++] = nd.b;
-    if (nd.kind == N_TRES) ops[n++] = nd.c;
-    return n;
+  // ---- macro-op list: linear-combination fusion ---------------------------------------------------------
+  const uint32_t max_terms = std::max(1u, std::min(std::min(opt.max_terms, DOT_MAX_TERMS), opt.n_regs - 3));
+  const double max_bound = 5.25;                       // 2^256 / M = 5.29: the reduced sum must fit 256 bits
+  std::vector<MOp> mops; mops.reserve(N);
+  std::vector<uint8_t> deferred(N, 0), absorbed(N, 0);
+  std::map<uint32_t, std::vector<PTerm>> dterms;       // term lists of deferred nodes
+  // Shr(x, k) with a constant 0 <= k < 254 whose only consumer is Band(., constant): one OP_SHRAND (Num2Bits, BinSum)
+  auto small_const = [&](uint32_t o, uint32_t* v) {
+    if (!is_const[o]) return false;
+    for (int k = 1; k < 8; k++) if (const_val[o].l[k]) return false;
+    *v = const_val[o].l[0];
+    return *v < 254u;
+  };
+  auto shr_absorbable = [&](uint32_t s) {
+    const Node& nd = g.nodes[s];
+    uint32_t k;
+    if (!(nd.kind == N_DUO && nd.op == OP_SHR && !is_const[nd.a] && small_const(nd.b, &k))) return false;
+    if (uses[s] != 1 || n_out(s) != 0 || !needed[consumer[s]]) return false;
+    const Node& c = g.nodes[consumer[s]];
+    if (!(c.kind == N_DUO && c.op == OP_BAND) || c.a == c.b) return false;
+    return is_const[c.a == s ? c.b : c.a] != 0;
+  };
+  auto emit_dot = [&](uint32_t node, std::vector<PTerm>& terms) {
+    MOp m; m.node = node; m.opc = OP_DOT; m.terms = std::move(terms);
+    double b = dot_bound(m.terms);
+    m.ncs = b <= 2.0 ? 1 : b <= 4.0 ? 2 : 3;
+    mops.push_back(std::move(m));
+  };
+  auto materialize = [&](uint32_t x) {
+    auto it = dterms.find(x);
+    emit_dot(x, it->second);
+    dterms.erase(it);
+    deferred[x] = 0;
+  };
+  for (size_t idx = 0; idx < N; idx++) {
+    const uint32_t i = (uint32_t)idx;
+    if (!needed[i] || is_const[i]) continue;
+    const Node& nd = g.nodes[i];
+    if (nd.kind == N_CONST) continue;
+    const bool mul_rc = opt.fuse_dot && nd.kind == N_DUO && nd.op == OP_MUL && (is_const[nd.a] != is_const[nd.b]);
+    const bool lin = opt.fuse_dot && is_addsub(i) && !(is_const[nd.a] && is_const[nd.b]);
+    if (mul_rc || lin) {
+      std::vector<PTerm> terms;
+      if (mul_rc) {
+        const uint32_t x = is_const[nd.a] ? nd.b : nd.a, c = is_const[nd.a] ? nd.a : nd.b;
+        terms.push_back(PTerm{0, false, x, const_val[c]});
+      } else {
+        for (int pass = 0; pass < 3; pass++) {
+          terms.clear();
+          for (int k = 0; k < 2; k++) {
+            const uint32_t o = operand(nd, k);
+            const bool neg = (k == 1 && nd.op == OP_SUB);
+            if (is_const[o]) terms.push_back(PTerm{2, neg, 0, const_val[o]});
+            else if (deferred[o]) { for (PTerm t : dterms[o]) { t.neg = (t.neg != neg); terms.push_back(t); } }
+            else terms.push_back(PTerm{1, neg, o, U256()});
+          }
+          if (terms.size() <= max_terms && dot_bound(terms) <= max_bound) break;
+          // over budget: turn the larger deferred operand into a plain value and retry
+          uint32_t victim = 0xFFFFFFFFu; size_t vsz = 0;
+          for (int k = 0; k < 2; k++) { uint32_t o = operand(nd, k); if (!is_const[o] && deferred[o] && dterms[o].size() >= vsz) { victim = o; vsz = dterms[o].size(); } }
+          if (victim == 0xFFFFFFFFu) break;
+          materialize(victim);
+        }
+        for (int k = 0; k < 2; k++) {                  // inlined operands are consumed
+          const uint32_t o = operand(nd, k);
+          if (!is_const[o] && deferred[o]) { dterms.erase(o); deferred[o] = 0; }
+        }
+      }
+      bool has_mac = false;
+      for (const PTerm& t : terms) has_mac |= (t.kind == 0);
+      if (has_mac) {
+        const bool can_defer = uses[i] == 1 && n_out(i) == 0 && is_addsub(consumer[i]) && needed[consumer[i]];
+        if (can_defer) { deferred[i] = 1; dterms[i] = std::move(terms); }
+        else emit_dot(i, terms);
+        continue;
+      }
+      // a plain Add/Sub of two values: regular op below
+    }
+    if (opt.fuse_dot && shr_absorbable(i)) { absorbed[i] = 1; continue; }
+    if (nd.kind == N_DUO && nd.op == OP_BAND && (absorbed[nd.a] || absorbed[nd.b])) {
+      const uint32_t s = absorbed[nd.a] ? nd.a : nd.b, c = absorbed[nd.a] ? nd.b : nd.a;
+      MOp m; m.node = i; m.opc = OP_SHRAND; m.n_in = 1; m.in[0] = g.nodes[s].a;
+      m.shift = const_val[g.nodes[s].b].l[0]; m.mask = const_val[c];
+      mops.push_back(m);
+      continue;
+    }
+    MOp m; m.node = i;
+    m.n_in = n_operands(nd);
+    for (int k = 0; k < m.n_in; k++) { m.in[k] = operand(nd, k); if (deferred[m.in[k]]) materialize(m.in[k]); }
+    if (nd.kind == N_INPUT) m.opc = OP_INPUT;
+    else if (nd.kind == N_UNO) m.opc = OP_NEG + nd.op;
+    else if (nd.kind == N_TRES) m.opc = OP_TERN;
+    else m.opc = (nd.op == OP_MUL && nd.a == nd.b && !is_const[nd.a]) ? (uint32_t)OP_SQR : nd.op;
+    mops.push_back(m);
+  }
+  if (!dterms.empty()) throw Error("plan: dangling deferred linear combination");
+
+  // value operands (non-constant nodes) of a macro op, without duplicates
+  auto value_operands = [&](const MOp& m, std::vector<uint32_t>& v) {
+    v.clear();
+    if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2 && std::find(v.begin(), v.end(), t.node) == v.end()) v.push_back(t.node); }
+    else for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]] && std::find(v.begin(), v.end(), m.in[k]) == v.end()) v.push_back(m.in[k]);
   };
 
-  // schedule: file order (any topological order is valid, graph.rs:343-356), except that an
-  // independent multiplication found within a small window is pulled up next to a multiplication so
-  // that the two can be issued as one pair (instruction-level parallelism inside a thread).
-  std::vector<uint32_t> order; order.reserve(N);
-  std::vector<int32_t> partner(N, -1);       // for the first node of a pair: the second one
-  {
-    std::vector<uint8_t> scheduled(N, 0);
-    auto is_mul = [&](size_t i) { const Node& nd = g.nodes[i]; return needed[i] && nd.kind == N_DUO && nd.op == OP_MUL && const_of[i] < 0; };
-    auto ready = [&](size_t j, size_t first) {
-      const Node& nd = g.nodes[j];
-      for (uint32_t x : {nd.a, nd.b}) {
-        if (x == first) return false;
-        if (const_of[x] < 0 && !scheduled[x]) return false;
+  // ---- pairing: instruction-level parallelism inside a thread ---------------------------------------------
+  // Large witnesses bound the number of resident threads (HBM capacity), so dependent carry chains cannot be hidden
+  // by other warps alone.  Two independent macro ops of the same class (value x value multiplications, or fused
+  // linear combinations) are issued as ONE bundle whose two instruction streams the kernel interleaves.  List
+  // scheduling: walk the ops in order; for an op of a pairable class pick, among the ops that are already READY
+  // (all operands computed), the next one of the same class; it runs ahead of its original position.
+  std::vector<uint32_t> vops;
+  std::vector<int32_t> pair_second(mops.size(), -1);     // in the NEW order: index of the op bundled with this one
+  if (opt.pair && mops.size() > 1) {
+    const size_t Mn = mops.size();
+    auto klass = [&](const MOp& m) { return (m.opc == OP_MUL || m.opc == OP_SQR) ? 1 : m.opc == OP_DOT ? 2 : 0; };
+    std::vector<int32_t> def_of(N, -1);
+    for (size_t k = 0; k < Mn; k++) def_of[mops[k].node] = (int32_t)k;
+    std::vector<uint32_t> pending(Mn, 0), succ_start(Mn + 1, 0), succ;
+    std::vector<std::vector<uint32_t>> preds(Mn);
+    for (size_t k = 0; k < Mn; k++) {
+      value_operands(mops[k], vops);
+      for (uint32_t x : vops) { int32_t d = def_of[x]; if (d < 0) throw Error("plan: operand without a definition"); preds[k].push_back((uint32_t)d); succ_start[d + 1]++; }
+      pending[k] = (uint32_t)preds[k].size();
+    }
+    for (size_t k = 0; k < Mn; k++) succ_start[k + 1] += succ_start[k];
+    succ.resize(succ_start[Mn]);
+    {
+      std::vector<uint32_t> fill(succ_start.begin(), succ_start.end() - 1);
+      for (size_t k = 0; k < Mn; k++) for (uint32_t d : preds[k]) succ[fill[d]++] = (uint32_t)k;
+    }
+    std::set<uint32_t> ready[3];
+    for (size_t k = 0; k < Mn; k++) if (pending[k] == 0 && klass(mops[k])) ready[klass(mops[k])].insert((uint32_t)k);
+    std::vector<uint8_t> done(Mn, 0);
+    std::vector<uint32_t> order; order.reserve(Mn);
+    std::vector<uint8_t> first_of_pair; first_of_pair.reserve(Mn);
+    auto schedule = [&](uint32_t k) {
+      done[k] = 1;
+      if (klass(mops[k])) ready[klass(mops[k])].erase(k);
+      for (uint32_t q = succ_start[k]; q < succ_start[k + 1]; q++) {
+        uint32_t c = succ[q];
+        if (--pending[c] == 0 && klass(mops[c])) ready[klass(mops[c])].insert(c);
       }
-      return true;
     };
-    for (size_t i = 0; i < N; i++) {
-      if (!needed[i] || scheduled[i]) continue;
-      scheduled[i] = 1; order.push_back((uint32_t)i);
-      if (!opt.pair_muls || !is_mul(i)) continue;
-      size_t end = std::min(N, i + 1 + (size_t)opt.pair_window);
-      for (size_t j = i + 1; j < end; j++) {
-        if (scheduled[j] || !is_mul(j) || !ready(j, i)) continue;
-        scheduled[j] = 1; order.push_back((uint32_t)j); partner[i] = (int32_t)j;
-        plan.stats.mul_pairs++;
-        break;
+    const uint32_t max_pair_terms = std::min(DOT_MAX_TERMS, opt.n_regs - 3);
+    for (uint32_t a = 0; a < Mn; a++) {
+      if (done[a]) continue;
+      const int ka = klass(mops[a]);
+      int32_t b = -1;
+      if (ka) {
+        for (auto it = ready[ka].upper_bound(a); it != ready[ka].end(); ++it) {
+          if (ka == 2 && mops[a].terms.size() + mops[*it].terms.size() > max_pair_terms) continue;
+          if (*it - a > opt.pair_distance) break;
+          b = (int32_t)*it; break;
+        }
+      }
+      order.push_back(a); first_of_pair.push_back(b >= 0);
+      if (b >= 0) { order.push_back((uint32_t)b); first_of_pair.push_back(0); }
+      schedule(a);
+      if (b >= 0) {
+        schedule((uint32_t)b);
+        // keep the run-ahead strand moving: unpairable ops (additions, selects ...) that only waited for b are
+        // issued right away, otherwise the strand would stall until the cursor reaches them
+        std::vector<uint32_t> work(1, (uint32_t)b);
+        while (!work.empty()) {
+          const uint32_t x = work.back(); work.pop_back();
+          for (uint32_t q = succ_start[x]; q < succ_start[x + 1]; q++) {
+            const uint32_t c = succ[q];
+            if (done[c] || pending[c] != 0 || klass(mops[c]) != 0) continue;
+            order.push_back(c); first_of_pair.push_back(0);
+            schedule(c);
+            work.push_back(c);
+          }
+        }
       }
     }
+    std::vector<MOp> re; re.reserve(Mn);
+    for (size_t k = 0; k < order.size(); k++) { re.push_back(std::move(mops[order[k]])); if (first_of_pair[k]) pair_second[k] = (int32_t)k + 1; }
+    mops.swap(re);
   }
-  std::vector<uint32_t> pos(N, 0);
-  for (size_t p = 0; p < order.size(); p++) pos[order[p]] = (uint32_t)p;
 
-  // use lists of non-constant values as schedule positions of their consumers (CSR, ascending)
+  // use lists of values as macro-op positions of their consumers (CSR, ascending)
   std::vector<uint32_t> use_start(N + 1, 0);
-  for (uint32_t i : order) {
-    uint32_t ops[3]; int n = operands(g.nodes[i], ops);
-    for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) use_start[ops[k] + 1]++;
-  }
+  for (const MOp& m : mops) { value_operands(m, vops); for (uint32_t x : vops) use_start[x + 1]++; }
   for (size_t i = 0; i < N; i++) use_start[i + 1] += use_start[i];
   std::vector<uint32_t> use_list(use_start[N]);
   {
     std::vector<uint32_t> fill(use_start.begin(), use_start.end() - 1);
-    for (uint32_t i : order) {
-      uint32_t ops[3]; int n = operands(g.nodes[i], ops);
-      for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) use_list[fill[ops[k]]++] = pos[i];
-    }
+    for (size_t p = 0; p < mops.size(); p++) { value_operands(mops[p], vops); for (uint32_t x : vops) use_list[fill[x]++] = (uint32_t)p; }
   }
 
+  // constants that are witness signals themselves (e.g. witness[0] = Input(0) = 1)
   Allocator al(N, opt.n_regs, use_start, use_list, plan);
-  plan.code.reserve(N + N / 4);
-  uint32_t live = 0;
+  plan.code.reserve(mops.size() + mops.size() / 2);
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i] || !is_const[i]) continue;
+    for (uint32_t k = out_start[i]; k < out_start[i + 1]; k++) { al.emit(make_instr(OP_OUT, F_A_CONST, NO_DST, intern(const_val[i]), 0, out_list[k])); plan.stats.outs++; }
+  }
 
-  struct Enc { uint32_t op, flags, dst, a, b, w; bool need_reg, has_uses, out_inline; };
-  // phase 1 of one node: operands resident (registers in `pinned` stay put); returns encodings of operands
-  auto load_operands = [&](uint32_t i, uint32_t* enc, uint32_t& flags, uint32_t* pinned, int& n_pin) {
-    const Node& nd = g.nodes[i];
-    uint32_t ops[3]; int n_ops = operands(nd, ops);
-    for (int k = 0; k < n_ops; k++) {
-      uint32_t x = ops[k];
-      if (const_of[x] >= 0) { enc[k] = (uint32_t)const_of[x]; flags |= (F_A_CONST << k); continue; }
+  uint32_t live = 0;
+  std::vector<uint32_t> pinned, uvops;
+  struct Enc { uint32_t enc[3]; uint32_t flags; std::vector<Instr> term_slots; };
+  for (size_t p = 0; p < mops.size();) {
+    const int n_unit = pair_second[p] >= 0 ? 2 : 1;          // a bundle is allocated like ONE instruction
+    const size_t last = p + n_unit - 1;
+    // operands of the whole unit resident
+    pinned.clear(); uvops.clear();
+    for (int u = 0; u < n_unit; u++) { value_operands(mops[p + u], vops); for (uint32_t x : vops) if (std::find(uvops.begin(), uvops.end(), x) == uvops.end()) uvops.push_back(x); }
+    for (uint32_t x : uvops) {
       if (al.reg_of[x] < 0) {
         if (al.spill_of[x] < 0) throw Error("plan: operand neither resident nor spilled");
-        uint32_t r = al.alloc_reg(pinned, n_pin);
+        uint32_t r = al.alloc_reg(pinned);
         al.emit(make_instr(OP_SPILL_LD, 0, r, (uint32_t)al.spill_of[x], 0, 0));
         plan.stats.spill_ld++;
         al.bind(x, r);
       }
-      enc[k] = (uint32_t)al.reg_of[x];
-      pinned[n_pin++] = enc[k];
+      pinned.push_back((uint32_t)al.reg_of[x]);
     }
-  };
-  // phase 2: consume the uses up to schedule position `upto`; operands that die give their register back
-  auto retire_operands = [&](uint32_t i, uint32_t upto) {
-    const Node& nd = g.nodes[i];
-    uint32_t ops[3]; int n_ops = operands(nd, ops);
-    for (int k = 0; k < n_ops; k++) {
-      uint32_t x = ops[k];
-      if (const_of[x] >= 0) continue;
-      while (al.use_ptr[x] < use_start[x + 1] && use_list[al.use_ptr[x]] <= upto) al.use_ptr[x]++;
+    // operand encodings (before the operands are retired)
+    Enc encs[2];
+    for (int u = 0; u < n_unit; u++) {
+      const MOp& m = mops[p + u];
+      Enc& e = encs[u]; e.enc[0] = e.enc[1] = e.enc[2] = 0; e.flags = 0;
+      if (m.opc == OP_DOT) {
+        std::vector<uint32_t> words;
+        for (const PTerm& t : m.terms) {
+          uint32_t kind = t.kind == 0 ? (uint32_t)T_MAC : t.kind == 2 ? (uint32_t)T_CONST : (t.neg ? (uint32_t)T_SUBHI : (uint32_t)T_ADDHI);
+          uint32_t reg = t.kind == 2 ? 0u : (uint32_t)al.reg_of[t.node];
+          uint32_t ci = t.kind == 1 ? 0u : intern(prescale(t.c, t.neg));
+          words.push_back(kind | (reg << 16)); words.push_back(ci);
+          plan.stats.dot_terms[kind]++;
+        }
+        if (words.size() & 2) { words.push_back(0); words.push_back(0); }
+        for (size_t k = 0; k < words.size(); k += 4) { Instr sl; sl.x = words[k]; sl.y = words[k + 1]; sl.z = words[k + 2]; sl.w = words[k + 3]; e.term_slots.push_back(sl); }
+      } else if (m.opc == OP_INPUT) {
+        e.enc[0] = g.nodes[m.node].a;
+      } else if (m.opc == OP_SHRAND) {
+        e.enc[0] = (uint32_t)al.reg_of[m.in[0]];
+        e.enc[1] = m.shift | (intern(m.mask) << 8);
+      } else {
+        for (int k = 0; k < m.n_in; k++) {
+          if (is_const[m.in[k]]) { e.enc[k] = intern(const_val[m.in[k]]); e.flags |= (F_A_CONST << k); }
+          else e.enc[k] = (uint32_t)al.reg_of[m.in[k]];
+        }
+      }
     }
-    for (int k = 0; k < n_ops; k++) {
-      uint32_t x = ops[k];
-      if (const_of[x] >= 0 || al.has_uses(x)) continue;
+    // retire operands: consume the uses of this unit; operands that die give their register back
+    for (uint32_t x : uvops) while (al.use_ptr[x] < use_start[x + 1] && use_list[al.use_ptr[x]] <= last) al.use_ptr[x]++;
+    for (uint32_t x : uvops) {
+      if (al.has_uses(x)) continue;
       if (al.reg_of[x] >= 0 || al.spill_of[x] >= 0) { al.release(x); live--; }
     }
-  };
-
-  for (size_t p = 0; p < order.size(); p++) {
-    const uint32_t i = order[p];
-    const Node& nd = g.nodes[i];
-    const uint32_t n_out = out_start[i + 1] - out_start[i];
-    const uint32_t* outs = &out_list[out_start[i]];
-
-    if (const_of[i] >= 0) {                 // constants never occupy a register
-      for (uint32_t k = 0; k < n_out; k++) { al.emit(make_instr(OP_OUT, F_A_CONST, NO_DST, (uint32_t)const_of[i], 0, outs[k])); plan.stats.outs++; }
-      continue;
-    }
-    if (nd.kind == N_CONST) continue;
-    if (nd.kind >= N_UNO) plan.stats.live_ops++;
-
-    const int n_nodes_here = partner[i] >= 0 ? 2 : 1;
-    uint32_t ids[2] = {i, partner[i] >= 0 ? (uint32_t)partner[i] : 0u};
-    if (n_nodes_here == 2) { plan.stats.live_ops++; p++; }       // the partner is order[p + 1]
-    uint32_t enc[2][3] = {{0, 0, 0}, {0, 0, 0}}; uint32_t flags[2] = {0, 0};
-    uint32_t pinned[8]; int n_pin = 0;
-    for (int s = 0; s < n_nodes_here; s++) load_operands(ids[s], enc[s], flags[s], pinned, n_pin);
-    for (int s = 0; s < n_nodes_here; s++) retire_operands(ids[s], pos[ids[n_nodes_here - 1]]);
-
+    // destinations (the second one must not evict the first)
     uint32_t dsts[2] = {NO_DST, NO_DST}; bool need_reg[2], has_uses[2], out_inline[2];
-    uint32_t dpin[2]; int n_dpin = 0;
-    for (int s = 0; s < n_nodes_here; s++) {
-      const uint32_t id = ids[s];
-      const uint32_t no = out_start[id + 1] - out_start[id];
-      has_uses[s] = al.has_uses(id);
-      out_inline[s] = no >= 1 && g.nodes[id].kind != N_TRES;       // .w is operand c for TernCond
-      need_reg[s] = has_uses[s] || no > (out_inline[s] ? 1u : 0u);
-      if (need_reg[s]) {
-        dsts[s] = al.alloc_reg(dpin, n_dpin); al.bind(id, dsts[s]); dpin[n_dpin++] = dsts[s];
+    pinned.clear();
+    for (int u = 0; u < n_unit; u++) {
+      const MOp& m = mops[p + u];
+      const uint32_t no = n_out(m.node);
+      has_uses[u] = al.has_uses(m.node);
+      out_inline[u] = no >= 1 && m.opc != OP_TERN;             // .w is operand c for TernCond
+      need_reg[u] = has_uses[u] || no > (out_inline[u] ? 1u : 0u);
+      if (need_reg[u]) {
+        dsts[u] = al.alloc_reg(pinned); al.bind(m.node, dsts[u]); pinned.push_back(dsts[u]);
         live++; plan.stats.max_live = std::max(plan.stats.max_live, live);
       }
     }
-    if (n_nodes_here == 2 && (plan.code.size() & 31) == 31) al.emit(make_instr(OP_NOP, 0, NO_DST, 0, 0, 0));
-    for (int s = 0; s < n_nodes_here; s++) {
-      const uint32_t id = ids[s];
-      const Node& n2 = g.nodes[id];
-      const uint32_t* o2 = &out_list[out_start[id]];
-      uint32_t op;
-      if (n2.kind == N_INPUT) { op = OP_INPUT; enc[s][0] = n2.a; }
-      else if (n2.kind == N_UNO) op = OP_NEG + n2.op;
-      else if (n2.kind == N_TRES) op = OP_TERN;
-      else op = (n2.op == OP_MUL && n2.a == n2.b && !(flags[s] & F_A_CONST)) ? (uint32_t)OP_SQR : n2.op;
-      uint32_t w = n2.kind == N_TRES ? enc[s][2] : (out_inline[s] ? o2[0] : 0);
-      if (out_inline[s]) { flags[s] |= F_OUT; plan.stats.outs++; }
-      if (n_nodes_here == 2 && s == 0) flags[s] |= F_PAIR;
-      al.emit(make_instr(op, flags[s], dsts[s], enc[s][0], enc[s][1], w));
+    for (int u = 0; u < n_unit; u++) {
+      const MOp& m = mops[p + u];
+      Enc& e = encs[u];
+      const uint32_t* outs = &out_list[out_start[m.node]];
+      if (out_inline[u]) { e.flags |= F_OUT; plan.stats.outs++; }
+      if (n_unit == 2 && u == 0) { e.flags |= F_PAIR; plan.stats.pairs++; if (m.opc == OP_DOT) plan.stats.pairs_dot++; }
+      if (m.opc == OP_DOT) {
+        al.emit(make_instr(OP_DOT, e.flags, dsts[u], (uint32_t)m.terms.size() | (m.ncs << 8), 0, out_inline[u] ? outs[0] : 0));
+        for (const Instr& sl : e.term_slots) plan.code.push_back(sl);
+      } else {
+        const uint32_t w = m.opc == OP_TERN ? e.enc[2] : (out_inline[u] ? outs[0] : 0);
+        al.emit(make_instr(m.opc, e.flags, dsts[u], e.enc[0], e.enc[1], w));
+      }
+      if (m.opc == OP_DIV || m.opc == OP_INV) plan.stats.inversions++;
     }
-    for (int s = 0; s < n_nodes_here; s++) {
-      const uint32_t id = ids[s];
-      const uint32_t no = out_start[id + 1] - out_start[id];
-      const uint32_t* o2 = &out_list[out_start[id]];
-      for (uint32_t k = out_inline[s] ? 1u : 0u; k < no; k++) { al.emit(make_instr(OP_OUT, 0, NO_DST, dsts[s], 0, o2[k])); plan.stats.outs++; }
-      if (need_reg[s] && !has_uses[s]) { al.release(id); live--; }
+    for (int u = 0; u < n_unit; u++) {
+      const MOp& m = mops[p + u];
+      const uint32_t no = n_out(m.node);
+      const uint32_t* outs = &out_list[out_start[m.node]];
+      for (uint32_t k = out_inline[u] ? 1u : 0u; k < no; k++) { al.emit(make_instr(OP_OUT, 0, NO_DST, dsts[u], 0, outs[k])); plan.stats.outs++; }
+      if (need_reg[u] && !has_uses[u]) { al.release(m.node); live--; }
     }
+    p += n_unit;
   }
   plan.n_spill = al.n_spill;
-  plan.stats.instrs = plan.code.size();
+  plan.stats.slots = plan.code.size();
   if (plan.consts.empty()) plan.consts.push_back(u256_from_u64(0));
   return plan;
 }

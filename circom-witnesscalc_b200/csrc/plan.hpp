@@ -6,6 +6,14 @@
 // instruction stream over a small per-witness register file (shared memory on the device) with
 // Belady-style spilling to a witness-major spill area in HBM.  Dead nodes are dropped, constants go
 // to a deduplicated table, witness positions are attached to the defining instruction.
+//
+// Two graph-level rewrites run first (both preserve every node value bit for bit):
+//   * Div batching: Div nodes on the same "division level" are independent, so groups of up to
+//     `div_batch` of them share ONE modular inversion (Montgomery's trick: 4k-3 multiplications + 1
+//     inversion instead of k inversions), with b == 0 -> 0 kept exact (graph.rs:109).
+//   * Linear-combination fusion: trees of Add/Sub whose inner nodes are single-use temporaries and whose
+//     leaves are Mul(value, constant) become one OP_DOT: products are accumulated in 512 bits and
+//     reduced once (the reference's build-circuit emits `lc += c * x` chains).
 #pragma once
 #include "graph.hpp"
 #include "isa.h"
@@ -13,21 +21,28 @@
 namespace gw {
 
 struct PlanOptions {
-  uint32_t n_regs = 12;      // per-witness registers kept in shared memory (12 x 32 B x 128 threads = 48 KB per CTA: 4 CTAs/SM)
-  bool pair_muls = true;     // schedule independent multiplications next to each other and issue them as pairs
-  uint32_t pair_window = 24; // how far ahead (in nodes) a partner is searched
+  uint32_t n_regs = 16;      // per-witness registers kept in shared memory
+  uint32_t div_batch = 8;    // max Div nodes sharing one inversion (1 = off)
+  bool fuse_dot = true;      // fuse linear combinations into OP_DOT
+  uint32_t max_terms = 8;    // max terms of one OP_DOT (<= DOT_MAX_TERMS, <= n_regs - 3)
+  bool pair = true;          // bundle two independent multiplications / linear combinations (F_PAIR)
+  uint32_t pair_distance = 1u << 30;   // how far ahead (in macro ops) a partner may be taken from
 };
 
 struct PlanStats {
   uint64_t graph_nodes = 0, graph_ops = 0;   // ops = Op + UnoOp + TresOp nodes of the file (node-ops/s metric)
-  uint64_t live_ops = 0;                     // ops reachable from the witness
-  uint64_t instrs = 0, spill_st = 0, spill_ld = 0, outs = 0, mul_pairs = 0;
-  uint64_t op_count[64] = {0};               // executed instructions by opcode
+  uint64_t live_ops = 0;                     // ops of the file reachable from the witness
+  uint64_t instrs = 0, slots = 0, spill_st = 0, spill_ld = 0, outs = 0, pairs = 0, pairs_dot = 0;
+  uint64_t op_count[64] = {0};               // emitted instructions by opcode
+  uint64_t dot_terms[4] = {0, 0, 0, 0};      // emitted OP_DOT terms by TermKind
+  uint64_t inversions = 0;                   // modular inversions per witness (OP_DIV + OP_INV)
+  uint64_t div_nodes = 0;                    // live Div nodes of the graph
+  uint64_t mul_nodes = 0;                    // live Mul nodes of the graph
   uint32_t max_live = 0;                     // peak number of simultaneously live values
 };
 
 struct Plan {
-  std::vector<Instr> code;
+  std::vector<Instr> code;   // slots
   std::vector<U256> consts;
   uint32_t n_regs = 0, n_spill = 0;
   uint32_t n_inputs = 0;     // I: length of the input buffer incl. slot 0

@@ -63,10 +63,19 @@ typedef struct {
   uint32_t n_instrs;      /* device instructions per witness */
   uint32_t n_regs;        /* per-witness registers in shared memory */
   uint32_t n_spill;       /* per-witness spill slots in HBM */
-  uint64_t n_mul;         /* field multiplications per witness (Mul) */
-  uint64_t n_div;         /* field divisions per witness (Div) */
+  uint64_t n_mul;         /* live Mul nodes of the graph (field multiplications per witness, algorithmic) */
+  uint64_t n_div;         /* live Div nodes of the graph (field divisions per witness, algorithmic) */
   uint64_t n_spill_ld;    /* spill loads per witness */
   uint64_t n_spill_st;    /* spill stores per witness */
+  /* what the plan compiler made of it (per witness) */
+  uint32_t n_slots;       /* 16-byte program slots */
+  uint32_t n_dot;         /* fused linear combinations (one Montgomery reduction each) */
+  uint32_t n_dot_mac;     /* value x constant products inside them */
+  uint32_t n_mul_instr;   /* value x value multiplications (Barrett) */
+  uint32_t n_inversions;  /* modular inversions after Div batching */
+  uint32_t threads;       /* threads per CTA */
+  uint32_t sets_per_thread; /* input sets evaluated per thread */
+  uint32_t reserved;
 } gw_graph_info_t;
 
 /* replaces storage::deserialize_witnesscalc_graph (src/storage.rs:214-249) + upload; parse once */

@@ -21,69 +21,102 @@ static fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 
 extern "C" {
 
-SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int pair, char* err, size_t errlen);
+// flags: bit 0 = fuse linear combinations (OP_DOT), bit 1 = NO pairing, bits 8.. = div_batch (0 -> default)
+SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags, char* err, size_t errlen);
 SimGraph* sim_load(const uint8_t* data, size_t len, uint32_t n_regs, char* err, size_t errlen) {
   return sim_load2(data, len, n_regs, 1, err, errlen);
 }
-SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int pair, char* err, size_t errlen) {
+SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags, char* err, size_t errlen) {
   try {
     std::unique_ptr<SimGraph> s(new SimGraph());
     s->g = deserialize_witnesscalc_graph(data, len);
-    PlanOptions o; o.n_regs = n_regs; o.pair_muls = pair != 0;
+    PlanOptions o; o.n_regs = n_regs; o.fuse_dot = (flags & 1) != 0; o.pair = (flags & 2) == 0;
+    if (flags >> 8) o.div_batch = (uint32_t)(flags >> 8);
     s->plan = compile_plan(s->g, o);
     return s.release();
   } catch (const std::exception& e) { if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; } return nullptr; }
 }
 void sim_free(SimGraph* s) { delete s; }
 void sim_info(SimGraph* s, uint64_t* out) {
-  out[0] = s->g.nodes.size(); out[1] = s->plan.n_inputs; out[2] = s->plan.n_witness; out[3] = s->plan.code.size();
-  out[4] = s->plan.n_regs; out[5] = s->plan.n_spill; out[6] = s->plan.stats.spill_ld; out[7] = s->plan.stats.spill_st;
-  out[8] = s->plan.stats.max_live; out[9] = s->plan.consts.size(); out[10] = s->plan.stats.live_ops; out[11] = s->plan.stats.graph_ops;
-  out[12] = s->plan.stats.mul_pairs;
+  const PlanStats& st = s->plan.stats;
+  out[0] = s->g.nodes.size(); out[1] = s->plan.n_inputs; out[2] = s->plan.n_witness; out[3] = st.instrs;
+  out[4] = s->plan.n_regs; out[5] = s->plan.n_spill; out[6] = st.spill_ld; out[7] = st.spill_st;
+  out[8] = st.max_live; out[9] = s->plan.consts.size(); out[10] = st.live_ops; out[11] = st.graph_ops;
+  out[12] = st.op_count[OP_DOT]; out[13] = st.dot_terms[T_MAC]; out[14] = st.inversions; out[15] = st.div_nodes;
+  out[16] = st.slots; out[17] = st.op_count[OP_MUL] + st.op_count[OP_SQR]; out[18] = st.op_count[OP_ADD] + st.op_count[OP_SUB];
+  out[19] = st.pairs; out[20] = st.pairs_dot;
 }
 // inputs: I x 32 B, witness: W x 32 B; returns status bits, or -1 on a malformed plan
 int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
   const Plan& p = s->plan;
   std::vector<fe> rf(p.n_regs, fe_zero()), spill(p.n_spill, fe_zero());
   uint32_t st = 0;
-  for (size_t pc = 0; pc < p.code.size(); pc++) {
+  // value of one instruction from the CURRENT register file (no writes); false on a malformed instruction
+  auto compute = [&](const Instr& ins, const Instr* tail, fe* out) {
+    const uint32_t op = ins.x & 0xFF;
+    fe A = fe_zero(), B = fe_zero(), C = fe_zero();
+    auto load = [&](uint32_t idx, bool is_const, fe* o) { if (is_const) { if (idx >= p.consts.size()) return false; *o = to_fe(p.consts[idx]); } else { if (idx >= p.n_regs) return false; *o = rf[idx]; } return true; };
+    if (op == OP_SPILL_LD) { if (ins.y >= p.n_spill) return false; *out = spill[ins.y]; return true; }
+    if (op == OP_INPUT) {
+      if (ins.y >= p.n_inputs) return false;
+      fe v; memcpy(v.l, inputs + 32 * (size_t)ins.y, 32);
+      *out = fe_reduce256(v); return true;
+    }
+    if (op == OP_DOT) {
+      const uint32_t nt = ins.y & 0xFF, ncs = (ins.y >> 8) & 0xFF;
+      if (nt == 0 || nt > DOT_MAX_TERMS || ncs < 1 || ncs > 3) return false;
+      uint32_t P[16]; for (int k = 0; k < 16; k++) P[k] = 0;
+      for (uint32_t t = 0; t < nt; t++) {
+        const Instr& sl = tail[t >> 1];
+        const uint32_t lo = (t & 1) ? sl.z : sl.x, ci = (t & 1) ? sl.w : sl.y;
+        const uint32_t kind = lo & 0xF, reg = lo >> 16;
+        if (kind > T_CONST || reg >= p.n_regs || ci >= p.consts.size()) return false;
+        dot_term(P, kind, rf[reg], to_fe(p.consts[ci]));
+      }
+      *out = fe_mont_reduce(P, (int)ncs); return true;
+    }
+    if (op == OP_SHRAND) {
+      if (ins.y >= p.n_regs || (ins.z >> 8) >= p.consts.size()) return false;
+      *out = fe_shr_and(rf[ins.y], ins.z & 0xFF, to_fe(p.consts[ins.z >> 8])); return true;
+    }
+    if (!load(ins.y, ins.x & F_A_CONST, &A)) return false;
+    if (op == OP_OUT) { *out = A; return true; }
+    if (op_has_b(op) && !load(ins.z, ins.x & F_B_CONST, &B)) return false;
+    if (op == OP_TERN && !load(ins.w, ins.x & F_C_CONST, &C)) return false;
+    *out = alu_exec(op, A, B, C, st);
+    return true;
+  };
+  auto commit = [&](const Instr& ins, const fe& R) {
+    const uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
+    if (op == OP_OUT) { if (ins.w >= p.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); return true; }
+    if (dst != NO_DST) { if (dst >= p.n_regs) return false; rf[dst] = R; }
+    if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
+    return true;
+  };
+  auto pairable = [](uint32_t op) { return op == OP_MUL || op == OP_SQR || op == OP_DOT; };
+  for (size_t pc = 0; pc < p.code.size();) {
     const Instr& ins = p.code[pc];
-    uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
-    if (op == OP_NOP) continue;
-    if (ins.x & F_PAIR) {                       // pair semantics: read all four operands, then write
-      if (pc + 1 >= p.code.size() || (pc & 31) == 31) return -1;
-      const Instr& in2 = p.code[++pc];
-      auto ld = [&](uint32_t idx, bool is_const, fe* o) { if (is_const) { if (idx >= p.consts.size()) return false; *o = to_fe(p.consts[idx]); } else { if (idx >= p.n_regs) return false; *o = rf[idx]; } return true; };
-      fe A1, B1, A2, B2, R1, R2;
-      uint32_t op2 = in2.x & 0xFF, dst2 = in2.x >> 16;
-      if ((op != OP_MUL && op != OP_SQR) || (op2 != OP_MUL && op2 != OP_SQR)) return -1;
-      if (!ld(ins.y, ins.x & F_A_CONST, &A1) || !ld(in2.y, in2.x & F_A_CONST, &A2)) return -1;
-      if (op == OP_SQR) B1 = A1; else if (!ld(ins.z, ins.x & F_B_CONST, &B1)) return -1;
-      if (op2 == OP_SQR) B2 = A2; else if (!ld(in2.z, in2.x & F_B_CONST, &B2)) return -1;
-      fe_mul2(A1, B1, A2, B2, R1, R2);
-      if (dst != NO_DST) { if (dst >= p.n_regs) return -1; rf[dst] = R1; }
-      if (dst2 != NO_DST) { if (dst2 >= p.n_regs) return -1; rf[dst2] = R2; }
-      if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, R1.l, 32); }
-      if (in2.x & F_OUT) { if (in2.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)in2.w, R2.l, 32); }
+    const uint32_t len = instr_slots(ins);
+    if (pc + len > p.code.size()) return -1;
+    const uint32_t op = ins.x & 0xFF;
+    if (ins.x & F_PAIR) {
+      // bundle: both instructions read the register file before either writes
+      if (pc + len >= p.code.size()) return -1;
+      const Instr& in2 = p.code[pc + len];
+      const uint32_t len2 = instr_slots(in2), op2 = in2.x & 0xFF;
+      if (pc + len + len2 > p.code.size() || (in2.x & F_PAIR)) return -1;
+      if (!pairable(op) || !pairable(op2) || (op == OP_DOT) != (op2 == OP_DOT)) return -1;
+      fe R1, R2;
+      if (!compute(ins, &p.code[pc + 1], &R1) || !compute(in2, &p.code[pc + len + 1], &R2)) return -1;
+      if (!commit(ins, R1) || !commit(in2, R2)) return -1;
+      pc += len + len2;
       continue;
     }
-    fe A = fe_zero(), B = fe_zero(), C = fe_zero(), R;
+    pc += len;
+    if (op == OP_NOP) continue;
     if (op == OP_SPILL_ST) { if (ins.y >= p.n_regs || ins.z >= p.n_spill) return -1; spill[ins.z] = rf[ins.y]; continue; }
-    if (op == OP_SPILL_LD) { if (dst >= p.n_regs || ins.y >= p.n_spill) return -1; rf[dst] = spill[ins.y]; continue; }
-    if (op == OP_INPUT) {
-      if (ins.y >= p.n_inputs) return -1;
-      fe v; memcpy(v.l, inputs + 32 * (size_t)ins.y, 32);
-      R = fe_reduce256(v);
-    } else {
-      auto load = [&](uint32_t idx, bool is_const, fe* o) { if (is_const) { if (idx >= p.consts.size()) return false; *o = to_fe(p.consts[idx]); } else { if (idx >= p.n_regs) return false; *o = rf[idx]; } return true; };
-      if (!load(ins.y, ins.x & F_A_CONST, &A)) return -1;
-      if (op == OP_OUT) { if (ins.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, A.l, 32); continue; }
-      if (op_has_b(op) && !load(ins.z, ins.x & F_B_CONST, &B)) return -1;
-      if (op == OP_TERN && !load(ins.w, ins.x & F_C_CONST, &C)) return -1;
-      R = alu_exec(op, A, B, C, st);
-    }
-    if (dst != NO_DST) { if (dst >= p.n_regs) return -1; rf[dst] = R; }
-    if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
+    fe R;
+    if (!compute(ins, &p.code[pc - len + 1], &R) || !commit(ins, R)) return -1;
   }
   return st;
 }

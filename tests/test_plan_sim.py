@@ -68,3 +68,82 @@ def test_golden_circuits(name, n_regs):
     assert st == 0 and po.wtns_from_witness(got) == util.golden_wtns(name)
     man = util.manifest()[name]
     assert g.info["W"] == man["n_witness"] and g.info["I"] == man["n_inputs"] and g.info["n_nodes"] == man["n_nodes"]
+
+
+def _lc_graph(rnd, n_ops=300, n_inputs=6):
+    """Graphs dominated by the patterns the plan compiler rewrites: Mul(value, const) feeding Add/Sub trees
+    (-> OP_DOT) and Div nodes (-> batched inversion), with extreme constants / values."""
+    nodes = [(po.K_INPUT, i) for i in range(n_inputs + 1)]
+    consts = []
+    for v in [0, 1, 2, po.M - 1, po.M - 2, (po.M >> 1), 1 << 253] + [util.random_value(rnd) for _ in range(10)]:
+        consts.append(len(nodes))
+        nodes.append((po.K_CONST, v % po.M))
+    vals = list(range(1, n_inputs + 1))
+    for _ in range(n_ops):
+        n = len(nodes)
+        r = rnd.random()
+        pick = lambda: rnd.choice(vals[-12:]) if rnd.random() < 0.7 else rnd.choice(vals)
+        if r < 0.35:
+            nodes.append((po.K_DUO, po.DUO["Mul"], pick(), rnd.choice(consts)) if rnd.random() < 0.5
+                         else (po.K_DUO, po.DUO["Mul"], rnd.choice(consts), pick()))
+        elif r < 0.75:
+            a = pick() if rnd.random() < 0.85 else rnd.choice(consts)
+            b = pick() if rnd.random() < 0.85 else rnd.choice(consts)
+            nodes.append((po.K_DUO, po.DUO["Add" if rnd.random() < 0.6 else "Sub"], a, b))
+        elif r < 0.87:
+            a = pick() if rnd.random() < 0.7 else consts[1]
+            nodes.append((po.K_DUO, po.DUO["Div"], a, pick()))
+        elif r < 0.93:
+            nodes.append((po.K_DUO, po.DUO["Mul"], pick(), pick()))
+        else:
+            nodes.append((po.K_DUO, po.DUO["Sub"], pick(), pick()))         # x - x = 0 now and then: Div by zero below
+        vals.append(n)
+    n = len(nodes)
+    wit = [0] + [rnd.randrange(n) for _ in range(25)] + list(range(n - 8, n))
+    return nodes, wit, {"x": (1, n_inputs)}
+
+
+@pytest.mark.parametrize("n_regs,div_batch", [(6, 2), (12, 8), (16, 3), (32, 16)])
+def test_linear_combination_fusion_and_div_batching(n_regs, div_batch):
+    rnd = random.Random(7000 + n_regs)
+    fused = batched = 0
+    for t in range(20):
+        nodes, wit, imap = _lc_graph(rnd)
+        data = po.serialize_graph(nodes, wit, imap)
+        g = util.SimGraph(data, n_regs, fuse=True, div_batch=div_batch)
+        plain = util.SimGraph(data, n_regs, fuse=False, div_batch=1, pair=False)
+        assert plain.info["n_dot"] == 0 and plain.info["inversions"] == plain.info["div_nodes"]
+        for row in range(4):
+            inp = [1] + [rnd.choice([0, 1, po.M - 1, po.M - 2, (1 << 256) - 1]) if rnd.random() < 0.4 else util.random_value(rnd)
+                         for _ in range(6)]
+            want = po.evaluate(nodes, inp, wit, "circom")
+            assert g.eval(inp)[0] == want, (t, row)
+            assert plain.eval(inp)[0] == want, (t, row)
+        fused += g.info["n_dot"]
+        batched += g.info["div_nodes"] - g.info["inversions"]
+    assert fused > 0 and batched > 0
+
+
+def test_dot_worst_case_bounds():
+    """every term at its maximum (value M-1, constant M-1 -> largest products) for each term count / kind mix the
+    compiler may emit: the reduced sum must stay exact"""
+    M = po.M
+    for n_mac in range(0, 9):
+        for n_plain in range(0, 5):
+            if n_mac == 0:
+                continue
+            nodes = [(po.K_INPUT, 0), (po.K_INPUT, 1), (po.K_CONST, M - 1), (po.K_CONST, 1)]
+            acc = None
+            for _ in range(n_mac):
+                nodes.append((po.K_DUO, po.DUO["Mul"], 1, 2))
+                m = len(nodes) - 1
+                if acc is None:
+                    acc = m
+                else:
+                    nodes.append((po.K_DUO, po.DUO["Add"], acc, m)); acc = len(nodes) - 1
+            for k in range(n_plain):
+                nodes.append((po.K_DUO, po.DUO["Add" if k % 2 == 0 else "Sub"], acc, 1)); acc = len(nodes) - 1
+            wit = [0, acc]
+            g = util.SimGraph(po.serialize_graph(nodes, wit, {"x": (1, 1)}), 16)
+            for x in (M - 1, 0, 1, M - 2):
+                assert g.eval([1, x])[0] == po.evaluate(nodes, [1, x], wit, "circom"), (n_mac, n_plain, x)

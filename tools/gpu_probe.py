@@ -31,6 +31,8 @@ for name in a.circuits.split(","):
     g = cwc.Graph(util.golden_graph(name))
     I, W = g.n_inputs, g.n_witness
     B = a.batch or max(1024, min(148 * 256 * 2, int(110e9 // (32 * W))))
+    if a.batch and not os.environ.get("GW_DEBUG_OUT_WRAP"):
+        B = min(B, int(150e9 // (32 * W)))
     rng = np.random.default_rng(9)
     vals = util.random_field_batch(rng, (min(B, 4096), I))
     if "sha256" in name:
@@ -41,7 +43,8 @@ for name in a.circuits.split(","):
     host = torch.from_numpy(vals.view(np.uint8).reshape(-1, I * 32))
     reps = (B + host.shape[0] - 1) // host.shape[0]
     d_in = host.repeat(reps, 1)[:B].contiguous().to(dev)
-    d_out = torch.empty((B, W * 32), dtype=torch.uint8, device=dev)
+    wrap = int(os.environ.get("GW_DEBUG_OUT_WRAP", "0"))     # profiling aid: all witnesses share `wrap` output rows
+    d_out = torch.empty((wrap or B, W * 32), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     g.calc_witness_batch_device(0, d_in.data_ptr(), B, d_out.data_ptr(), None, stream)   # warm-up
     torch.cuda.synchronize()
