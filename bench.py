@@ -195,7 +195,7 @@ def main():
     B = a.batch
     free_b, _ = torch.cuda.mem_get_info()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    wave = sms * info["threads"] * info["sets_per_thread"]   # one CTA per SM
+    wave = sms * 32                                          # one CTA per SM, whole warps: chunk = sms x T input sets
     max_chunk = int(max(wave, (free_b * 0.85 - B * I * 32) // (W * 32)))
     if a.chunk:
         chunk = a.chunk

@@ -111,7 +111,7 @@ int gw_graph_info(const gw_graph_t* graph, gw_graph_info_t* info) {
   info->n_dot_mac = (uint32_t)p.stats.dot_terms[T_MAC];
   info->n_mul_instr = (uint32_t)(p.stats.op_count[OP_MUL] + p.stats.op_count[OP_SQR]);
   info->n_inversions = (uint32_t)p.stats.inversions;
-  info->threads = (uint32_t)graph->engine->threads; info->sets_per_thread = (uint32_t)graph->engine->sets_per_thread;
+  info->threads = (uint32_t)graph->engine->max_threads; info->sets_per_thread = 1;
   return 0;
 }
 

@@ -25,10 +25,10 @@ namespace gw {
 
 struct KParams {
   const uint4* code; uint32_t n_slots;
-  const uint4* consts;
+  const uint4* consts; uint32_t n_hot;   // the first n_hot table constants (most used first) are staged in shared memory
   const uint4* inputs;     // [B][I][2]
   uint4* out;              // [B][W][2]
-  uint4* spill;            // [n_spill][2][V][spill_threads]
+  uint4* spill;            // [n_spill][2][spill_threads]
   uint32_t* status;        // [B] or null
   unsigned long long B;
   uint32_t I, W;
@@ -44,71 +44,41 @@ __device__ __forceinline__ uint4 fe_lo(const fe& a) { return make_uint4(a.l[0], 
 __device__ __forceinline__ uint4 fe_hi(const fe& a) { return make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-static const int RING = 64;     // instruction slots staged per warp in shared memory (two blocks of 32)
+static const int RING = 64;          // instruction slots staged per warp in shared memory (two blocks of 32)
+static const int MAX_THREADS = 512;  // one persistent CTA per SM; 512 threads x 128 registers = the whole register file
 
-// T threads per CTA, V input sets per thread.  Shared memory: [T/32 warps][RING] instruction slots, then the
-// register file [n_regs][2 halves][V][T] of uint4.
-template <int T, int V>
-__global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
+// One thread = one input set; blockDim.x = T threads (a multiple of 32, chosen per launch so that one CTA per SM covers
+// the batch).  Dynamic shared memory: [T/32 warps][RING] instruction slots | [n_hot][2] hot constants | register file
+// [n_regs][2 halves][T], all uint4.  Warps never synchronise with each other after the constants are staged.
+__global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParams p) {
   extern __shared__ uint4 smem[];
+  const int T = blockDim.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   uint4* ring = smem + (tid >> 5) * RING;
-  uint4* rf = smem + (T / 32) * RING;
+  uint4* hot = smem + (T >> 5) * RING;
+  uint4* rf = hot + 2 * (size_t)p.n_hot + tid;       // this thread's column of the register file
   const unsigned long long gthread = (unsigned long long)blockIdx.x * T + tid;
   const uint32_t n = p.n_slots;
 
-  auto rf_load = [&](uint32_t r, int v) { return fe_from(rf[((r * 2) * V + v) * T + tid], rf[((r * 2 + 1) * V + v) * T + tid]); };
-  auto rf_store = [&](uint32_t r, int v, const fe& x) { rf[((r * 2) * V + v) * T + tid] = fe_lo(x); rf[((r * 2 + 1) * V + v) * T + tid] = fe_hi(x); };
-  auto const_load = [&](uint32_t c) { return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1)); };
+  for (uint32_t k = tid; k < 2 * p.n_hot; k += T) hot[k] = __ldg(p.consts + k);
+  __syncthreads();
+
+  auto rf_load = [&](uint32_t r) { return fe_from(rf[(r * 2) * T], rf[(r * 2 + 1) * T]); };
+  auto rf_store = [&](uint32_t r, const fe& x) { rf[(r * 2) * T] = fe_lo(x); rf[(r * 2 + 1) * T] = fe_hi(x); };
+  auto const_load = [&](uint32_t c) {
+    if (c < p.n_hot) return fe_from(hot[2 * c], hot[2 * c + 1]);
+    return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1));
+  };
 
   for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const uint4* in[V]; uint4* out[V]; bool active[V]; unsigned long long wv[V];
-    uint32_t st[V];
-#pragma unroll
-    for (int v = 0; v < V; v++) {
-      wv[v] = ((unsigned long long)tile * V + v) * T + tid;
-      active[v] = wv[v] < p.B;
-      const unsigned long long wl = active[v] ? wv[v] : p.B - 1;
-      in[v] = p.inputs + wl * p.I * 2;
-      out[v] = p.out + (p.out_wrap ? wl % p.out_wrap : wl) * p.W * 2;
-      st[v] = 0;
-    }
-    auto out_store = [&](uint32_t j, int v, const fe& x) { if (active[v]) { out[v][2 * (size_t)j] = fe_lo(x); out[v][2 * (size_t)j + 1] = fe_hi(x); } };
-
-    // pull what the NEXT instruction reads from global memory (table constants, spilled values) towards L1 while
-    // the current instruction computes; its header (and term slots) are already in the ring
-    auto prefetch_one = [&](const uint4& h, uint32_t at) {
-      const uint32_t o = h.x & 0xFFu;
-      if (o == OP_DOT) {
-        const uint32_t nt = h.y & 0xFFu;
-#pragma unroll 1
-        for (uint32_t t = 0; t < nt; t += 2) {
-          const uint4 sl = ring[(at + 1 + (t >> 1)) & (RING - 1)];
-          if ((sl.x & 0xFu) != T_ADDHI && (sl.x & 0xFu) != T_SUBHI) prefetch_l1(p.consts + 2 * (size_t)sl.y);
-          if (t + 1 < nt && (sl.z & 0xFu) != T_ADDHI && (sl.z & 0xFu) != T_SUBHI) prefetch_l1(p.consts + 2 * (size_t)sl.w);
-        }
-      } else if (o == OP_SPILL_LD) {
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          prefetch_l1(p.spill + (((size_t)h.y * 2) * V + v) * p.spill_threads + gthread);
-          prefetch_l1(p.spill + (((size_t)h.y * 2 + 1) * V + v) * p.spill_threads + gthread);
-        }
-      } else if (o == OP_SHRAND) {
-        prefetch_l1(p.consts + 2 * (size_t)(h.z >> 8));
-      } else if (o < 48u) {
-        if (h.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)h.y);
-        if ((h.x & F_B_CONST) && o < 32u) prefetch_l1(p.consts + 2 * (size_t)h.z);
-      }
-    };
-
-    auto prefetch_operands = [&](const uint4& h, uint32_t at) {
-      prefetch_one(h, at);
-      if ((V == 1) && (h.x & F_PAIR)) {
-        const uint32_t at2 = at + (((h.x & 0xFFu) == OP_DOT) ? 1u + (((h.y & 0xFFu) + 1u) >> 1) : 1u);
-        prefetch_one(ring[at2 & (RING - 1)], at2);
-      }
-    };
+    const unsigned long long w = (unsigned long long)tile * T + tid;
+    const bool active = w < p.B;
+    const unsigned long long wl = active ? w : p.B - 1;
+    const uint4* in = p.inputs + wl * p.I * 2;
+    uint4* out = p.out + (p.out_wrap ? wl % p.out_wrap : wl) * p.W * 2;
+    uint32_t st = 0;
+    auto out_store = [&](uint32_t j, const fe& x) { if (active) { out[2 * (size_t)j] = fe_lo(x); out[2 * (size_t)j + 1] = fe_hi(x); } };
 
     // instruction ring: blocks 0 and 1 staged, block 2 in flight in nblk
     __syncwarp();
@@ -123,82 +93,18 @@ __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
       const uint32_t op = ins.x & 0xFFu;
       const uint32_t dst = ins.x >> 16;
       const uint32_t len = (op == OP_DOT) ? 1u + (((ins.y & 0xFFu) + 1u) >> 1) : 1u;
-      uint32_t npc = pc + len;
-      uint4 ins2 = ins;
-      const bool paired = (V == 1) && (ins.x & F_PAIR);
-      if (paired) {                                   // bundle: the partner follows immediately
-        ins2 = ring[npc & (RING - 1)];
-        npc += ((ins2.x & 0xFFu) == OP_DOT) ? 1u + (((ins2.y & 0xFFu) + 1u) >> 1) : 1u;
-      }
+      const uint32_t npc = pc + len;
       const bool cross = (npc >> 5) != (pc >> 5);
-      if (!cross) { nxt = ring[npc & (RING - 1)]; if (npc < n) prefetch_operands(nxt, npc); }
+      if (!cross) nxt = ring[npc & (RING - 1)];     // next header early: its latency hides behind this instruction
 
-      fe R[V];
+      fe R;
       bool have_result = true;
-      if (paired) {
-        // ---- two independent instructions of the same class as one bundle (V == 1): their carry chains sit in the
-        // same basic block, so the scheduler interleaves them; every operand is read before either result is stored
-        fe R1, R2;
-        if (op == OP_DOT) {
-          const uint32_t nt1 = ins.y & 0xFFu, nt2 = ins2.y & 0xFFu;
-          const uint32_t base1 = pc + 1, base2 = pc + len + 1;
-          const uint32_t tmin = min(nt1, nt2);
-          uint32_t P1[16], P2[16];
+      if (op == OP_DOT) {
+        // fused linear combination: 512-bit accumulator, ONE Montgomery reduction
+        const uint32_t nt = ins.y & 0xFFu;
+        uint32_t P[16];
 #pragma unroll
-          for (int k = 0; k < 16; k++) { P1[k] = 0; P2[k] = 0; }
-          auto term_at = [&](uint32_t base, uint32_t t, uint32_t& kind, uint32_t& reg, uint32_t& ci) {
-            const uint4 sl = ring[(base + (t >> 1)) & (RING - 1)];
-            const uint32_t lo = (t & 1) ? sl.z : sl.x;
-            ci = (t & 1) ? sl.w : sl.y; kind = lo & 0xFu; reg = lo >> 16;
-          };
-          auto one_term = [&](uint32_t* P, uint32_t kind, uint32_t reg, uint32_t ci) {
-            if (kind == T_MAC) { const fe c = const_load(ci); const fe x = rf_load(reg, 0); uint32_t Q[16]; u256_mul_wide(Q, x.l, c.l); u512_add(P, Q); }
-            else if (kind == T_CONST) { const fe c = const_load(ci); u512_add256(P, c.l, 0); }
-            else dot_term(P, kind, rf_load(reg, 0), fe_zero());
-          };
-#pragma unroll 1
-          for (uint32_t t = 0; t < tmin; t++) {
-            uint32_t k1, r1, c1, k2, r2, c2;
-            term_at(base1, t, k1, r1, c1); term_at(base2, t, k2, r2, c2);
-            if (k1 == T_MAC && k2 == T_MAC) {
-              const fe cv1 = const_load(c1), cv2 = const_load(c2);
-              const fe x1 = rf_load(r1, 0), x2 = rf_load(r2, 0);
-              uint32_t Q1[16], Q2[16];
-              u256_mul_wide(Q1, x1.l, cv1.l); u256_mul_wide(Q2, x2.l, cv2.l);
-              u512_add(P1, Q1); u512_add(P2, Q2);
-            } else { one_term(P1, k1, r1, c1); one_term(P2, k2, r2, c2); }
-          }
-#pragma unroll 1
-          for (uint32_t t = tmin; t < nt1; t++) { uint32_t k1, r1, c1; term_at(base1, t, k1, r1, c1); one_term(P1, k1, r1, c1); }
-#pragma unroll 1
-          for (uint32_t t = tmin; t < nt2; t++) { uint32_t k2, r2, c2; term_at(base2, t, k2, r2, c2); one_term(P2, k2, r2, c2); }
-          R1 = fe_mont_reduce_core(P1); R2 = fe_mont_reduce_core(P2);
-          fe_cond_sub_n(R1, (int)((ins.y >> 8) & 0xFFu)); fe_cond_sub_n(R2, (int)((ins2.y >> 8) & 0xFFu));
-        } else {                                       // MUL / SQR x MUL / SQR
-          const uint32_t op2 = ins2.x & 0xFFu;
-          const fe A1 = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y, 0);
-          const fe B1 = (op == OP_SQR) ? A1 : ((ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z, 0));
-          const fe A2 = (ins2.x & F_A_CONST) ? const_load(ins2.y) : rf_load(ins2.y, 0);
-          const fe B2 = (op2 == OP_SQR) ? A2 : ((ins2.x & F_B_CONST) ? const_load(ins2.z) : rf_load(ins2.z, 0));
-          uint32_t Pm1[16], Pm2[16];
-          u256_mul_wide(Pm1, A1.l, B1.l); u256_mul_wide(Pm2, A2.l, B2.l);
-          R1 = fe_barrett(Pm1); R2 = fe_barrett(Pm2);
-        }
-        const uint32_t dst2 = ins2.x >> 16;
-        if (dst != NO_DST) rf_store(dst, 0, R1);
-        if (dst2 != NO_DST) rf_store(dst2, 0, R2);
-        if (ins.x & F_OUT) out_store(ins.w, 0, R1);
-        if (ins2.x & F_OUT) out_store(ins2.w, 0, R2);
-        have_result = false;
-      } else if (op == OP_DOT) {
-        // fused linear combination: 512-bit accumulators, one Montgomery reduction per input set
-        const uint32_t nt = ins.y & 0xFFu, ncs = (ins.y >> 8) & 0xFFu;
-        uint32_t P[V][16];
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-#pragma unroll
-          for (int k = 0; k < 16; k++) P[v][k] = 0;
-        }
+        for (int k = 0; k < 16; k++) P[k] = 0;
 #pragma unroll 1
         for (uint32_t t = 0; t < nt; t++) {
           const uint4 sl = ring[(pc + 1 + (t >> 1)) & (RING - 1)];
@@ -206,145 +112,55 @@ __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
           const uint32_t kind = lo & 0xFu, reg = lo >> 16;
           if (kind == T_MAC) {
             const fe c = const_load(ci);
-            uint32_t Q[V][16];
-#pragma unroll
-            for (int v = 0; v < V; v++) { const fe x = rf_load(reg, v); u256_mul_wide(Q[v], x.l, c.l); }
-#pragma unroll
-            for (int v = 0; v < V; v++) u512_add(P[v], Q[v]);
+            const fe x = rf_load(reg);
+            uint32_t Q[16];
+            u256_mul_wide(Q, x.l, c.l);
+            u512_add(P, Q);
           } else if (kind == T_CONST) {
             const fe c = const_load(ci);
-#pragma unroll
-            for (int v = 0; v < V; v++) u512_add256(P[v], c.l, 0);
+            u512_add256(P, c.l, 0);
           } else {
-#pragma unroll
-            for (int v = 0; v < V; v++) dot_term(P[v], kind, rf_load(reg, v), fe_zero());
+            dot_term(P, kind, rf_load(reg), fe_zero());
           }
         }
-#pragma unroll
-        for (int v = 0; v < V; v++) R[v] = fe_mont_reduce(P[v], (int)ncs);
+        R = fe_mont_reduce(P, (int)((ins.y >> 8) & 0xFFu));
       } else if (op == OP_MUL || op == OP_SQR) {
-        fe A[V], Bv[V];
-        if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
-#pragma unroll
-          for (int v = 0; v < V; v++) A[v] = c;
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) A[v] = rf_load(ins.y, v);
-        }
-        if (op == OP_SQR) {
-#pragma unroll
-          for (int v = 0; v < V; v++) Bv[v] = A[v];
-        } else if (ins.x & F_B_CONST) { const fe c = const_load(ins.z);
-#pragma unroll
-          for (int v = 0; v < V; v++) Bv[v] = c;
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) Bv[v] = rf_load(ins.z, v);
-        }
-        uint32_t Pm[V][16];
-#pragma unroll
-        for (int v = 0; v < V; v++) u256_mul_wide(Pm[v], A[v].l, Bv[v].l);
-#pragma unroll
-        for (int v = 0; v < V; v++) R[v] = fe_barrett(Pm[v]);
+        const fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
+        const fe Bv = (op == OP_SQR) ? A : ((ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z));
+        uint32_t Pm[16];
+        u256_mul_wide(Pm, A.l, Bv.l);
+        R = fe_barrett(Pm);
       } else if (op == OP_ADD || op == OP_SUB) {
-        fe A[V], Bv[V];
-        if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
-#pragma unroll
-          for (int v = 0; v < V; v++) A[v] = c;
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) A[v] = rf_load(ins.y, v);
-        }
-        if (ins.x & F_B_CONST) { const fe c = const_load(ins.z);
-#pragma unroll
-          for (int v = 0; v < V; v++) Bv[v] = c;
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) Bv[v] = rf_load(ins.z, v);
-        }
-#pragma unroll
-        for (int v = 0; v < V; v++) R[v] = (op == OP_ADD) ? fe_add(A[v], Bv[v]) : fe_sub(A[v], Bv[v]);
+        const fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
+        const fe Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z);
+        R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);
       } else if (op == OP_SPILL_ST) {
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const fe x = rf_load(ins.y, v);
-          p.spill[(((size_t)ins.z * 2) * V + v) * p.spill_threads + gthread] = fe_lo(x);
-          p.spill[(((size_t)ins.z * 2 + 1) * V + v) * p.spill_threads + gthread] = fe_hi(x);
-        }
+        const fe x = rf_load(ins.y);
+        p.spill[((size_t)ins.z * 2) * p.spill_threads + gthread] = fe_lo(x);
+        p.spill[((size_t)ins.z * 2 + 1) * p.spill_threads + gthread] = fe_hi(x);
         have_result = false;
       } else if (op == OP_SPILL_LD) {
-#pragma unroll
-        for (int v = 0; v < V; v++)
-          R[v] = fe_from(p.spill[(((size_t)ins.y * 2) * V + v) * p.spill_threads + gthread],
-                         p.spill[(((size_t)ins.y * 2 + 1) * V + v) * p.spill_threads + gthread]);
+        R = fe_from(p.spill[((size_t)ins.y * 2) * p.spill_threads + gthread], p.spill[((size_t)ins.y * 2 + 1) * p.spill_threads + gthread]);
       } else if (op == OP_OUT) {
-        if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
-#pragma unroll
-          for (int v = 0; v < V; v++) out_store(ins.w, v, c);
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) out_store(ins.w, v, rf_load(ins.y, v));
-        }
+        out_store(ins.w, (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y));
         have_result = false;
       } else if (op == OP_INPUT) {
-#pragma unroll
-        for (int v = 0; v < V; v++) R[v] = fe_reduce256(fe_from(__ldg(in[v] + 2 * (size_t)ins.y), __ldg(in[v] + 2 * (size_t)ins.y + 1)));
+        R = fe_reduce256(fe_from(__ldg(in + 2 * (size_t)ins.y), __ldg(in + 2 * (size_t)ins.y + 1)));
       } else if (op == OP_SHRAND) {
-        const fe c = const_load(ins.z >> 8);
-#pragma unroll
-        for (int v = 0; v < V; v++) R[v] = fe_shr_and(rf_load(ins.y, v), ins.z & 0xFFu, c);
-      } else if (op == OP_INV || op == OP_DIV) {
-        // modular inversion for all V input sets at once (interleaved safegcd chains); Div = a * b^-1, b == 0 -> 0
-        fe X[V];
-        const uint32_t src = (op == OP_INV) ? ins.y : ins.z;
-        const uint32_t src_const = (op == OP_INV) ? (ins.x & F_A_CONST) : (ins.x & F_B_CONST);
-        if (src_const) { const fe c = const_load(src);
-#pragma unroll
-          for (int v = 0; v < V; v++) X[v] = c;
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) X[v] = rf_load(src, v);
-        }
-        fe_inv_batch<V>(X);
-        if (op == OP_DIV) {
-          uint32_t Pm[V][16];
-          if (ins.x & F_A_CONST) { const fe c = const_load(ins.y);
-#pragma unroll
-            for (int v = 0; v < V; v++) u256_mul_wide(Pm[v], c.l, X[v].l);
-          } else {
-#pragma unroll
-            for (int v = 0; v < V; v++) { const fe a = rf_load(ins.y, v); u256_mul_wide(Pm[v], a.l, X[v].l); }
-          }
-#pragma unroll
-          for (int v = 0; v < V; v++) R[v] = fe_barrett(Pm[v]);
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) R[v] = X[v];
-        }
+        R = fe_shr_and(rf_load(ins.y), ins.z & 0xFFu, const_load(ins.z >> 8));
       } else if (op != OP_NOP) {
-        // everything else (rare ops, out-of-line helpers), one input set after the other
-#pragma unroll 1
-        for (int v = 0; v < V; v++) {
-          fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y, v), Bv = fe_zero(), C = fe_zero();
-          if (op_has_b(op)) Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z, v);
-          if (op == OP_TERN) C = (ins.x & F_C_CONST) ? const_load(ins.w) : rf_load(ins.w, v);
-          uint32_t s = 0;
-          const fe r = alu_exec(op, A, Bv, C, s);
-#pragma unroll
-          for (int u = 0; u < V; u++) if (u == v) { R[u] = r; st[u] |= s; }
-        }
+        // everything else (Div, Inv and the rare ops; out-of-line helpers)
+        const fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
+        fe Bv = fe_zero(), C = fe_zero();
+        if (op_has_b(op)) Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z);
+        if (op == OP_TERN) C = (ins.x & F_C_CONST) ? const_load(ins.w) : rf_load(ins.w);
+        R = alu_exec(op, A, Bv, C, st);
       } else {
         have_result = false;
       }
       if (have_result) {
-        if (dst != NO_DST) {
-#pragma unroll
-          for (int v = 0; v < V; v++) rf_store(dst, v, R[v]);
-        }
-        if (ins.x & F_OUT) {
-#pragma unroll
-          for (int v = 0; v < V; v++) out_store(ins.w, v, R[v]);
-        }
+        if (dst != NO_DST) rf_store(dst, R);
+        if (ins.x & F_OUT) out_store(ins.w, R);
       }
 
       if (cross) {
@@ -354,12 +170,10 @@ __global__ void __launch_bounds__(T) eval_batch_kernel(const KParams p) {
         nblk = __ldg(p.code + min(((pc >> 5) + 3u) * 32u + lane, n - 1));
         __syncwarp();
         nxt = ring[npc & (RING - 1)];
-        if (npc < n) prefetch_operands(nxt, npc);
       }
       pc = npc;
     }
-#pragma unroll
-    for (int v = 0; v < V; v++) if (p.status != nullptr && active[v]) p.status[wv[v]] = st[v];
+    if (p.status != nullptr && active) p.status[w] = st;
   }
 }
 
@@ -501,18 +315,10 @@ double imad_microbench(int device, int which) {
 }
 
 // ---- engine ------------------------------------------------------------------------------------------
-typedef void (*BatchKernel)(const KParams);
-static BatchKernel batch_kernel(int T, int V) {
-  if (T == 32 && V == 1) return eval_batch_kernel<32, 1>;
-  if (T == 32 && V == 2) return eval_batch_kernel<32, 2>;
-  if (T == 64 && V == 1) return eval_batch_kernel<64, 1>;
-  if (T == 64 && V == 2) return eval_batch_kernel<64, 2>;
-  throw Error("GW_THREADS must be 32 or 64 and GW_V 1 or 2");
-}
-
 struct Engine::Dev {
   int device = -1;
-  int sms = 0, ctas_per_sm = 0;
+  int sms = 0, max_threads = 0;          // threads per CTA the device allows for this plan (one CTA per SM)
+  size_t smem_max = 0;
   uint4* code = nullptr; uint4* consts = nullptr;
   uint4* spill = nullptr; size_t spill_threads = 0;
   // staging for the host-buffer API
@@ -530,19 +336,26 @@ static int env_int(const char* name, int dflt) { const char* s = getenv(name); r
 
 Engine::Engine(const uint8_t* graph_data, size_t len) {
   graph = deserialize_witnesscalc_graph(graph_data, len);
-  threads = env_int("GW_THREADS", 64);
-  sets_per_thread = env_int("GW_V", 1);
-  batch_kernel(threads, sets_per_thread);      // validates the combination
+  max_threads = env_int("GW_THREADS", MAX_THREADS);
+  if (max_threads < 32 || max_threads > MAX_THREADS || (max_threads & 31)) throw Error("GW_THREADS must be a multiple of 32 in [32, 512]");
   PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", (int)opt.n_regs);
   opt.div_batch = (uint32_t)env_int("GW_DIV_BATCH", (int)opt.div_batch);
   opt.fuse_dot = env_int("GW_FUSE_DOT", 1) != 0;
   opt.max_terms = (uint32_t)env_int("GW_MAX_TERMS", (int)opt.max_terms);
-  opt.pair = env_int("GW_PAIR", 0) != 0 && sets_per_thread == 1;   // bundles are the V == 1 source of ILP
   plan = compile_plan(graph, opt);
 }
 
-size_t Engine::smem_bytes() const {
-  return (size_t)(threads / 32) * RING * 16 + (size_t)plan.n_regs * 32 * sets_per_thread * threads;
+// shared memory of a CTA of T threads without the hot-constant area: instruction rings + register file
+static size_t smem_base(const Plan& plan, int T) { return (size_t)(T / 32) * RING * 16 + (size_t)plan.n_regs * 32 * T; }
+
+// Launch geometry for a batch of B input sets: one persistent CTA per SM; T = the smallest multiple of 32 that
+// covers the batch in the fewest waves of full CTAs.
+int Engine::threads_for(size_t B, int sms, int t_max) const {
+  const size_t per_wave = (size_t)sms * t_max;
+  const size_t waves = (B + per_wave - 1) / per_wave;
+  size_t t = (B + (size_t)sms * waves - 1) / ((size_t)sms * waves);
+  t = (t + 31) / 32 * 32;
+  return (int)std::min<size_t>(std::max<size_t>(t, 32), (size_t)t_max);
 }
 
 Engine::~Engine() {
@@ -569,18 +382,19 @@ Engine::Dev* Engine::dev(int device) {
   d->device = device;
   cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   d->sms = prop.multiProcessorCount;
-  const size_t smem = smem_bytes();
-  if (smem > (size_t)prop.sharedMemPerBlockOptin) throw Error("register file does not fit shared memory: lower GW_REGS or GW_THREADS");
-  BatchKernel k = batch_kernel(threads, sets_per_thread);
-  CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->ctas_per_sm, k, threads, smem));
-  if (d->ctas_per_sm < 1) throw Error("kernel cannot be resident with this register-file size");
+  d->smem_max = prop.sharedMemPerBlockOptin;
+  cudaFuncAttributes fa; CUDA_CHECK(cudaFuncGetAttributes(&fa, eval_batch_kernel));
+  int t_max = std::min(max_threads, (int)(prop.regsPerBlock / std::max(fa.numRegs, 1)) / 32 * 32);
+  while (t_max >= 32 && smem_base(plan, t_max) > d->smem_max) t_max -= 32;
+  if (t_max < 32) throw Error("register file does not fit shared memory: lower GW_REGS");
+  d->max_threads = t_max;
+  CUDA_CHECK(cudaFuncSetAttribute(eval_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
   CUDA_CHECK(cudaMalloc(&d->code, plan.code.size() * sizeof(Instr)));
   CUDA_CHECK(cudaMemcpy(d->code, plan.code.data(), plan.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMalloc(&d->consts, plan.consts.size() * 32));
   CUDA_CHECK(cudaMemcpy(d->consts, plan.consts.data(), plan.consts.size() * 32, cudaMemcpyHostToDevice));
-  d->spill_threads = (size_t)d->sms * d->ctas_per_sm * threads;
-  if (plan.n_spill) CUDA_CHECK(cudaMalloc(&d->spill, (size_t)plan.n_spill * 32 * sets_per_thread * d->spill_threads));
+  d->spill_threads = (size_t)d->sms * t_max;
+  if (plan.n_spill) CUDA_CHECK(cudaMalloc(&d->spill, (size_t)plan.n_spill * 32 * d->spill_threads));
   devs[device] = d;
   return d;
 }
@@ -591,16 +405,22 @@ void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uin
   p.code = d->code; p.n_slots = (uint32_t)plan.code.size(); p.consts = d->consts;
   p.inputs = (const uint4*)d_inputs; p.out = (uint4*)d_witness; p.spill = d->spill; p.status = d_status;
   p.B = B; p.I = plan.n_inputs; p.W = plan.n_witness;
-  const size_t tile = (size_t)threads * sets_per_thread;
-  size_t n_tiles = (B + tile - 1) / tile;
+  const int T = threads_for(B, d->sms, d->max_threads);
+  size_t n_tiles = (B + T - 1) / T;
   if (n_tiles > 0xFFFFFFFFull) throw Error("batch too large");
   p.n_tiles = (uint32_t)n_tiles;
   p.spill_threads = d->spill_threads;
   p.out_wrap = (unsigned long long)env_int("GW_DEBUG_OUT_WRAP", 0);
-  int grid = (int)std::min<size_t>(n_tiles, (size_t)d->sms * d->ctas_per_sm);
-  batch_kernel(threads, sets_per_thread)<<<grid, threads, smem_bytes(), (cudaStream_t)stream>>>(p);
+  // whatever shared memory the rings and the register file leave goes to the most used constants
+  const size_t base = smem_base(plan, T);
+  p.n_hot = (uint32_t)std::min<size_t>(plan.consts.size(), (d->smem_max - base) / 32);
+  if (env_int("GW_HOT_CONSTS", -1) >= 0) p.n_hot = std::min<uint32_t>(p.n_hot, (uint32_t)env_int("GW_HOT_CONSTS", 0));
+  const int grid = (int)std::min<size_t>(n_tiles, (size_t)d->sms);
+  eval_batch_kernel<<<grid, T, base + (size_t)p.n_hot * 32, (cudaStream_t)stream>>>(p);
   CUDA_CHECK(cudaGetLastError());
 }
+
+int Engine::device_max_threads(int device) { return dev(device)->max_threads; }
 
 void Engine::run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
   Dev* d = dev(device);
@@ -622,7 +442,7 @@ void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* w
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   size_t budget = (size_t)env_int("GW_CHUNK_MB", 24576) << 20;
   budget = std::min(budget, (free_b + 2 * d->chunk * (in_b + out_b)) / 5);
-  size_t chunk = std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 2 * d->spill_threads * sets_per_thread);
+  size_t chunk = std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 2 * d->spill_threads);
   if (B >= 4 * 2048) chunk = std::min(chunk, (B + 3) / 4);
   chunk = std::max<size_t>(std::min(chunk, B), 1);
   if (chunk > d->chunk) {

@@ -18,9 +18,9 @@ class Engine {
 
   Graph graph;
   Plan plan;
-  int threads = 64;           // threads per CTA (GW_THREADS)
-  int sets_per_thread = 1;    // input sets evaluated by one thread, interleaved for instruction-level parallelism (GW_V)
-  size_t smem_bytes() const;
+  int max_threads = 512;      // upper bound of threads per CTA (GW_THREADS); one persistent CTA per SM
+  int threads_for(size_t B, int sms, int t_max) const;
+  int device_max_threads(int device);   // threads per CTA (= input sets per SM and wave) the device allows for this plan
 
   // inputs/witness resident on `device`: inputs [B][I][32 B LE], witness [B][W][32 B LE]; asynchronous on `stream`
   void run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);

@@ -166,57 +166,4 @@ GW_HD_NOINLINE fe fe_inv(const fe& x) {
   return r;
 }
 
-#if defined(__CUDACC__)
-// V independent inversions with interleaved instruction streams (the batch kernel evaluates V input sets per
-// thread): every divstep is executed for all V values before the next one, so the V dependent chains overlap.
-template <int V>
-__device__ __forceinline__ void fe_inv_batch(fe* x) {
-  s30 f[V], g[V], d[V], e[V];
-  int32_t zeta[V];
-#pragma unroll
-  for (int v = 0; v < V; v++) {
-    g[v] = s30_from_u256(x[v].l);
-#pragma unroll
-    for (int i = 0; i < 9; i++) { f[v].v[i] = MOD30(i); d[v].v[i] = 0; e[v].v[i] = 0; }
-    e[v].v[0] = 1;
-    zeta[v] = -1;
-  }
-#pragma unroll 1
-  for (int it = 0; it < 20; it++) {
-    uint32_t fl[V], gl[V], u[V], w[V], q[V], r[V];
-#pragma unroll
-    for (int v = 0; v < V; v++) {
-      fl[v] = (uint32_t)f[v].v[0] | ((uint32_t)f[v].v[1] << 30);
-      gl[v] = (uint32_t)g[v].v[0] | ((uint32_t)g[v].v[1] << 30);
-      u[v] = 1; w[v] = 0; q[v] = 0; r[v] = 1;
-    }
-#pragma unroll 5
-    for (int i = 0; i < 30; i++) {
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        uint32_t c1 = (uint32_t)(zeta[v] >> 31);
-        uint32_t c2 = (uint32_t)0 - (gl[v] & 1u);
-        uint32_t xx = (fl[v] ^ c1) - c1, yy = (u[v] ^ c1) - c1, zz = (w[v] ^ c1) - c1;
-        gl[v] += xx & c2; q[v] += yy & c2; r[v] += zz & c2;
-        c1 &= c2;
-        zeta[v] = (int32_t)(((uint32_t)zeta[v] ^ c1) - 1u);
-        fl[v] += gl[v] & c1; u[v] += q[v] & c1; w[v] += r[v] & c1;
-        gl[v] >>= 1; u[v] <<= 1; w[v] <<= 1;
-      }
-    }
-#pragma unroll
-    for (int v = 0; v < V; v++) {
-      int32_t t[4] = {(int32_t)u[v], (int32_t)w[v], (int32_t)q[v], (int32_t)r[v]};
-      update_de_30(d[v], e[v], t);
-      update_fg_30(f[v], g[v], t);
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < V; v++) {
-    normalize_30(d[v], f[v].v[8]);
-    s30_to_u256(x[v].l, d[v]);
-  }
-}
-#endif
-
 }  // namespace gw

@@ -38,8 +38,6 @@ enum Flags : uint32_t {
   F_B_CONST = 1u << 9,
   F_C_CONST = 1u << 10,
   F_OUT = 1u << 11,      // also store the result to witness position .w
-  F_PAIR = 1u << 12,     // the next instruction is independent and of the same class (MUL/SQR or DOT): both are executed
-                         // as one bundle -- all operands of both are read before either result is written
 };
 
 // OP_DOT terms.  A term is (lo, hi): lo = kind[3:0] | register << 16, hi = constant-table index.

@@ -28,6 +28,8 @@ std::vector<uint8_t> liveness(const Graph& g) {
   return needed;
 }
 
+inline bool op_has_b_host(uint32_t op) { return op < 32 || op == OP_TERN; }
+
 fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 U256 to_u256(const fe& v) { U256 r; memcpy(r.l, v.l, 32); return r; }
 // c * 2^256 mod M (or (M - c) * 2^256 mod M): the form OP_DOT constants are stored in
@@ -355,82 +357,7 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
     else for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]] && std::find(v.begin(), v.end(), m.in[k]) == v.end()) v.push_back(m.in[k]);
   };
 
-  // ---- pairing: instruction-level parallelism inside a thread ---------------------------------------------
-  // Large witnesses bound the number of resident threads (HBM capacity), so dependent carry chains cannot be hidden
-  // by other warps alone.  Two independent macro ops of the same class (value x value multiplications, or fused
-  // linear combinations) are issued as ONE bundle whose two instruction streams the kernel interleaves.  List
-  // scheduling: walk the ops in order; for an op of a pairable class pick, among the ops that are already READY
-  // (all operands computed), the next one of the same class; it runs ahead of its original position.
   std::vector<uint32_t> vops;
-  std::vector<int32_t> pair_second(mops.size(), -1);     // in the NEW order: index of the op bundled with this one
-  if (opt.pair && mops.size() > 1) {
-    const size_t Mn = mops.size();
-    auto klass = [&](const MOp& m) { return (m.opc == OP_MUL || m.opc == OP_SQR) ? 1 : m.opc == OP_DOT ? 2 : 0; };
-    std::vector<int32_t> def_of(N, -1);
-    for (size_t k = 0; k < Mn; k++) def_of[mops[k].node] = (int32_t)k;
-    std::vector<uint32_t> pending(Mn, 0), succ_start(Mn + 1, 0), succ;
-    std::vector<std::vector<uint32_t>> preds(Mn);
-    for (size_t k = 0; k < Mn; k++) {
-      value_operands(mops[k], vops);
-      for (uint32_t x : vops) { int32_t d = def_of[x]; if (d < 0) throw Error("plan: operand without a definition"); preds[k].push_back((uint32_t)d); succ_start[d + 1]++; }
-      pending[k] = (uint32_t)preds[k].size();
-    }
-    for (size_t k = 0; k < Mn; k++) succ_start[k + 1] += succ_start[k];
-    succ.resize(succ_start[Mn]);
-    {
-      std::vector<uint32_t> fill(succ_start.begin(), succ_start.end() - 1);
-      for (size_t k = 0; k < Mn; k++) for (uint32_t d : preds[k]) succ[fill[d]++] = (uint32_t)k;
-    }
-    std::set<uint32_t> ready[3];
-    for (size_t k = 0; k < Mn; k++) if (pending[k] == 0 && klass(mops[k])) ready[klass(mops[k])].insert((uint32_t)k);
-    std::vector<uint8_t> done(Mn, 0);
-    std::vector<uint32_t> order; order.reserve(Mn);
-    std::vector<uint8_t> first_of_pair; first_of_pair.reserve(Mn);
-    auto schedule = [&](uint32_t k) {
-      done[k] = 1;
-      if (klass(mops[k])) ready[klass(mops[k])].erase(k);
-      for (uint32_t q = succ_start[k]; q < succ_start[k + 1]; q++) {
-        uint32_t c = succ[q];
-        if (--pending[c] == 0 && klass(mops[c])) ready[klass(mops[c])].insert(c);
-      }
-    };
-    const uint32_t max_pair_terms = std::min(DOT_MAX_TERMS, opt.n_regs - 3);
-    for (uint32_t a = 0; a < Mn; a++) {
-      if (done[a]) continue;
-      const int ka = klass(mops[a]);
-      int32_t b = -1;
-      if (ka) {
-        for (auto it = ready[ka].upper_bound(a); it != ready[ka].end(); ++it) {
-          if (ka == 2 && mops[a].terms.size() + mops[*it].terms.size() > max_pair_terms) continue;
-          if (*it - a > opt.pair_distance) break;
-          b = (int32_t)*it; break;
-        }
-      }
-      order.push_back(a); first_of_pair.push_back(b >= 0);
-      if (b >= 0) { order.push_back((uint32_t)b); first_of_pair.push_back(0); }
-      schedule(a);
-      if (b >= 0) {
-        schedule((uint32_t)b);
-        // keep the run-ahead strand moving: unpairable ops (additions, selects ...) that only waited for b are
-        // issued right away, otherwise the strand would stall until the cursor reaches them
-        std::vector<uint32_t> work(1, (uint32_t)b);
-        while (!work.empty()) {
-          const uint32_t x = work.back(); work.pop_back();
-          for (uint32_t q = succ_start[x]; q < succ_start[x + 1]; q++) {
-            const uint32_t c = succ[q];
-            if (done[c] || pending[c] != 0 || klass(mops[c]) != 0) continue;
-            order.push_back(c); first_of_pair.push_back(0);
-            schedule(c);
-            work.push_back(c);
-          }
-        }
-      }
-    }
-    std::vector<MOp> re; re.reserve(Mn);
-    for (size_t k = 0; k < order.size(); k++) { re.push_back(std::move(mops[order[k]])); if (first_of_pair[k]) pair_second[k] = (int32_t)k + 1; }
-    mops.swap(re);
-  }
-
   // use lists of values as macro-op positions of their consumers (CSR, ascending)
   std::vector<uint32_t> use_start(N + 1, 0);
   for (const MOp& m : mops) { value_operands(m, vops); for (uint32_t x : vops) use_start[x + 1]++; }
@@ -453,7 +380,7 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
   std::vector<uint32_t> pinned, uvops;
   struct Enc { uint32_t enc[3]; uint32_t flags; std::vector<Instr> term_slots; };
   for (size_t p = 0; p < mops.size();) {
-    const int n_unit = pair_second[p] >= 0 ? 2 : 1;          // a bundle is allocated like ONE instruction
+    const int n_unit = 1;
     const size_t last = p + n_unit - 1;
     // operands of the whole unit resident
     pinned.clear(); uvops.clear();
@@ -521,7 +448,6 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       Enc& e = encs[u];
       const uint32_t* outs = &out_list[out_start[m.node]];
       if (out_inline[u]) { e.flags |= F_OUT; plan.stats.outs++; }
-      if (n_unit == 2 && u == 0) { e.flags |= F_PAIR; plan.stats.pairs++; if (m.opc == OP_DOT) plan.stats.pairs_dot++; }
       if (m.opc == OP_DOT) {
         al.emit(make_instr(OP_DOT, e.flags, dsts[u], (uint32_t)m.terms.size() | (m.ncs << 8), 0, out_inline[u] ? outs[0] : 0));
         for (const Instr& sl : e.term_slots) plan.code.push_back(sl);
@@ -543,6 +469,41 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
   plan.n_spill = al.n_spill;
   plan.stats.slots = plan.code.size();
   if (plan.consts.empty()) plan.consts.push_back(u256_from_u64(0));
+
+  // most used constants first: the kernel stages a prefix of the table in shared memory
+  {
+    auto for_each_const_ref = [&](auto&& fn) {
+      for (size_t pc = 0; pc < plan.code.size();) {
+        Instr& h = plan.code[pc];
+        const uint32_t op = h.x & 0xFFu, len = instr_slots(h);
+        if (op == OP_DOT) {
+          const uint32_t nt = h.y & 0xFFu;
+          for (uint32_t t = 0; t < nt; t++) {
+            Instr& sl = plan.code[pc + 1 + (t >> 1)];
+            const uint32_t kind = ((t & 1) ? sl.z : sl.x) & 0xFu;
+            if (kind == T_MAC || kind == T_CONST) fn((t & 1) ? sl.w : sl.y);
+          }
+        } else if (op == OP_SHRAND) {
+          uint32_t ci = h.z >> 8; fn(ci); h.z = (h.z & 0xFFu) | (ci << 8);
+        } else if (op != OP_INPUT && op != OP_SPILL_LD && op != OP_SPILL_ST && op != OP_NOP) {
+          if (h.x & F_A_CONST) fn(h.y);
+          if ((h.x & F_B_CONST) && op_has_b_host(op)) fn(h.z);
+          if ((h.x & F_C_CONST) && op == OP_TERN) fn(h.w);
+        }
+        pc += len;
+      }
+    };
+    std::vector<uint64_t> cnt(plan.consts.size(), 0);
+    for_each_const_ref([&](uint32_t& ci) { cnt[ci]++; });
+    std::vector<uint32_t> byuse(plan.consts.size());
+    for (uint32_t k = 0; k < byuse.size(); k++) byuse[k] = k;
+    std::stable_sort(byuse.begin(), byuse.end(), [&](uint32_t a, uint32_t b) { return cnt[a] > cnt[b]; });
+    std::vector<uint32_t> new_ix(plan.consts.size());
+    std::vector<U256> sorted(plan.consts.size());
+    for (uint32_t k = 0; k < byuse.size(); k++) { new_ix[byuse[k]] = k; sorted[k] = plan.consts[byuse[k]]; }
+    plan.consts.swap(sorted);
+    for_each_const_ref([&](uint32_t& ci) { ci = new_ix[ci]; });
+  }
   return plan;
 }
 

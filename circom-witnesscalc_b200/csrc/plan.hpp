@@ -21,18 +21,16 @@
 namespace gw {
 
 struct PlanOptions {
-  uint32_t n_regs = 16;      // per-witness registers kept in shared memory
+  uint32_t n_regs = 12;      // per-witness registers kept in shared memory (12 x 32 B x 512 threads = 192 KB)
   uint32_t div_batch = 8;    // max Div nodes sharing one inversion (1 = off)
   bool fuse_dot = true;      // fuse linear combinations into OP_DOT
   uint32_t max_terms = 8;    // max terms of one OP_DOT (<= DOT_MAX_TERMS, <= n_regs - 3)
-  bool pair = true;          // bundle two independent multiplications / linear combinations (F_PAIR)
-  uint32_t pair_distance = 1u << 30;   // how far ahead (in macro ops) a partner may be taken from
 };
 
 struct PlanStats {
   uint64_t graph_nodes = 0, graph_ops = 0;   // ops = Op + UnoOp + TresOp nodes of the file (node-ops/s metric)
   uint64_t live_ops = 0;                     // ops of the file reachable from the witness
-  uint64_t instrs = 0, slots = 0, spill_st = 0, spill_ld = 0, outs = 0, pairs = 0, pairs_dot = 0;
+  uint64_t instrs = 0, slots = 0, spill_st = 0, spill_ld = 0, outs = 0;
   uint64_t op_count[64] = {0};               // emitted instructions by opcode
   uint64_t dot_terms[4] = {0, 0, 0, 0};      // emitted OP_DOT terms by TermKind
   uint64_t inversions = 0;                   // modular inversions per witness (OP_DIV + OP_INV)

@@ -21,7 +21,7 @@ static fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 
 extern "C" {
 
-// flags: bit 0 = fuse linear combinations (OP_DOT), bit 1 = NO pairing, bits 8.. = div_batch (0 -> default)
+// flags: bit 0 = fuse linear combinations (OP_DOT), bits 8.. = div_batch (0 -> default)
 SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags, char* err, size_t errlen);
 SimGraph* sim_load(const uint8_t* data, size_t len, uint32_t n_regs, char* err, size_t errlen) {
   return sim_load2(data, len, n_regs, 1, err, errlen);
@@ -30,7 +30,7 @@ SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags,
   try {
     std::unique_ptr<SimGraph> s(new SimGraph());
     s->g = deserialize_witnesscalc_graph(data, len);
-    PlanOptions o; o.n_regs = n_regs; o.fuse_dot = (flags & 1) != 0; o.pair = (flags & 2) == 0;
+    PlanOptions o; o.n_regs = n_regs; o.fuse_dot = (flags & 1) != 0;
     if (flags >> 8) o.div_batch = (uint32_t)(flags >> 8);
     s->plan = compile_plan(s->g, o);
     return s.release();
@@ -44,7 +44,6 @@ void sim_info(SimGraph* s, uint64_t* out) {
   out[8] = st.max_live; out[9] = s->plan.consts.size(); out[10] = st.live_ops; out[11] = st.graph_ops;
   out[12] = st.op_count[OP_DOT]; out[13] = st.dot_terms[T_MAC]; out[14] = st.inversions; out[15] = st.div_nodes;
   out[16] = st.slots; out[17] = st.op_count[OP_MUL] + st.op_count[OP_SQR]; out[18] = st.op_count[OP_ADD] + st.op_count[OP_SUB];
-  out[19] = st.pairs; out[20] = st.pairs_dot;
 }
 // inputs: I x 32 B, witness: W x 32 B; returns status bits, or -1 on a malformed plan
 int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
@@ -93,25 +92,11 @@ int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
     if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
     return true;
   };
-  auto pairable = [](uint32_t op) { return op == OP_MUL || op == OP_SQR || op == OP_DOT; };
   for (size_t pc = 0; pc < p.code.size();) {
     const Instr& ins = p.code[pc];
     const uint32_t len = instr_slots(ins);
     if (pc + len > p.code.size()) return -1;
     const uint32_t op = ins.x & 0xFF;
-    if (ins.x & F_PAIR) {
-      // bundle: both instructions read the register file before either writes
-      if (pc + len >= p.code.size()) return -1;
-      const Instr& in2 = p.code[pc + len];
-      const uint32_t len2 = instr_slots(in2), op2 = in2.x & 0xFF;
-      if (pc + len + len2 > p.code.size() || (in2.x & F_PAIR)) return -1;
-      if (!pairable(op) || !pairable(op2) || (op == OP_DOT) != (op2 == OP_DOT)) return -1;
-      fe R1, R2;
-      if (!compute(ins, &p.code[pc + 1], &R1) || !compute(in2, &p.code[pc + len + 1], &R2)) return -1;
-      if (!commit(ins, R1) || !commit(in2, R2)) return -1;
-      pc += len + len2;
-      continue;
-    }
     pc += len;
     if (op == OP_NOP) continue;
     if (op == OP_SPILL_ST) { if (ins.y >= p.n_regs || ins.z >= p.n_spill) return -1; spill[ins.z] = rf[ins.y]; continue; }

@@ -111,7 +111,7 @@ def test_linear_combination_fusion_and_div_batching(n_regs, div_batch):
         nodes, wit, imap = _lc_graph(rnd)
         data = po.serialize_graph(nodes, wit, imap)
         g = util.SimGraph(data, n_regs, fuse=True, div_batch=div_batch)
-        plain = util.SimGraph(data, n_regs, fuse=False, div_batch=1, pair=False)
+        plain = util.SimGraph(data, n_regs, fuse=False, div_batch=1)
         assert plain.info["n_dot"] == 0 and plain.info["inversions"] == plain.info["div_nodes"]
         for row in range(4):
             inp = [1] + [rnd.choice([0, 1, po.M - 1, po.M - 2, (1 << 256) - 1]) if rnd.random() < 0.4 else util.random_value(rnd)

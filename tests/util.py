@@ -164,16 +164,16 @@ def sim_lib():
 class SimGraph:
     """ctypes wrapper over tests/csrc/plan_host_sim.cpp"""
 
-    def __init__(self, data: bytes, n_regs=24, fuse=True, div_batch=0, pair=True):
+    def __init__(self, data: bytes, n_regs=24, fuse=True, div_batch=0):
         self.L = sim_lib()
         err = ctypes.create_string_buffer(512)
-        self.h = self.L.sim_load2(data, len(data), n_regs, int(bool(fuse)) | (0 if pair else 2) | (int(div_batch) << 8), err, 512)
+        self.h = self.L.sim_load2(data, len(data), n_regs, int(bool(fuse)) | (int(div_batch) << 8), err, 512)
         if not self.h:
             raise ValueError(err.value.decode())
-        info = (ctypes.c_uint64 * 21)()
+        info = (ctypes.c_uint64 * 19)()
         self.L.sim_info(self.h, info)
         keys = ["n_nodes", "I", "W", "n_instrs", "n_regs", "n_spill", "spill_ld", "spill_st", "max_live", "n_consts",
-                "live_ops", "graph_ops", "n_dot", "n_dot_mac", "inversions", "div_nodes", "slots", "n_mul", "n_addsub", "pairs", "pairs_dot"]
+                "live_ops", "graph_ops", "n_dot", "n_dot_mac", "inversions", "div_nodes", "slots", "n_mul", "n_addsub"]
         self.info = dict(zip(keys, [int(x) for x in info]))
 
     def eval(self, inputs):
