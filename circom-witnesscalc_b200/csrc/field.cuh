@@ -64,6 +64,25 @@ GW_HD fe fe_small(uint32_t v) { fe r = fe_zero(); r.l[0] = v; return r; }
 GW_HD fe fe_modulus() { fe r; for (int i = 0; i < 8; i++) r.l[i] = MOD_L(i); return r; }
 
 // ---- carry-chain primitives ----------------------------------------------------------------------
+// GW_CHAINS: the carry-chain formulations below are compiled (device code, or the host emulation of the PTX carry flag
+// used by the unit tests: -DGW_EMULATE_PTX runs the DEVICE algorithms on the CPU, instruction for instruction)
+#if defined(__CUDA_ARCH__) || defined(GW_EMULATE_PTX)
+#define GW_CHAINS 1
+#endif
+#if !defined(__CUDA_ARCH__) && defined(GW_EMULATE_PTX)
+static thread_local uint32_t gw_cf = 0;     // the PTX condition-code carry flag
+inline uint32_t ptx_add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; gw_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + gw_cf; gw_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_addc(uint32_t a, uint32_t b) { return a + b + gw_cf; }
+inline uint32_t ptx_sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; gw_cf = (uint32_t)(t >> 32) & 1u; return (uint32_t)t; }   // CF = borrow here
+inline uint32_t ptx_subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - gw_cf; gw_cf = (uint32_t)(t >> 32) & 1u; return (uint32_t)t; }
+inline uint32_t ptx_subc(uint32_t a, uint32_t b) { return a - b - gw_cf; }
+inline uint32_t ptx_mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c; gw_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c + gw_cf; gw_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c; gw_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + gw_cf; gw_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((((uint64_t)a * b) >> 32) + c + gw_cf); }
+#endif
 #if defined(__CUDA_ARCH__)
 #define GW_ASM asm volatile
 __device__ __forceinline__ uint32_t ptx_add_cc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -74,13 +93,14 @@ __device__ __forceinline__ uint32_t ptx_subc_cc(uint32_t a, uint32_t b) { uint32
 __device__ __forceinline__ uint32_t ptx_subc(uint32_t a, uint32_t b) { uint32_t r; GW_ASM("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t ptx_mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t ptx_madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t ptx_mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t ptx_madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t ptx_madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 #endif
 
 // r = a + b (mod 2^256); returns the carry out
 GW_HD uint32_t u256_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
-#if defined(__CUDA_ARCH__)
+#if defined(GW_CHAINS)
   r[0] = ptx_add_cc(a[0], b[0]);
 #pragma unroll
   for (int i = 1; i < 8; i++) r[i] = ptx_addc_cc(a[i], b[i]);
@@ -94,7 +114,7 @@ GW_HD uint32_t u256_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 
 // r = a - b (mod 2^256); returns the borrow out (1 if a < b)
 GW_HD uint32_t u256_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
-#if defined(__CUDA_ARCH__)
+#if defined(GW_CHAINS)
   r[0] = ptx_sub_cc(a[0], b[0]);
 #pragma unroll
   for (int i = 1; i < 8; i++) r[i] = ptx_subc_cc(a[i], b[i]);
@@ -176,7 +196,7 @@ GW_HD fe fe_neg(const fe& a) {                       // graph.rs:190-194
 // accumulate a full 32x32+64 result per pair (IMAD.WIDE.U32 with carry in SASS).  e[] collects the
 // even columns, o[] the odd ones (o[k] is column k+1); they are merged once at the end.
 GW_HD void u256_mul_wide(uint32_t* out, const uint32_t* a, const uint32_t* b) {
-#if defined(__CUDA_ARCH__)
+#if defined(GW_CHAINS)
   uint32_t e[18], o[18];
 #pragma unroll
   for (int i = 0; i < 18; i++) { e[i] = 0; o[i] = 0; }
@@ -229,7 +249,7 @@ GW_HD void u256_mul_wide(uint32_t* out, const uint32_t* a, const uint32_t* b) {
 
 // low 8 limbs of a*b
 GW_HD void u256_mul_lo(uint32_t* out, const uint32_t* a, const uint32_t* b) {
-#if defined(__CUDA_ARCH__)
+#if defined(GW_CHAINS)
   uint32_t e[10], o[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) { e[i] = 0; o[i] = 0; }
@@ -283,7 +303,7 @@ GW_HD void u256_mul_lo(uint32_t* out, const uint32_t* a, const uint32_t* b) {
 // are accumulated (43 of the 64), so out[8..15] is below the true value by less than 2^-60 of one
 // unit of out[8]; out[0..5] are not produced (left 0), out[6..7] are partial.
 GW_HD void u256_mul_hi_trunc(uint32_t* out, const uint32_t* a, const uint32_t* b) {
-#if defined(__CUDA_ARCH__)
+#if defined(GW_CHAINS)
   uint32_t e[18], o[18];
 #pragma unroll
   for (int i = 0; i < 18; i++) { e[i] = 0; o[i] = 0; }
@@ -391,7 +411,7 @@ GW_HD_NOINLINE fe fe_mul_ni(const fe& a, const fe& b) { return fe_mul(a, b); }
 // ---- fused linear combinations (OP_DOT): 512-bit accumulator + ONE Montgomery reduction -----------------
 // P (16 limbs) += Q (16 limbs); the caller guarantees the sum stays below 2^512
 GW_HD void u512_add(uint32_t* P, const uint32_t* Q) {
-#if defined(__CUDA_ARCH__)
+#if defined(GW_CHAINS)
   P[0] = ptx_add_cc(P[0], Q[0]);
 #pragma unroll
   for (int i = 1; i < 15; i++) P[i] = ptx_addc_cc(P[i], Q[i]);
@@ -403,7 +423,7 @@ GW_HD void u512_add(uint32_t* P, const uint32_t* Q) {
 }
 // P += v (8 limbs) at limb offset `off` (0 or 8), carry propagated to the top
 GW_HD void u512_add256(uint32_t* P, const uint32_t* v, int off) {
-#if defined(__CUDA_ARCH__)
+#if defined(GW_CHAINS)
   P[off] = ptx_add_cc(P[off], v[0]);
 #pragma unroll
   for (int i = 1; i < 8; i++) P[off + i] = ptx_addc_cc(P[off + i], v[i]);
@@ -424,34 +444,60 @@ GW_HD void u512_add256(uint32_t* P, const uint32_t* v, int off) {
 // carry-outs are collected lazily in K (columns 8..16 are never read by a later round).  P is clobbered.
 GW_HD fe fe_mont_reduce_core(uint32_t* P) {
   fe r;
-#if defined(__CUDA_ARCH__)
-  uint32_t K[9];
+#if defined(GW_CHAINS)
+  // IMAD.WIDE accumulates into an ALIGNED register pair, so a column may only ever be the low half of a pair in one
+  // array: e[] holds pairs starting at even columns (e[k] = column k), o[] pairs starting at odd columns (o[k] = column
+  // k + 1); P enters as e, o starts at zero.  Round i clears column i: its low word t = e[i] + o[i-1] + carry decides
+  // m; lo(m*M0) makes the column 0 mod 2^32 (carry out = [t != 0] + the carries of forming t) and is never stored.
+  // The array whose pairs START at column i takes hi(m*M0) and m*M2, m*M4, m*M6, the other one m*M1 .. m*M7; chain
+  // carry-outs (columns i+8, i+9) are counted in K, which no later round reads.  Nothing is ever re-paired.
+  uint32_t e[16], o[15], K[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) K[i] = 0;
+  for (int k = 0; k < 16; k++) e[k] = P[k];
+#pragma unroll
+  for (int k = 0; k < 15; k++) o[k] = 0;
+#pragma unroll
+  for (int k = 0; k < 9; k++) K[k] = 0;
+  uint32_t c = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const uint32_t m = P[i] * MONT_INV32;
-    P[i] = ptx_mad_lo_cc(m, MOD_L(0), P[i]);
-    P[i + 1] = ptx_madc_hi_cc(m, MOD_L(0), P[i + 1]);
+    uint32_t t;
+    if (i == 0) { t = e[0]; }
+    else { const uint64_t s = (uint64_t)e[i] + o[i - 1] + c; t = (uint32_t)s; c = (uint32_t)(s >> 32); }
+    c += (t != 0u) ? 1u : 0u;
+    const uint32_t m = t * MONT_INV32;
+    if ((i & 1) == 0) {
+      // pairs starting at column i live in e
+      e[i + 1] = ptx_mad_hi_cc(m, MOD_L(0), e[i + 1]);
 #pragma unroll
-    for (int j = 2; j < 8; j += 2) {
-      P[i + j] = ptx_madc_lo_cc(m, MOD_L(j), P[i + j]);
-      P[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), P[i + j + 1]);
-    }
-    K[i] = ptx_addc(K[i], 0);
-    P[i + 1] = ptx_mad_lo_cc(m, MOD_L(1), P[i + 1]);
-    P[i + 2] = ptx_madc_hi_cc(m, MOD_L(1), P[i + 2]);
+      for (int j = 2; j < 8; j += 2) { e[i + j] = ptx_madc_lo_cc(m, MOD_L(j), e[i + j]); e[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), e[i + j + 1]); }
+      K[i] = ptx_addc(K[i], 0);
+      o[i] = ptx_mad_lo_cc(m, MOD_L(1), o[i]); o[i + 1] = ptx_madc_hi_cc(m, MOD_L(1), o[i + 1]);
 #pragma unroll
-    for (int j = 3; j < 8; j += 2) {
-      P[i + j] = ptx_madc_lo_cc(m, MOD_L(j), P[i + j]);
-      P[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), P[i + j + 1]);
+      for (int j = 3; j < 8; j += 2) { o[i + j - 1] = ptx_madc_lo_cc(m, MOD_L(j), o[i + j - 1]); o[i + j] = ptx_madc_hi_cc(m, MOD_L(j), o[i + j]); }
+      K[i + 1] = ptx_addc(K[i + 1], 0);
+    } else {
+      // pairs starting at column i live in o (o[i - 1] = column i)
+      o[i] = ptx_mad_hi_cc(m, MOD_L(0), o[i]);
+#pragma unroll
+      for (int j = 2; j < 8; j += 2) { o[i + j - 1] = ptx_madc_lo_cc(m, MOD_L(j), o[i + j - 1]); o[i + j] = ptx_madc_hi_cc(m, MOD_L(j), o[i + j]); }
+      K[i] = ptx_addc(K[i], 0);
+      e[i + 1] = ptx_mad_lo_cc(m, MOD_L(1), e[i + 1]); e[i + 2] = ptx_madc_hi_cc(m, MOD_L(1), e[i + 2]);
+#pragma unroll
+      for (int j = 3; j < 8; j += 2) { e[i + j] = ptx_madc_lo_cc(m, MOD_L(j), e[i + j]); e[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), e[i + j + 1]); }
+      K[i + 1] = ptx_addc(K[i + 1], 0);
     }
-    K[i + 1] = ptx_addc(K[i + 1], 0);
   }
-  r.l[0] = ptx_add_cc(P[8], K[0]);
+  // columns 8..15: e + o + K + carry of column 7 (the caller's bound makes the total fit 256 bits)
+  K[0] += c;
+  r.l[0] = ptx_add_cc(e[8], o[7]);
 #pragma unroll
-  for (int i = 1; i < 7; i++) r.l[i] = ptx_addc_cc(P[8 + i], K[i]);
-  r.l[7] = ptx_addc(P[15], K[7]);
+  for (int k = 1; k < 7; k++) r.l[k] = ptx_addc_cc(e[8 + k], o[7 + k]);
+  r.l[7] = ptx_addc(e[15], o[14]);
+  r.l[0] = ptx_add_cc(r.l[0], K[0]);
+#pragma unroll
+  for (int k = 1; k < 7; k++) r.l[k] = ptx_addc_cc(r.l[k], K[k]);
+  r.l[7] = ptx_addc(r.l[7], K[7]);
 #else
   uint64_t top = 0;                                    // carries out of column 15
   for (int i = 0; i < 8; i++) {

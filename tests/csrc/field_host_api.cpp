@@ -29,3 +29,13 @@ void t_inv(const uint32_t* a, uint32_t* r) { st(r, fe_inv_fermat(ld(a))); }
 #include "../../circom-witnesscalc_b200/csrc/inv_safegcd.cuh"
 extern "C" void t_inv_safegcd(const uint32_t* a, uint32_t* r) { st(r, gw::fe_inv(ld(a))); }
 extern "C" void t_mul_hi_trunc(const uint32_t* a, const uint32_t* b, uint32_t* r16) { gw::u256_mul_hi_trunc(r16, a, b); }
+// OP_DOT pieces: P (16 limbs) * 2^-256 mod M with n conditional subtractions, and one accumulated term
+extern "C" void t_mont_reduce(const uint32_t* p16, int ncs, uint32_t* r) { uint32_t P[16]; memcpy(P, p16, 64); st(r, gw::fe_mont_reduce(P, ncs)); }
+extern "C" void t_dot_term(uint32_t* p16, uint32_t kind, const uint32_t* x, const uint32_t* c) { gw::dot_term(p16, kind, ld(x), ld(c)); }
+extern "C" int t_emulates_ptx(void) {
+#if defined(GW_EMULATE_PTX)
+  return 1;
+#else
+  return 0;
+#endif
+}

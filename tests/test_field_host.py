@@ -1,8 +1,11 @@
-"""Host path of csrc/field.cuh (the algorithms the CUDA kernels run: Barrett multiplication, the
-Montgomery helpers, shifts, bitwise ops, signed comparisons, long division, pow, inversion) against
-Python integers.  The device path (PTX carry chains) is covered on the GPU by test_gpu_parity.py."""
+"""csrc/field.cuh (the algorithms the CUDA kernels run: Barrett multiplication, the Montgomery helpers and
+reduction, shifts, bitwise ops, signed comparisons, long division, pow, inversion) against Python integers, twice:
+the plain host path, and the DEVICE formulations (PTX carry chains on even/odd accumulators) compiled for the host
+with an emulated carry flag (-DGW_EMULATE_PTX).  The real PTX is covered on the GPU by test_gpu_parity.py."""
 import ctypes
 import random
+
+import pytest
 
 from tests import util
 from tests.util import M
@@ -31,8 +34,10 @@ def call1(f, a):
     return dec(r)
 
 
-def test_field_and_integer_ops_random_and_edges():
-    L = util.field_host_lib()
+@pytest.mark.parametrize("ptx", [False, True])
+def test_field_and_integer_ops_random_and_edges(ptx):
+    L = util.field_host_lib(ptx)
+    assert bool(L.t_emulates_ptx()) == ptx
     rnd = random.Random(1)
     R = (1 << 256) % M
     Rinv = pow(R, -1, M)
@@ -72,8 +77,53 @@ def test_field_and_integer_ops_random_and_edges():
             assert call1(L.t_inv, a) == (pow(a, -1, M) if a else 0)
 
 
-def test_barrett_worst_cases():
-    L = util.field_host_lib()
+@pytest.mark.parametrize("ptx", [False, True])
+def test_barrett_worst_cases(ptx):
+    L = util.field_host_lib(ptx)
     for a in (M - 1, M - 2, (M >> 1) + 1, 1 << 253, (1 << 253) + 1):
         for b in (M - 1, M - 2, (M >> 1), (1 << 253) - 1, 3):
             assert call2(L.t_mul, a, b) == a * b % M
+
+
+@pytest.mark.parametrize("ptx", [False, True])
+def test_montgomery_reduction_of_accumulated_terms(ptx):
+    """OP_DOT: P = sum of terms (value x pre-scaled constant, +-value << 256, constant), then ONE reduction
+    P * 2^-256 mod M with the number of conditional subtractions the plan compiler derives from the term mix."""
+    L = util.field_host_lib(ptx)
+    rnd = random.Random(2)
+    R = 1 << 256
+    Rinv = pow(R, -1, M)
+    edge = [0, 1, M - 1, M - 2, (1 << 253), (1 << 224) - 1, 0xFFFFFFFF, (1 << 32), (M >> 1)]
+    pick = lambda: rnd.choice(edge) if rnd.random() < 0.4 else rnd.randrange(M)
+    # raw 512-bit values: anything whose reduced value stays below 2^ncs * M and 2^256
+    for t in range(3000):
+        ncs = rnd.choice([1, 2, 3])
+        lim = min((1 << ncs) * M, R) - M        # (P + mM) / R < P / R + M must stay below the bound
+        P = rnd.randrange(lim * R) if rnd.random() < 0.7 else rnd.choice([0, 1, R - 1, R, lim * R - 1, (lim - 1) * R, (1 << 32) - 1,
+                                                                              ((1 << 256) - 1) << 32, (lim * R - 1) & ~((1 << 224) - 1)])
+        P %= lim * R
+        r = A8(); L.t_mont_reduce(A16(*[(P >> (32 * i)) & 0xFFFFFFFF for i in range(16)]), ncs, r)
+        assert dec(r) == P * Rinv % M, (t, ncs, hex(P))
+    # term by term, like the kernel
+    for t in range(1500):
+        n_mac, n_hi = rnd.randrange(0, 9), rnd.randrange(0, 4)
+        if n_mac + n_hi == 0:
+            continue
+        bound = 1 + 0.18906 * n_mac + n_hi
+        if bound > 5.25:
+            continue
+        ncs = 1 if bound <= 2 else 2 if bound <= 4 else 3
+        P = A16(); want = 0
+        for _ in range(n_mac):
+            x, c = pick(), pick()
+            L.t_dot_term(P, 0, enc(x), enc(c * R % M)); want += x * c
+        for _ in range(n_hi):
+            x = pick()
+            if rnd.random() < 0.5:
+                L.t_dot_term(P, 1, enc(x), enc(0)); want += x
+            else:
+                L.t_dot_term(P, 2, enc(x), enc(0)); want -= x
+        if rnd.random() < 0.5:
+            c = pick(); L.t_dot_term(P, 3, enc(0), enc(c * R % M)); want += c
+        r = A8(); L.t_mont_reduce(P, ncs, r)
+        assert dec(r) == want % M, (t, n_mac, n_hi)

@@ -133,10 +133,15 @@ def _build(name, sources, extra=()):
 _libs = {}
 
 
-def field_host_lib():
-    if "field" not in _libs:
-        _libs["field"] = ctypes.CDLL(_build("libfieldhost.so", [os.path.join(ROOT, "tests/csrc/field_host_api.cpp")]))
-    return _libs["field"]
+def field_host_lib(emulate_ptx=False):
+    """csrc/field.cuh on the host.  emulate_ptx=True compiles the DEVICE formulations (PTX carry chains, even/odd
+    accumulators) with an emulated carry flag instead of the plain host loops."""
+    key = "field_ptx" if emulate_ptx else "field"
+    if key not in _libs:
+        _libs[key] = ctypes.CDLL(_build("libfieldhost_ptx.so" if emulate_ptx else "libfieldhost.so",
+                                        [os.path.join(ROOT, "tests/csrc/field_host_api.cpp")],
+                                        extra=("-DGW_EMULATE_PTX",) if emulate_ptx else ()))
+    return _libs[key]
 
 
 def sim_lib():
