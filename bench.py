@@ -196,11 +196,17 @@ def main():
     free_b, _ = torch.cuda.mem_get_info()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     wave = sms * 32                                          # one CTA per SM, whole warps: chunk = sms x T input sets
-    max_chunk = int(max(wave, (free_b * 0.85 - B * I * 32) // (W * 32)))
+    quad = sms * 128                                         # ... and the same number of warps on each of the 4 schedulers of an SM
+    # HBM budget: the chunk's witnesses (W x 32 B each) next to the inputs of the whole batch and the spill area
+    # (n_spill x 32 B for each of the sms x 512 threads a launch can have)
+    reserve = B * I * 32 + info["n_spill"] * 32 * sms * 512 + (3 << 30)
+    max_chunk = int(max(wave, (free_b - reserve) // (W * 32)))
     if a.chunk:
         chunk = a.chunk
     elif B <= max_chunk:
         chunk = B
+    elif max_chunk >= quad:
+        chunk = min(max_chunk // quad * quad, sms * 512)     # kernel time steps with ceil(warps per SM / 4): fill whole quads
     else:
         chunk = max_chunk // wave * wave                     # whole CTAs on every SM: no ragged last wave
     n_chunks = (B + chunk - 1) // chunk
@@ -326,8 +332,8 @@ def main():
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit limbs, canonical BN254 scalars)", "data": "synthetic",
-        "config": {"workload": f"{a.circuit} (iden3 authV2(40,64)): {B} input sets per GPU and step, {len(chunks)} launches of "
-                               f"{chunk} sets", "graph_nodes": info["n_nodes"], "node_ops": info["n_ops"], "inputs_len": I,
+        "config": {"workload": f"{a.circuit} (iden3 authV2(40,64)): {B} input sets per GPU and step, {len(chunks)} launches: "
+                               f"{len(chunks) - 1} x {chunk} + {chunks[-1][1] - chunks[-1][0]} sets", "graph_nodes": info["n_nodes"], "node_ops": info["n_ops"], "inputs_len": I,
                    "witness_len": W, "unique_input_sets": n_unique,
                    "l2": f"every launch writes {chunk * W * 32 / 1e9:.1f} GB of witness (>> 126 MB L2), no flush needed",
                    "regs_per_witness": info["n_regs"], "spill_slots": info["n_spill"]},

@@ -12,11 +12,11 @@ namespace gw {
 // op: an Opcode that is not a data-movement op.  C is only read for OP_TERN.  st collects StatusBits.
 GW_HD fe alu_exec(uint32_t op, const fe& A, fe Bv, const fe& C, uint32_t& st) {
   fe R;
-  if (op == OP_SQR) { Bv = A; op = OP_MUL; }
   if (op == OP_DIV) { Bv = fe_inv(Bv); op = OP_MUL; }                        // graph.rs:109 (b == 0 -> 0)
   else if (op == OP_POW) { R = fe_pow(A, Bv); st |= ST_POW; }
   switch (op) {
     case OP_MUL: R = fe_mul(A, Bv); break;                                   // graph.rs:105
+    case OP_SQR: R = fe_sqr(A); break;                                       // Mul(a, a)
     case OP_ADD: R = fe_add(A, Bv); break;                                   // graph.rs:110
     case OP_SUB: R = fe_sub(A, Bv); break;                                   // graph.rs:111
     case OP_POW: break;

@@ -102,9 +102,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
       if (op == OP_DOT) {
         // fused linear combination: 512-bit accumulator, ONE Montgomery reduction
         const uint32_t nt = ins.y & 0xFFu;
-        uint32_t P[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) P[k] = 0;
+        dot_acc P;
+        dot_init(P);
 #pragma unroll 1
         for (uint32_t t = 0; t < nt; t++) {
           const uint4 sl = ring[(pc + 1 + (t >> 1)) & (RING - 1)];
@@ -113,12 +112,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
           if (kind == T_MAC) {
             const fe c = const_load(ci);
             const fe x = rf_load(reg);
-            uint32_t Q[16];
-            u256_mul_wide(Q, x.l, c.l);
-            u512_add(P, Q);
+            dot_mac(P, x.l, c.l);
           } else if (kind == T_CONST) {
             const fe c = const_load(ci);
-            u512_add256(P, c.l, 0);
+            dot_add256(P, c.l, 0);
           } else {
             dot_term(P, kind, rf_load(reg), fe_zero());
           }
@@ -126,9 +123,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
         R = fe_mont_reduce(P, (int)((ins.y >> 8) & 0xFFu));
       } else if (op == OP_MUL || op == OP_SQR) {
         const fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
-        const fe Bv = (op == OP_SQR) ? A : ((ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z));
         uint32_t Pm[16];
-        u256_mul_wide(Pm, A.l, Bv.l);
+        if (op == OP_SQR) {
+          u256_sqr_wide(Pm, A.l);
+        } else {
+          const fe Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z);
+          u256_mul_wide(Pm, A.l, Bv.l);
+        }
         R = fe_barrett(Pm);
       } else if (op == OP_ADD || op == OP_SUB) {
         const fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
@@ -206,8 +207,7 @@ __global__ void __launch_bounds__(T) eval_latency_kernel(const LParams p) {
       R = fe_reduce256(fe_from(__ldg(p.inputs + 2 * (size_t)ins.y), __ldg(p.inputs + 2 * (size_t)ins.y + 1)));
     } else if (op == OP_MUL || op == OP_SQR) {
       fe A = operand(ins.x & F_A_CONST, ins.y);
-      fe Bv = (op == OP_SQR) ? A : operand(ins.x & F_B_CONST, ins.z);
-      R = fe_mul(A, Bv);
+      R = (op == OP_SQR) ? fe_sqr(A) : fe_mul(A, operand(ins.x & F_B_CONST, ins.z));
     } else if (op == OP_ADD || op == OP_SUB) {
       fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
       R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);

@@ -247,6 +247,70 @@ GW_HD void u256_mul_wide(uint32_t* out, const uint32_t* a, const uint32_t* b) {
 #endif
 }
 
+// a^2 as a 16-limb integer: the 28 cross products a_i*a_j (i < j) accumulated once on the even/odd pair accumulators
+// of u256_mul_wide, doubled with funnel shifts, and the 8 diagonal squares added by ONE carry chain of
+// (mad.lo.cc, madc.hi.cc) pairs whose addend is the doubled cross sum: 36 wide multiply-accumulates instead of 64.
+GW_HD void u256_sqr_wide(uint32_t* out, const uint32_t* a) {
+#if defined(GW_CHAINS)
+  uint32_t e[16], o[15];
+#pragma unroll
+  for (int i = 0; i < 16; i++) e[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 15; i++) o[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const uint32_t bi = a[i];
+    if (i + 2 < 8) {                       // j = i+2, i+4, ..: even columns i+j
+      e[2 * i + 2] = ptx_mad_lo_cc(a[i + 2], bi, e[2 * i + 2]);
+      e[2 * i + 3] = ptx_madc_hi_cc(a[i + 2], bi, e[2 * i + 3]);
+      int jl = i + 2;
+#pragma unroll
+      for (int j = i + 4; j < 8; j += 2) {
+        e[i + j] = ptx_madc_lo_cc(a[j], bi, e[i + j]);
+        e[i + j + 1] = ptx_madc_hi_cc(a[j], bi, e[i + j + 1]);
+        jl = j;
+      }
+      if (i + jl + 2 < 16) e[i + jl + 2] = ptx_addc(e[i + jl + 2], 0);
+    }
+    {                                      // j = i+1, i+3, ..: odd columns i+j, held at o[i+j-1]
+      o[2 * i] = ptx_mad_lo_cc(a[i + 1], bi, o[2 * i]);
+      o[2 * i + 1] = ptx_madc_hi_cc(a[i + 1], bi, o[2 * i + 1]);
+      int jl = i + 1;
+#pragma unroll
+      for (int j = i + 3; j < 8; j += 2) {
+        o[i + j - 1] = ptx_madc_lo_cc(a[j], bi, o[i + j - 1]);
+        o[i + j] = ptx_madc_hi_cc(a[j], bi, o[i + j]);
+        jl = j;
+      }
+      if (i + jl + 1 < 15) o[i + jl + 1] = ptx_addc(o[i + jl + 1], 0);
+    }
+  }
+  // cross sum C (columns 1..15; column 0 and e[0], e[1] are empty)
+  uint32_t C[16];
+  C[0] = 0;
+  C[1] = o[0];
+  C[2] = ptx_add_cc(e[2], o[1]);
+#pragma unroll
+  for (int k = 3; k < 15; k++) C[k] = ptx_addc_cc(e[k], o[k - 1]);
+  C[15] = ptx_addc(e[15], o[14]);
+  // out = 2 C + sum a_i^2 2^(64 i)
+  uint32_t D[16];
+  D[0] = 0;
+#pragma unroll
+  for (int k = 1; k < 16; k++) D[k] = (C[k] << 1) | (C[k - 1] >> 31);
+  out[0] = ptx_mad_lo_cc(a[0], a[0], D[0]);
+  out[1] = ptx_madc_hi_cc(a[0], a[0], D[1]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    out[2 * i] = ptx_madc_lo_cc(a[i], a[i], D[2 * i]);
+    if (i < 7) out[2 * i + 1] = ptx_madc_hi_cc(a[i], a[i], D[2 * i + 1]);
+    else out[2 * i + 1] = ptx_madc_hi(a[i], a[i], D[2 * i + 1]);
+  }
+#else
+  u256_mul_wide(out, a, a);
+#endif
+}
+
 // low 8 limbs of a*b
 GW_HD void u256_mul_lo(uint32_t* out, const uint32_t* a, const uint32_t* b) {
 #if defined(GW_CHAINS)
@@ -396,7 +460,11 @@ GW_HD fe fe_mul(const fe& a, const fe& b) {          // graph.rs:105
   u256_mul_wide(P, a.l, b.l);
   return fe_barrett(P);
 }
-GW_HD fe fe_sqr(const fe& a) { return fe_mul(a, a); }
+GW_HD fe fe_sqr(const fe& a) {
+  uint32_t P[16];
+  u256_sqr_wide(P, a.l);
+  return fe_barrett(P);
+}
 // two independent products in one basic block (instruction-level parallelism for the scheduler)
 GW_HD void fe_mul2(const fe& a1, const fe& b1, const fe& a2, const fe& b2, fe& r1, fe& r2) {
   uint32_t P1[16], P2[16];
@@ -409,30 +477,87 @@ GW_HD void fe_mul2(const fe& a1, const fe& b1, const fe& a2, const fe& b2, fe& r
 GW_HD_NOINLINE fe fe_mul_ni(const fe& a, const fe& b) { return fe_mul(a, b); }
 
 // ---- fused linear combinations (OP_DOT): 512-bit accumulator + ONE Montgomery reduction -----------------
-// P (16 limbs) += Q (16 limbs); the caller guarantees the sum stays below 2^512
-GW_HD void u512_add(uint32_t* P, const uint32_t* Q) {
+// The accumulator holds a 512-bit non-negative integer P; the plan compiler guarantees P < 2^512 (plan.cpp,
+// dot_bound).  Device form: the even/odd pair accumulators of u256_mul_wide (e[k] = column k, o[k] = column k + 1),
+// never merged -- products are accumulated in place and the Montgomery reduction consumes e and o directly.
+struct dot_acc {
 #if defined(GW_CHAINS)
-  P[0] = ptx_add_cc(P[0], Q[0]);
-#pragma unroll
-  for (int i = 1; i < 15; i++) P[i] = ptx_addc_cc(P[i], Q[i]);
-  P[15] = ptx_addc(P[15], Q[15]);
+  uint32_t e[16], o[15], K[9];   // K[k] counts lazy carries into column 8 + k: P = e + (o << 32) + (K << 256)
 #else
+  uint32_t P[16];
+#endif
+};
+GW_HD void dot_init(dot_acc& A) {
+#if defined(GW_CHAINS)
+#pragma unroll
+  for (int k = 0; k < 16; k++) A.e[k] = 0;
+#pragma unroll
+  for (int k = 0; k < 15; k++) A.o[k] = 0;
+#pragma unroll
+  for (int k = 0; k < 9; k++) A.K[k] = 0;
+#else
+  for (int k = 0; k < 16; k++) A.P[k] = 0;
+#endif
+}
+GW_HD void dot_load(dot_acc& A, const uint32_t* p16) {   // P <- a 16-limb integer
+  dot_init(A);
+#if defined(GW_CHAINS)
+#pragma unroll
+  for (int k = 0; k < 16; k++) A.e[k] = p16[k];
+#else
+  for (int k = 0; k < 16; k++) A.P[k] = p16[k];
+#endif
+}
+// P += a * b (8 x 8 limbs): the rows of u256_mul_wide; the carry out of every row chain is counted in K.
+GW_HD void dot_mac(dot_acc& A, const uint32_t* a, const uint32_t* b) {
+#if defined(GW_CHAINS)
+  uint32_t* e = A.e; uint32_t* o = A.o; uint32_t* K = A.K;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t bi = b[i];
+    const int p = i & 1;
+    {
+      const int c0 = i + p;
+      e[c0] = ptx_mad_lo_cc(a[p], bi, e[c0]);
+      e[c0 + 1] = ptx_madc_hi_cc(a[p], bi, e[c0 + 1]);
+#pragma unroll
+      for (int j = p + 2; j < 8; j += 2) {
+        e[i + j] = ptx_madc_lo_cc(a[j], bi, e[i + j]);
+        e[i + j + 1] = ptx_madc_hi_cc(a[j], bi, e[i + j + 1]);
+      }
+      K[c0] = ptx_addc(K[c0], 0);          // carry out of the last pair (columns c0+6, c0+7) -> column c0+8
+    }
+    {
+      const int q = 1 - p;
+      const int c0 = i + q - 1;
+      o[c0] = ptx_mad_lo_cc(a[q], bi, o[c0]);
+      o[c0 + 1] = ptx_madc_hi_cc(a[q], bi, o[c0 + 1]);
+#pragma unroll
+      for (int j = q + 2; j < 8; j += 2) {
+        o[i + j - 1] = ptx_madc_lo_cc(a[j], bi, o[i + j - 1]);
+        o[i + j] = ptx_madc_hi_cc(a[j], bi, o[i + j]);
+      }
+      K[c0 + 1] = ptx_addc(K[c0 + 1], 0);  // o[c0+8] is column c0+9
+    }
+  }
+#else
+  uint32_t Q[16];
+  u256_mul_wide(Q, a, b);
   uint64_t c = 0;
-  for (int i = 0; i < 16; i++) { c += (uint64_t)P[i] + Q[i]; P[i] = (uint32_t)c; c >>= 32; }
+  for (int i = 0; i < 16; i++) { c += (uint64_t)A.P[i] + Q[i]; A.P[i] = (uint32_t)c; c >>= 32; }
 #endif
 }
 // P += v (8 limbs) at limb offset `off` (0 or 8), carry propagated to the top
-GW_HD void u512_add256(uint32_t* P, const uint32_t* v, int off) {
+GW_HD void dot_add256(dot_acc& A, const uint32_t* v, int off) {
 #if defined(GW_CHAINS)
+  uint32_t* P = A.e;
   P[off] = ptx_add_cc(P[off], v[0]);
 #pragma unroll
-  for (int i = 1; i < 8; i++) P[off + i] = ptx_addc_cc(P[off + i], v[i]);
-  if (off == 0) {
-#pragma unroll
-    for (int i = 8; i < 15; i++) P[i] = ptx_addc_cc(P[i], 0);
-    P[15] = ptx_addc(P[15], 0);
-  }
+  for (int i = 1; i < 7; i++) P[off + i] = ptx_addc_cc(P[off + i], v[i]);
+  P[off + 7] = ptx_addc_cc(P[off + 7], v[7]);
+  A.K[off] = ptx_addc(A.K[off], 0);        // column off + 8 (K[8] = column 16 stays 0: P < 2^512)
 #else
+  uint32_t* P = A.P;
   uint64_t c = 0;
   for (int i = 0; i < 8; i++) { c += (uint64_t)P[off + i] + v[i]; P[off + i] = (uint32_t)c; c >>= 32; }
   for (int i = off + 8; i < 16; i++) { c += P[i]; P[i] = (uint32_t)c; c >>= 32; }
@@ -441,23 +566,17 @@ GW_HD void u512_add256(uint32_t* P, const uint32_t* v, int off) {
 // t = P * 2^-256 mod M for P < 2^512 with t_before_subtraction = (P + m*M) / 2^256 < 2^(n_cond_sub) * M and < 2^256
 // (the plan compiler bounds P term by term, see plan.cpp).  Word-serial Montgomery reduction: 8 rounds of
 // m = P[i] * (-M^-1) mod 2^32; P += m * M << 32 i, as two carry chains per round (even / odd limbs of M) whose
-// carry-outs are collected lazily in K (columns 8..16 are never read by a later round).  P is clobbered.
-GW_HD fe fe_mont_reduce_core(uint32_t* P) {
+// carry-outs are collected lazily in K (columns 8..16 are never read by a later round).  The accumulator is clobbered.
+GW_HD fe fe_mont_reduce_core(dot_acc& A) {
   fe r;
 #if defined(GW_CHAINS)
   // IMAD.WIDE accumulates into an ALIGNED register pair, so a column may only ever be the low half of a pair in one
   // array: e[] holds pairs starting at even columns (e[k] = column k), o[] pairs starting at odd columns (o[k] = column
-  // k + 1); P enters as e, o starts at zero.  Round i clears column i: its low word t = e[i] + o[i-1] + carry decides
-  // m; lo(m*M0) makes the column 0 mod 2^32 (carry out = [t != 0] + the carries of forming t) and is never stored.
+  // k + 1).  Round i clears column i: its low word t = e[i] + o[i-1] + carry decides m; lo(m*M0) makes the column
+  // 0 mod 2^32 (carry out = [t != 0] + the carries of forming t) and is never stored.
   // The array whose pairs START at column i takes hi(m*M0) and m*M2, m*M4, m*M6, the other one m*M1 .. m*M7; chain
   // carry-outs (columns i+8, i+9) are counted in K, which no later round reads.  Nothing is ever re-paired.
-  uint32_t e[16], o[15], K[9];
-#pragma unroll
-  for (int k = 0; k < 16; k++) e[k] = P[k];
-#pragma unroll
-  for (int k = 0; k < 15; k++) o[k] = 0;
-#pragma unroll
-  for (int k = 0; k < 9; k++) K[k] = 0;
+  uint32_t* e = A.e; uint32_t* o = A.o; uint32_t* K = A.K;
   uint32_t c = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -499,6 +618,7 @@ GW_HD fe fe_mont_reduce_core(uint32_t* P) {
   for (int k = 1; k < 7; k++) r.l[k] = ptx_addc_cc(r.l[k], K[k]);
   r.l[7] = ptx_addc(r.l[7], K[7]);
 #else
+  uint32_t* P = A.P;
   uint64_t top = 0;                                    // carries out of column 15
   for (int i = 0; i < 8; i++) {
     const uint32_t m = P[i] * MONT_INV32;
@@ -518,25 +638,23 @@ GW_HD void fe_cond_sub_n(fe& r, int n_cond_sub) {
   if (n_cond_sub >= 2) fe_cond_sub_ms<1>(r);
   fe_cond_sub_m(r);
 }
-GW_HD fe fe_mont_reduce(uint32_t* P, int n_cond_sub) {
-  fe r = fe_mont_reduce_core(P);
+GW_HD fe fe_mont_reduce(dot_acc& A, int n_cond_sub) {
+  fe r = fe_mont_reduce_core(A);
   fe_cond_sub_n(r, n_cond_sub);
   return r;
 }
 // one OP_DOT term (isa.h TermKind) accumulated into P; x = register value, c = table constant (pre-scaled)
-GW_HD void dot_term(uint32_t* P, uint32_t kind, const fe& x, const fe& c) {
+GW_HD void dot_term(dot_acc& A, uint32_t kind, const fe& x, const fe& c) {
   if (kind == 0) {                                     // T_MAC
-    uint32_t Q[16];
-    u256_mul_wide(Q, x.l, c.l);
-    u512_add(P, Q);
+    dot_mac(A, x.l, c.l);
   } else if (kind == 1) {                              // T_ADDHI
-    u512_add256(P, x.l, 8);
+    dot_add256(A, x.l, 8);
   } else if (kind == 2) {                              // T_SUBHI: + (M - x)
     fe m = fe_modulus(); uint32_t t[8];
     u256_sub(t, m.l, x.l);
-    u512_add256(P, t, 8);
+    dot_add256(A, t, 8);
   } else {                                             // T_CONST
-    u512_add256(P, c.l, 0);
+    dot_add256(A, c.l, 0);
   }
 }
 

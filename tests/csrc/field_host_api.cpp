@@ -9,6 +9,8 @@ static void st(uint32_t* p, const fe& a) { memcpy(p, a.l, 32); }
 extern "C" {
 void t_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, fe_mul(ld(a), ld(b))); }
 void t_mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* r16) { u256_mul_wide(r16, a, b); }
+void t_sqr_wide(const uint32_t* a, uint32_t* r16) { u256_sqr_wide(r16, a); }
+void t_sqr(const uint32_t* a, uint32_t* r) { st(r, fe_sqr(ld(a))); }
 void t_mul_lo(const uint32_t* a, const uint32_t* b, uint32_t* r8) { u256_mul_lo(r8, a, b); }
 void t_mont_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, fe_mont_mul(ld(a), ld(b))); }
 void t_to_mont(const uint32_t* a, uint32_t* r) { st(r, fe_to_mont(ld(a))); }
@@ -30,8 +32,13 @@ void t_inv(const uint32_t* a, uint32_t* r) { st(r, fe_inv_fermat(ld(a))); }
 extern "C" void t_inv_safegcd(const uint32_t* a, uint32_t* r) { st(r, gw::fe_inv(ld(a))); }
 extern "C" void t_mul_hi_trunc(const uint32_t* a, const uint32_t* b, uint32_t* r16) { gw::u256_mul_hi_trunc(r16, a, b); }
 // OP_DOT pieces: P (16 limbs) * 2^-256 mod M with n conditional subtractions, and one accumulated term
-extern "C" void t_mont_reduce(const uint32_t* p16, int ncs, uint32_t* r) { uint32_t P[16]; memcpy(P, p16, 64); st(r, gw::fe_mont_reduce(P, ncs)); }
-extern "C" void t_dot_term(uint32_t* p16, uint32_t kind, const uint32_t* x, const uint32_t* c) { gw::dot_term(p16, kind, ld(x), ld(c)); }
+extern "C" void t_mont_reduce(const uint32_t* p16, int ncs, uint32_t* r) { gw::dot_acc A; gw::dot_load(A, p16); st(r, gw::fe_mont_reduce(A, ncs)); }
+// n terms (kinds[t], xs[8t..], cs[8t..]) accumulated like the kernel does, then reduced
+extern "C" void t_dot_eval(const uint32_t* kinds, const uint32_t* xs, const uint32_t* cs, int n, int ncs, uint32_t* r) {
+  gw::dot_acc A; gw::dot_init(A);
+  for (int t = 0; t < n; t++) gw::dot_term(A, kinds[t], ld(xs + 8 * t), ld(cs + 8 * t));
+  st(r, gw::fe_mont_reduce(A, ncs));
+}
 extern "C" int t_emulates_ptx(void) {
 #if defined(GW_EMULATE_PTX)
   return 1;

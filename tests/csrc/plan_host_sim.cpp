@@ -64,7 +64,7 @@ int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
     if (op == OP_DOT) {
       const uint32_t nt = ins.y & 0xFF, ncs = (ins.y >> 8) & 0xFF;
       if (nt == 0 || nt > DOT_MAX_TERMS || ncs < 1 || ncs > 3) return false;
-      uint32_t P[16]; for (int k = 0; k < 16; k++) P[k] = 0;
+      dot_acc P; dot_init(P);
       for (uint32_t t = 0; t < nt; t++) {
         const Instr& sl = tail[t >> 1];
         const uint32_t lo = (t & 1) ? sl.z : sl.x, ci = (t & 1) ? sl.w : sl.y;

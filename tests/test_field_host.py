@@ -45,6 +45,8 @@ def test_field_and_integer_ops_random_and_edges(ptx):
         a, b = util.random_value(rnd), util.random_value(rnd)
         assert call2(L.t_mul, a, b) == a * b % M
         r16 = A16(); L.t_mul_wide(enc(a), enc(b), r16); assert dec(r16) == a * b
+        r16 = A16(); L.t_sqr_wide(enc(a), r16); assert dec(r16) == a * a
+        assert call1(L.t_sqr, a) == a * a % M
         r8 = A8(); L.t_mul_lo(enc(a), enc(b), r8); assert dec(r8) == (a * b) % (1 << 256)
         assert call2(L.t_mont_mul, a, b) == a * b * Rinv % M
         assert call1(L.t_to_mont, a) == a * R % M and call1(L.t_from_mont, a) == a * Rinv % M
@@ -80,6 +82,8 @@ def test_field_and_integer_ops_random_and_edges(ptx):
 @pytest.mark.parametrize("ptx", [False, True])
 def test_barrett_worst_cases(ptx):
     L = util.field_host_lib(ptx)
+    for a in ((1 << 256) - 1, (1 << 256) - (1 << 32), 0xFFFFFFFF, ((1 << 256) - 1) // 3, 1 << 255, 0):
+        r16 = A16(); L.t_sqr_wide(enc(a), r16); assert dec(r16) == a * a
     for a in (M - 1, M - 2, (M >> 1) + 1, 1 << 253, (1 << 253) + 1):
         for b in (M - 1, M - 2, (M >> 1), (1 << 253) - 1, 3):
             assert call2(L.t_mul, a, b) == a * b % M
@@ -113,17 +117,24 @@ def test_montgomery_reduction_of_accumulated_terms(ptx):
         if bound > 5.25:
             continue
         ncs = 1 if bound <= 2 else 2 if bound <= 4 else 3
-        P = A16(); want = 0
+        kinds, xs, cs, want = [], [], [], 0
+        def term(k, x, c):
+            kinds.append(k); xs.extend(enc(x)); cs.extend(enc(c))
         for _ in range(n_mac):
             x, c = pick(), pick()
-            L.t_dot_term(P, 0, enc(x), enc(c * R % M)); want += x * c
+            term(0, x, c * R % M); want += x * c
         for _ in range(n_hi):
             x = pick()
             if rnd.random() < 0.5:
-                L.t_dot_term(P, 1, enc(x), enc(0)); want += x
+                term(1, x, 0); want += x
             else:
-                L.t_dot_term(P, 2, enc(x), enc(0)); want -= x
+                term(2, x, 0); want -= x
         if rnd.random() < 0.5:
-            c = pick(); L.t_dot_term(P, 3, enc(0), enc(c * R % M)); want += c
-        r = A8(); L.t_mont_reduce(P, ncs, r)
+            c = pick(); term(3, 0, c * R % M); want += c
+        rnd.shuffle(order := list(range(len(kinds))))
+        kinds2 = [kinds[i] for i in order]
+        xs2 = [v for i in order for v in xs[8 * i:8 * i + 8]]
+        cs2 = [v for i in order for v in cs[8 * i:8 * i + 8]]
+        n = len(kinds2)
+        r = A8(); L.t_dot_eval((ctypes.c_uint32 * n)(*kinds2), (ctypes.c_uint32 * (8 * n))(*xs2), (ctypes.c_uint32 * (8 * n))(*cs2), n, ncs, r)
         assert dec(r) == want % M, (t, n_mac, n_hi)
