@@ -223,17 +223,28 @@ __global__ void __launch_bounds__(T) eval_latency_kernel(const LParams p) {
   const uint4 nop = make_uint4(OP_NOP, 0, 0, 0);
   const uint32_t nl = p.n_levels;
   uint32_t pos = 0;
+  // software pipeline over levels: the instruction of level L+2 is being fetched and the constants of level L+1
+  // are being pulled into L1 while level L executes, so a level starts with everything it needs already on the SM
   uint32_t c0 = __ldg(p.level_count), c1 = nl > 1 ? __ldg(p.level_count + 1) : 0, c2 = nl > 2 ? __ldg(p.level_count + 2) : 0;
   uint4 nxt = tid < c0 ? __ldg(p.code + tid) : nop;
+  uint4 nxt2 = tid < c1 ? __ldg(p.code + c0 + tid) : nop;
+  auto prefetch_consts = [&](const uint4& in) {
+    const uint32_t o = in.x & 0xFFu;
+    if (o == OP_NOP || o == OP_INPUT) return;
+    if (in.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)in.y);
+    if ((in.x & F_B_CONST) && op_has_b(o)) prefetch_l1(p.consts + 2 * (size_t)in.z);
+    if ((in.x & F_C_CONST) && o == OP_TERN) prefetch_l1(p.consts + 2 * (size_t)in.w);
+  };
+  prefetch_consts(nxt);
   for (uint32_t L = 0; L < nl; L++) {
     const uint4 ins = nxt;
     const uint32_t c = c0, npos = pos + c;
-    nxt = tid < c1 ? __ldg(p.code + npos + tid) : nop;                    // next level's instruction
+    nxt = nxt2;
+    prefetch_consts(nxt);                                                  // level L+1: a whole level of slack
+    nxt2 = tid < c2 ? __ldg(p.code + npos + c1 + tid) : nop;               // level L+2
     const uint32_t c3 = (L + 3 < nl) ? __ldg(p.level_count + L + 3) : 0;
     if (tid < c) exec(ins);
     for (uint32_t i = tid + T; i < c; i += T) exec(__ldg(p.code + pos + i));   // wide levels
-    if (nxt.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)nxt.y);
-    if ((nxt.x & F_B_CONST) && (nxt.x & 0xFFu) < 32) prefetch_l1(p.consts + 2 * (size_t)nxt.z);
     __syncthreads();
     pos = npos; c0 = c1; c1 = c2; c2 = c3;
   }
