@@ -56,13 +56,19 @@ _L.gw_calc_witness_batch.argtypes = [_vp, _vp, _sz, _vp, _vp, ctypes.c_int, ctyp
 _L.gw_calc_witness_batch_device.argtypes = [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, ctypes.POINTER(gw_status_t)]
 _L.gw_calc_witness_latency.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(gw_status_t)]
 _L.gw_wtns_header.argtypes = [ctypes.c_uint32, _vp]
+_L.gw_inputs_parse_batch.argtypes = [_vp, ctypes.c_char_p, _sz, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_sz), ctypes.POINTER(gw_status_t)]
+_L.gw_wtns_file_size.restype = _sz
+_L.gw_wtns_file_size.argtypes = [_vp]
+_L.gw_calc_witness_batch_wtns.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, ctypes.c_int, ctypes.POINTER(gw_status_t)]
+_L.gw_graph_select.argtypes = [_vp, _vp, _sz, ctypes.POINTER(_vp), ctypes.POINTER(gw_status_t)]
 _L.gw_device_count.restype = ctypes.c_int
 _L.gw_microbench_imad.restype = ctypes.c_double
 _L.gw_microbench_imad.argtypes = [ctypes.c_int, ctypes.c_int]
 
 EXPORTS = ["gw_calc_witness", "gw_graph_load", "gw_graph_free", "gw_graph_info", "gw_graph_input_signal",
            "gw_graph_calc_witness", "gw_calc_witness_batch", "gw_calc_witness_batch_device", "gw_calc_witness_latency", "gw_wtns_header",
-           "gw_device_count", "gw_microbench_imad"]
+           "gw_device_count", "gw_microbench_imad", "gw_inputs_parse_batch", "gw_wtns_file_size", "gw_calc_witness_batch_wtns",
+           "gw_graph_select"]
 
 
 class WitnessCalcError(RuntimeError):
@@ -119,11 +125,14 @@ def microbench_imad(device=0, which=0) -> float:
 class Graph:
     """A graph parsed, planned and (lazily) uploaded once: gw_graph_load."""
 
-    def __init__(self, graph_data: bytes):
+    def __init__(self, graph_data: bytes = None, _handle=None):
         self._h = _vp()
-        st = gw_status_t()
-        rc = _L.gw_graph_load(graph_data, len(graph_data), ctypes.byref(self._h), ctypes.byref(st))
-        _check(rc, st)
+        if _handle is not None:
+            self._h = _handle
+        else:
+            st = gw_status_t()
+            rc = _L.gw_graph_load(graph_data, len(graph_data), ctypes.byref(self._h), ctypes.byref(st))
+            _check(rc, st)
         info = gw_graph_info_t()
         _L.gw_graph_info(self._h, ctypes.byref(info))
         self.info = {k: int(getattr(info, k)) for k, _ in gw_graph_info_t._fields_}
@@ -178,6 +187,41 @@ class Graph:
                                       flags.ctypes.data if want_flags else None, n_gpus, ctypes.byref(st))
         _check(rc, st)
         return (out, flags) if want_flags else out
+
+    def parse_inputs_batch(self, text, n_threads=0) -> np.ndarray:
+        """JSON Lines (or a JSON array of objects) -> uint8 [B, I, 32] (gw_inputs_parse_batch, multi-threaded)."""
+        if isinstance(text, str):
+            text = text.encode("utf-8")
+        out, n, st = _vp(), _sz(), gw_status_t()
+        rc = _L.gw_inputs_parse_batch(self._h, text, len(text), n_threads, ctypes.byref(out), ctypes.byref(n), ctypes.byref(st))
+        _check(rc, st)
+        nbytes = n.value * self.n_inputs * 32
+        arr = np.frombuffer(ctypes.string_at(out.value, nbytes), dtype=np.uint8).reshape(n.value, self.n_inputs, 32).copy()
+        _libc.free(out)
+        return arr
+
+    def wtns_file_size(self) -> int:
+        return int(_L.gw_wtns_file_size(self._h))
+
+    def calc_witness_batch_wtns(self, inputs: np.ndarray, file_pitch=0, n_gpus=1) -> np.ndarray:
+        """HOST buffers: inputs uint8 [B, I, 32] -> uint8 [B, file_pitch]: row i starts with set i's complete .wtns
+        file (gw_calc_witness_batch_wtns)."""
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+        B = inputs.shape[0]
+        pitch = file_pitch or self.wtns_file_size()
+        out = np.zeros((B, pitch), dtype=np.uint8)
+        st = gw_status_t()
+        rc = _L.gw_calc_witness_batch_wtns(self._h, inputs.ctypes.data, B, out.ctypes.data, pitch, None, n_gpus, ctypes.byref(st))
+        _check(rc, st)
+        return out
+
+    def select(self, positions) -> "Graph":
+        """gw_graph_select: a graph whose witness is the given witness positions of this one."""
+        pos = np.ascontiguousarray(positions, dtype=np.uint32)
+        h, st = _vp(), gw_status_t()
+        rc = _L.gw_graph_select(self._h, pos.ctypes.data, len(pos), ctypes.byref(h), ctypes.byref(st))
+        _check(rc, st)
+        return Graph(_handle=h)
 
     def calc_witness_latency(self, inputs_row: np.ndarray, device=0):
         """ONE input set uint8 [I, 32] -> (witness uint8 [W, 32], kernel milliseconds): gw_calc_witness_latency."""

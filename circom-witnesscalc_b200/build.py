@@ -5,6 +5,7 @@
 Outputs (git-ignored, shipped to the GPU box by gpurun):
   circom-witnesscalc_b200/lib/libcircom_witnesscalc.so   the C-ABI library of include/graph_witness.h
   circom-witnesscalc_b200/bin/calc-witness               CLI with the reference's argv contract
+  circom-witnesscalc_b200/bin/calc-witness-batch         batch companion: <graph.bin> <inputs.jsonl> <out_dir> [n_gpus]
 """
 import os
 import subprocess
@@ -14,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libcircom_witnesscalc.so")
 BIN = os.path.join(HERE, "bin", "calc-witness")
+BIN_BATCH = os.path.join(HERE, "bin", "calc-witness-batch")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["engine.cu", "graph.cpp", "plan.cpp", "inputs.cpp", "wtns.cpp", "capi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -38,6 +40,10 @@ def build(force=False, verbose=False):
         subprocess.check_call(cmd)
     if force or _newer(BIN, [LIB, os.path.join(CSRC, "calc_witness_main.cpp")]):
         cmd = ["g++", "-O2", "-std=c++17", "-o", BIN, os.path.join(CSRC, "calc_witness_main.cpp"),
+               "-L" + os.path.dirname(LIB), "-lcircom_witnesscalc", "-Wl,-rpath,$ORIGIN/../lib"]
+        subprocess.check_call(cmd)
+    if force or _newer(BIN_BATCH, [LIB, os.path.join(CSRC, "calc_witness_batch_main.cpp")]):
+        cmd = ["g++", "-O2", "-std=c++17", "-o", BIN_BATCH, os.path.join(CSRC, "calc_witness_batch_main.cpp"),
                "-L" + os.path.dirname(LIB), "-lcircom_witnesscalc", "-Wl,-rpath,$ORIGIN/../lib"]
         subprocess.check_call(cmd)
     return LIB

@@ -153,6 +153,54 @@ int gw_calc_witness_latency(gw_graph_t* graph, int device, const uint8_t* inputs
   return guarded(status, [&]() { graph->engine->run_latency(device, inputs, witness, flags, kernel_ms); });
 }
 
+int gw_inputs_parse_batch(const gw_graph_t* graph, const char* text, size_t text_len, int n_threads, uint8_t** inputs,
+                          size_t* n_sets, gw_status_t* status) {
+  if (!graph || !text || !inputs || !n_sets) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() {
+    std::vector<U256> rows;
+    size_t n = parse_inputs_batch(graph->engine->graph, text, text_len, n_threads, rows);
+    uint8_t* out = (uint8_t*)malloc(std::max<size_t>(rows.size() * sizeof(U256), 1));
+    if (!out) throw Error("Failed to allocate memory for the input buffer");
+    memcpy(out, rows.data(), rows.size() * sizeof(U256));
+    *inputs = out; *n_sets = n;
+  });
+}
+
+size_t gw_wtns_file_size(const gw_graph_t* graph) { return graph ? wtns_size(graph->engine->plan.n_witness) : 0; }
+
+int gw_calc_witness_batch_wtns(gw_graph_t* graph, const uint8_t* inputs, size_t n_sets, uint8_t* files, size_t file_pitch,
+                               uint32_t* flags, int n_gpus, gw_status_t* status) {
+  if (!graph || (n_sets && (!inputs || !files))) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() {
+    const uint32_t W = graph->engine->plan.n_witness;
+    if (file_pitch < wtns_size(W)) throw Error("file_pitch is smaller than a .wtns file of this graph");
+    int ndev = cuda_device_count();
+    if (ndev == 0) throw Error("no CUDA device available: this library has no CPU fallback");
+    if (n_gpus < 1) n_gpus = 1;
+    if (n_gpus > ndev) throw Error("n_gpus exceeds the number of visible CUDA devices");
+    for (size_t i = 0; i < n_sets; i++) wtns_write_header(files + i * file_pitch, W);
+    graph->engine->run_host(inputs, n_sets, files + WTNS_HEADER_BYTES, flags, n_gpus, 0, file_pitch);
+  });
+}
+
+int gw_graph_select(const gw_graph_t* graph, const uint32_t* positions, size_t n_positions, gw_graph_t** selected,
+                    gw_status_t* status) {
+  if (!graph || !selected || (n_positions && !positions)) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() {
+    Graph sub = graph->engine->graph;                       // same nodes, constants and input map
+    const std::vector<uint32_t>& ws = graph->engine->graph.witness_signals;
+    sub.witness_signals.clear();
+    for (size_t i = 0; i < n_positions; i++) {
+      if (positions[i] >= ws.size()) throw Error("witness position out of range");
+      sub.witness_signals.push_back(ws[positions[i]]);
+    }
+    std::unique_ptr<gw_graph> g(new gw_graph());
+    g->engine.reset(new Engine(std::move(sub)));
+    g->input_names = graph->input_names;
+    *selected = g.release();
+  });
+}
+
 void gw_wtns_header(uint32_t n_witness, uint8_t* dst76) { wtns_write_header(dst76, n_witness); }
 
 int gw_device_count(void) { return cuda_device_count(); }

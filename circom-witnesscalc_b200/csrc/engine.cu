@@ -347,6 +347,11 @@ static int env_int(const char* name, int dflt) { const char* s = getenv(name); r
 
 Engine::Engine(const uint8_t* graph_data, size_t len) {
   graph = deserialize_witnesscalc_graph(graph_data, len);
+  init_plan();
+}
+Engine::Engine(Graph g) : graph(std::move(g)) { init_plan(); }
+
+void Engine::init_plan() {
   max_threads = env_int("GW_THREADS", MAX_THREADS);
   if (max_threads < 32 || max_threads > MAX_THREADS || (max_threads & 31)) throw Error("GW_THREADS must be a multiple of 32 in [32, 512]");
   PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", (int)opt.n_regs);
@@ -441,11 +446,13 @@ void Engine::run_device(int device, const void* d_inputs, size_t B, void* d_witn
 }
 
 // host buffers: chunked, double-buffered H2D -> kernel -> D2H on two streams
-void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status) {
+void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, size_t out_pitch) {
   Dev* d = dev(device);
   CUDA_CHECK(cudaSetDevice(device));
   std::lock_guard<std::mutex> lk(d->mu);
   const size_t in_b = (size_t)plan.n_inputs * 32, out_b = (size_t)plan.n_witness * 32;
+  if (out_pitch == 0) out_pitch = out_b;
+  if (out_pitch < out_b) throw Error("witness pitch is smaller than a witness row");
   // chunk size: bounded by a device-memory budget per staging buffer (two of them), at most two full
   // waves of resident threads, and small enough to give the copy/compute pipeline >= 4 stages when the
   // batch is large.  GW_CHUNK_MB overrides the budget.
@@ -477,7 +484,8 @@ void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* w
     if (off) CUDA_CHECK(cudaStreamWaitEvent(s, kdone[k ^ 1], 0));
     launch(d, d->d_in[k], nb, d->d_out[k], status ? d->d_status[k] : nullptr, s);
     CUDA_CHECK(cudaEventRecord(kdone[k], s));
-    CUDA_CHECK(cudaMemcpyAsync(witness + off * out_b, d->d_out[k], nb * out_b, cudaMemcpyDeviceToHost, s));
+    if (out_pitch == out_b) CUDA_CHECK(cudaMemcpyAsync(witness + off * out_b, d->d_out[k], nb * out_b, cudaMemcpyDeviceToHost, s));
+    else if (out_b) CUDA_CHECK(cudaMemcpy2DAsync(witness + off * out_pitch, out_pitch, d->d_out[k], out_b, out_b, nb, cudaMemcpyDeviceToHost, s));
     if (status) CUDA_CHECK(cudaMemcpyAsync(status + off, d->d_status[k], nb * 4, cudaMemcpyDeviceToHost, s));
   }
   CUDA_CHECK(cudaStreamSynchronize(d->stream[0]));
@@ -485,18 +493,19 @@ void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* w
   cudaEventDestroy(kdone[0]); cudaEventDestroy(kdone[1]);
 }
 
-void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device) {
+void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device, size_t out_pitch) {
   if (B == 0) return;
-  if (n_gpus <= 1) { run_host_on(first_device, inputs, B, witness, status); return; }
+  if (out_pitch == 0) out_pitch = (size_t)plan.n_witness * 32;
+  if (n_gpus <= 1) { run_host_on(first_device, inputs, B, witness, status, out_pitch); return; }
   // independent input sets: contiguous shards, one host thread per GPU, no collective
-  const size_t in_b = (size_t)plan.n_inputs * 32, out_b = (size_t)plan.n_witness * 32;
+  const size_t in_b = (size_t)plan.n_inputs * 32;
   std::vector<std::thread> th;
   std::vector<std::string> errs(n_gpus);
   for (int g = 0; g < n_gpus; g++) {
     size_t lo = B * g / n_gpus, hi = B * (g + 1) / n_gpus;
     if (hi == lo) continue;
     th.emplace_back([=, &errs]() {
-      try { run_host_on(first_device + g, inputs + lo * in_b, hi - lo, witness + lo * out_b, status ? status + lo : nullptr); }
+      try { run_host_on(first_device + g, inputs + lo * in_b, hi - lo, witness + lo * out_pitch, status ? status + lo : nullptr, out_pitch); }
       catch (const std::exception& e) { errs[g] = e.what(); }
     });
   }

@@ -13,6 +13,7 @@ namespace gw {
 class Engine {
  public:
   Engine(const uint8_t* graph_data, size_t len);
+  explicit Engine(Graph g);     // an already parsed graph (gw_graph_select: same nodes, a subset of the witness)
   ~Engine();
   Engine(const Engine&) = delete;
 
@@ -25,7 +26,10 @@ class Engine {
   // inputs/witness resident on `device`: inputs [B][I][32 B LE], witness [B][W][32 B LE]; asynchronous on `stream`
   void run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
   // host buffers; shards the batch over n_gpus devices starting at first_device (no collective)
-  void run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device);
+  // witness row r is written at witness + r * out_pitch (out_pitch >= W * 32 bytes; 0 = dense rows): with a pitch of
+  // wtns_size(W) rounded up and witness pointing WTNS_HEADER_BYTES into the first row, every row becomes a complete
+  // .wtns file image once the caller has written the 76-byte headers (the DMA engine does the framing).
+  void run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device, size_t out_pitch = 0);
   // single witness, latency mode (one CTA, intra-level node parallelism); host buffers
   void run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms);
   LatencyPlan lat_plan;
@@ -35,7 +39,8 @@ class Engine {
   struct Dev;
   Dev* dev(int device);
   void launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
-  void run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status);
+  void run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, size_t out_pitch);
+  void init_plan();
   std::map<int, Dev*> devs;
   std::mutex mu;
 };

@@ -2,6 +2,10 @@
 
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <thread>
+
 namespace gw {
 
 namespace {
@@ -145,6 +149,74 @@ std::vector<U256> build_inputs_buffer(const Graph& g, const InputList& inputs) {
     for (uint32_t i = 0; i < ln; i++) buf[off + i] = kv.second[i];
   }
   return buf;
+}
+
+
+// record boundaries: JSON Lines, or the elements of one top-level array (split at depth-1 commas, strings skipped)
+static void split_records(const char* text, size_t len, std::vector<std::pair<size_t, size_t>>& rec) {
+  size_t i = 0;
+  while (i < len && (text[i] == ' ' || text[i] == '\t' || text[i] == '\n' || text[i] == '\r')) i++;
+  if (i < len && text[i] == '[') {
+    int depth = 0; bool in_str = false; size_t start = 0;
+    for (; i < len; i++) {
+      const char c = text[i];
+      if (in_str) { if (c == '\\') i++; else if (c == '"') in_str = false; continue; }
+      if (c == '"') in_str = true;
+      else if (c == '[' || c == '{') { if (depth == 1 && c == '{') start = i; depth++; }
+      else if (c == ']' || c == '}') {
+        depth--;
+        if (depth == 1 && c == '}') rec.emplace_back(start, i + 1);
+        if (depth == 0) { i++; break; }
+      }
+    }
+    if (depth != 0 || in_str) throw Error("Failed to parse inputs: invalid JSON: unterminated array of input sets");
+    for (; i < len; i++) if (!(text[i] == ' ' || text[i] == '\t' || text[i] == '\n' || text[i] == '\r')) throw Error("Failed to parse inputs: invalid JSON: trailing characters");
+    return;
+  }
+  size_t ls = 0;
+  for (size_t k = 0; k <= len; k++) {
+    if (k == len || text[k] == '\n') {
+      size_t a = ls, b = k;
+      while (a < b && (text[a] == ' ' || text[a] == '\t' || text[a] == '\r')) a++;
+      while (b > a && (text[b - 1] == ' ' || text[b - 1] == '\t' || text[b - 1] == '\r')) b--;
+      if (b > a) rec.emplace_back(a, b);
+      ls = k + 1;
+    }
+  }
+}
+
+size_t parse_inputs_batch(const Graph& g, const char* text, size_t len, int n_threads, std::vector<U256>& out) {
+  std::vector<std::pair<size_t, size_t>> rec;
+  split_records(text, len, rec);
+  const size_t n = rec.size(), I = g.inputs_size;
+  out.assign(n * I, u256_from_u64(0));
+  if (n == 0) return 0;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<size_t>((size_t)n_threads, (n + 63) / 64);
+  std::atomic<size_t> next(0);
+  std::mutex emu; size_t err_rec = (size_t)-1; std::string err;
+  auto work = [&]() {
+    while (true) {
+      const size_t lo = next.fetch_add(64);
+      if (lo >= n) break;
+      for (size_t r = lo; r < std::min(n, lo + 64); r++) {
+        try {
+          InputList in = deserialize_inputs(text + rec[r].first, rec[r].second - rec[r].first);
+          std::vector<U256> row = build_inputs_buffer(g, in);
+          memcpy(&out[r * I], row.data(), I * sizeof(U256));
+        } catch (const std::exception& e) {
+          std::lock_guard<std::mutex> lk(emu);
+          if (r < err_rec) { err_rec = r; err = e.what(); }
+        }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (err_rec != (size_t)-1) throw Error("input set " + std::to_string(err_rec + 1) + ": " + err);
+  return n;
 }
 
 }  // namespace gw

@@ -14,4 +14,12 @@ InputList deserialize_inputs(const char* json, size_t len);
 // buffer of g.inputs_size values, slot 0 = 1, unmentioned slots = 0 (lib.rs:177-181)
 std::vector<U256> build_inputs_buffer(const Graph& g, const InputList& inputs);
 
+
+// Batch input path: a JSON Lines text (one inputs object per non-empty line; a single top-level
+// JSON array of objects is accepted too) -> n_sets x inputs_size x 32 B packed little-endian rows, parsed by
+// n_threads host threads (0 = hardware concurrency).  Every row goes through deserialize_inputs +
+// build_inputs_buffer, so values, errors and missing-key behaviour are those of the single-witness path.
+// Errors name the 1-based record.  `out` is resized to n_sets * inputs_size.
+size_t parse_inputs_batch(const Graph& g, const char* text, size_t len, int n_threads, std::vector<U256>& out);
+
 }  // namespace gw

@@ -111,6 +111,29 @@ int gw_calc_witness_batch_device(gw_graph_t *graph, int device, const void *d_in
 int gw_calc_witness_latency(gw_graph_t *graph, int device, const uint8_t *inputs, uint8_t *witness, uint32_t *flags,
                             float *kernel_ms, gw_status_t *status);
 
+/* ---- batch input path (replaces deserialize_inputs + populate_inputs, src/lib.rs:154-247, for many
+ * input sets).  `text` is JSON Lines (one inputs object per non-empty line) or one top-level JSON array of such
+ * objects; it is parsed by n_threads host threads (0 = all) into *inputs = a malloc'ed n_sets x n_inputs x 32 B
+ * buffer in the layout gw_calc_witness_batch takes (caller frees).  Per-record semantics and error texts are those
+ * of gw_calc_witness; the error message names the 1-based record. */
+int gw_inputs_parse_batch(const gw_graph_t *graph, const char *text, size_t text_len, int n_threads,
+                          uint8_t **inputs, size_t *n_sets, gw_status_t *status);
+
+/* ---- batch output path ----
+ * .wtns framing: like gw_calc_witness_batch, but set i is delivered as a complete .wtns file image
+ * (wtns_from_witness, src/lib.rs:114-123: 76-byte header + n_witness x 32 B) at files + i * file_pitch;
+ * file_pitch >= gw_wtns_file_size(graph) (bytes between consecutive images; pad as you like).  The payload rows
+ * are placed by the device-to-host DMA itself (pitched copy), the headers are written by the host. */
+size_t gw_wtns_file_size(const gw_graph_t *graph);
+int gw_calc_witness_batch_wtns(gw_graph_t *graph, const uint8_t *inputs, size_t n_sets, uint8_t *files, size_t file_pitch,
+                               uint32_t *flags, int n_gpus, gw_status_t *status);
+/* Selected signals only (e.g. the public outputs): a new graph handle whose witness consists of the given witness
+ * positions of `graph`, in the given order (repeats allowed).  Everything the selection does not depend on is dead
+ * code for the device program, and only n_positions x 32 B per set cross PCIe.  All entry points work on the result;
+ * free it with gw_graph_free. */
+int gw_graph_select(const gw_graph_t *graph, const uint32_t *positions, size_t n_positions, gw_graph_t **selected,
+                    gw_status_t *status);
+
 /* writes the 76-byte .wtns header for n_witness values (src/lib.rs:114-123) */
 void gw_wtns_header(uint32_t n_witness, uint8_t *dst76);
 

@@ -65,3 +65,65 @@ def test_string_escapes_and_whitespace():
     g = util.SimGraph(po.serialize_graph([(po.K_INPUT, 0), (po.K_INPUT, 1)], [1], {'a"b': (1, 1)}))
     assert g.inputs_from_json(' {\n "a\\"b" :\t"7" }\n') == [1, 7]
     assert g.inputs_from_json('{"a\\u0022b": ["7"]}') == [1, 7]
+
+
+# ---- batch input path (gw_inputs_parse_batch): product library, host-only code, no GPU needed ---------------------
+def _cwc():
+    import importlib
+    import subprocess
+    import os
+    subprocess.check_call(["python", os.path.join(util.ROOT, "circom-witnesscalc_b200", "build.py")])
+    return importlib.import_module("circom-witnesscalc_b200")
+
+
+def test_batch_parse_jsonl_and_array_match_single_record_semantics():
+    import json
+    import random
+    cwc = _cwc()
+    g = cwc.Graph(_graph())
+    nodes, _, imap = po.deserialize_graph(_graph())
+    rnd = random.Random(3)
+    recs = []
+    for i in range(1000):
+        r = {}
+        if rnd.random() < 0.9:
+            r["key1"] = [str(rnd.randrange(1 << 256)), rnd.randrange(1 << 64), str(rnd.randrange(M))]
+        if rnd.random() < 0.7:
+            r["key2"] = str(rnd.randrange(M)) if rnd.random() < 0.5 else rnd.randrange(1 << 40)
+        if rnd.random() < 0.5:
+            r["key3"] = [str(i)]
+        recs.append(r)
+    want = [po.build_input_buffer(nodes, imap, po.deserialize_inputs(json.dumps(r))) for r in recs]
+    jsonl = "\n".join(json.dumps(r) for r in recs) + "\n\n  \n"
+    for text in (jsonl, "\r\n".join(json.dumps(r, indent=None) for r in recs), json.dumps(recs, indent=1)):
+        for nt in (1, 4, 0):
+            arr = g.parse_inputs_batch(text, nt)
+            assert arr.shape == (1000, 6, 32)
+            got = [util.unpack_u256(arr[i].tobytes()) for i in range(0, 1000, 37)]
+            assert got == [want[i] for i in range(0, 1000, 37)]
+    assert g.parse_inputs_batch("").shape == (0, 6, 32) and g.parse_inputs_batch("[]").shape == (0, 6, 32)
+
+
+def test_batch_parse_errors_name_the_record():
+    cwc = _cwc()
+    g = cwc.Graph(_graph())
+    good = '{"key2": "5"}'
+    for bad, what in (('{"zzz": "1"}', "unknown input signal"), ('{"key1": ["1"]}', "Invalid input length"),
+                      ('{"key2": -1}', "not a positive integer"), ('{"key2": "1"', "invalid JSON"),
+                      ('{"key2": "12x"}', "InputFieldNumberParseError")):
+        text = "\n".join([good] * 70 + [bad] + [good] * 5)
+        with pytest.raises(cwc.WitnessCalcError, match="input set 71: .*" + what):
+            g.parse_inputs_batch(text, 3)
+    with pytest.raises(cwc.WitnessCalcError, match="unterminated array"):
+        g.parse_inputs_batch('[{"key2": "5"}, {"key2": "6"}')
+
+
+def test_graph_select_compiles_a_pruned_plan_without_gpu():
+    cwc = _cwc()
+    g = cwc.Graph(util.golden_graph("circuit9_authV2"))
+    sel = g.select([0, 1, 2, 1])
+    assert sel.n_witness == 4 and sel.n_inputs == g.n_inputs and sel.input_signals == g.input_signals
+    assert sel.info["n_instrs"] < g.info["n_instrs"]          # what the selection does not need is dead code
+    assert sel.wtns_file_size() == 76 + 4 * 32 and g.wtns_file_size() == 76 + 32 * g.n_witness
+    with pytest.raises(cwc.WitnessCalcError, match="out of range"):
+        g.select([g.n_witness])
