@@ -17,12 +17,14 @@ cat $OUT/bench_ref.json
 # launch list of the bench command (reduced steps; numbers printed under ncu are not bench values)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-# full capture of the batch kernel at the bench's occupancy (47 360 input sets = 320 threads per SM).  ncu replays the
+# full capture of the batch kernel at the bench's occupancy (56 832 input sets = 384 threads per SM).  ncu replays the
 # launch ~40 times and would have to save/restore the 146 GB of witness output each time, so for THIS capture only the
 # witness rows wrap modulo 4096 rows (GW_DEBUG_OUT_WRAP: same instruction stream, same stores, smaller footprint).
 GW_DEBUG_OUT_WRAP=4096 timeout 900 ncu --set full --clock-control none --import-source on -k regex:eval_batch -s 1 -c 1 -o $OUT/prof_authv2 \
-  python tools/gpu_probe.py --circuits circuit9_authV2 --batch 47360 --reps 1 --no-imad > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+  python tools/gpu_probe.py --circuits circuit9_authV2 --batch 56832 --reps 1 --no-imad > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:eval_batch -s 1 -c 1 -o $OUT/prof_poseidon4 \
   python tools/gpu_probe.py --circuits circuit7_poseidon4 --batch 75776 --reps 1 --no-imad > $OUT/ncu_full_p4.log 2>&1; echo "ncu full p4 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:eval_batch -s 1 -c 1 -o $OUT/prof_sha256 \
+  python tools/gpu_probe.py --circuits circuit8_sha256_512 --batch 16384 --reps 1 --no-imad > $OUT/ncu_full_sha.log 2>&1; echo "ncu full sha rc=$?"
 timeout 600 python tools/gpu_latency.py --reps 50 > $OUT/latency.jsonl 2> $OUT/latency.err; echo "latency rc=$?"; cat $OUT/latency.jsonl
 ls -la $OUT
