@@ -104,7 +104,7 @@ int gw_graph_info(const gw_graph_t* graph, gw_graph_info_t* info) {
   info->n_nodes = p.stats.graph_nodes; info->n_ops = p.stats.graph_ops;
   info->n_inputs = p.n_inputs; info->n_witness = p.n_witness;
   info->n_input_signals = (uint32_t)graph->input_names.size();
-  info->n_instrs = (uint32_t)p.stats.instrs; info->n_regs = p.n_regs; info->n_spill = p.n_spill;
+  info->n_instrs = (uint32_t)p.stats.instrs; info->n_regs = p.n_regs; info->n_spill = p.n_spill + (p.n_spill_narrow + 3) / 4;   /* 32-byte slot equivalents */
   info->n_mul = p.stats.mul_nodes; info->n_div = p.stats.div_nodes;
   info->n_spill_ld = p.stats.spill_ld; info->n_spill_st = p.stats.spill_st;
   info->n_slots = (uint32_t)p.stats.slots; info->n_dot = (uint32_t)p.stats.op_count[OP_DOT];
@@ -112,6 +112,7 @@ int gw_graph_info(const gw_graph_t* graph, gw_graph_info_t* info) {
   info->n_mul_instr = (uint32_t)(p.stats.op_count[OP_MUL] + p.stats.op_count[OP_SQR]);
   info->n_inversions = (uint32_t)p.stats.inversions;
   info->threads = (uint32_t)graph->engine->max_threads; info->sets_per_thread = 1;
+  info->n_narrow_instr = (uint32_t)p.stats.narrow_instrs;
   return 0;
 }
 

@@ -29,6 +29,8 @@ struct KParams {
   const uint4* inputs;     // [B][I][2]
   uint4* out;              // [B][W][2]
   uint4* spill;            // [n_spill][2][spill_threads]
+  uint2* nspill;           // [n_spill_narrow][spill_threads]: narrow values (threads of different warps are at
+                           // different instructions, so a slot must never change its per-thread layout)
   uint32_t* status;        // [B] or null
   unsigned long long B;
   uint32_t I, W;
@@ -70,6 +72,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
     if (c < p.n_hot) return fe_from(hot[2 * c], hot[2 * c + 1]);
     return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1));
   };
+  // narrow values: limbs 0..1 only
+  auto nrf_load2 = [&](uint32_t r) { return *reinterpret_cast<const uint2*>(&rf[(r * 2) * T]); };
+  auto nrf_load = [&](uint32_t r) { const uint2 v = nrf_load2(r); return (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32)); };
+  auto nrf_store = [&](uint32_t r, int64_t x) { *reinterpret_cast<uint2*>(&rf[(r * 2) * T]) = make_uint2((uint32_t)(uint64_t)x, (uint32_t)((uint64_t)x >> 32)); };
+  auto nconst_load = [&](uint32_t c) {
+    const uint2 v = (c < p.n_hot) ? *reinterpret_cast<const uint2*>(&hot[2 * c]) : __ldg(reinterpret_cast<const uint2*>(p.consts + 2 * (size_t)c));
+    return (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32));
+  };
 
   for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const unsigned long long w = (unsigned long long)tile * T + tid;
@@ -99,7 +109,45 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
 
       fe R;
       bool have_result = true;
-      if (op == OP_DOT) {
+      if (ins.x & F_NARROW) {
+        // narrow instruction (isa.h): int64 values in limbs 0..1 of their registers, 8-byte moves
+        int64_t r = 0;
+        bool have_r = true;
+        if (op == OP_DOT) {
+          const uint32_t nt = ins.y & 0xFFu;
+#pragma unroll 1
+          for (uint32_t t = 0; t < nt; t++) {
+            const uint4 sl = ring[(pc + 1 + (t >> 1)) & (RING - 1)];
+            const uint32_t lo = (t & 1) ? sl.z : sl.x, ci = (t & 1) ? sl.w : sl.y;
+            const uint32_t kind = lo & 0xFu;
+            const int64_t x = (kind == T_CONST) ? 0 : nrf_load(lo >> 16);
+            const int64_t c = (kind == T_MAC || kind == T_CONST) ? nconst_load(ci) : 0;
+            r = narrow_dot_term(r, kind, x, c);
+          }
+        } else if (op == OP_SPILL_ST) {
+          p.nspill[(size_t)ins.z * p.spill_threads + gthread] = nrf_load2(ins.y);
+          have_r = false;
+        } else if (op == OP_SPILL_LD) {
+          const uint2 v = p.nspill[(size_t)ins.y * p.spill_threads + gthread];
+          r = (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32));
+        } else if (op == OP_OUT) {
+          out_store(ins.w, fe_from_narrow(nrf_load(ins.y)));
+          have_r = false;
+        } else if (op == OP_SHRAND) {
+          r = narrow_shr_and(nrf_load(ins.y), ins.z & 0xFFu, nconst_load(ins.z >> 8));
+        } else {
+          const int64_t a = (ins.x & F_A_CONST) ? nconst_load(ins.y) : nrf_load(ins.y);
+          int64_t b = 0, c = 0;
+          if (op_has_b(op)) b = (ins.x & F_B_CONST) ? nconst_load(ins.z) : nrf_load(ins.z);
+          if (op == OP_TERN) c = (ins.x & F_C_CONST) ? nconst_load(ins.w) : nrf_load(ins.w);
+          r = narrow_exec(op, a, b, c);
+        }
+        if (have_r) {
+          if (dst != NO_DST) nrf_store(dst, r);
+          if (ins.x & F_OUT) out_store(ins.w, fe_from_narrow(r));
+        }
+        have_result = false;
+      } else if (op == OP_DOT) {
         // fused linear combination: 512-bit accumulator, ONE Montgomery reduction
         const uint32_t nt = ins.y & 0xFFu;
         dot_acc P;
@@ -357,6 +405,7 @@ void Engine::init_plan() {
   PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", (int)opt.n_regs);
   opt.div_batch = (uint32_t)env_int("GW_DIV_BATCH", (int)opt.div_batch);
   opt.fuse_dot = env_int("GW_FUSE_DOT", 1) != 0;
+  opt.narrow = env_int("GW_NARROW", 1) != 0;
   opt.max_terms = (uint32_t)env_int("GW_MAX_TERMS", (int)opt.max_terms);
   plan = compile_plan(graph, opt);
 }
@@ -410,7 +459,7 @@ Engine::Dev* Engine::dev(int device) {
   CUDA_CHECK(cudaMalloc(&d->consts, plan.consts.size() * 32));
   CUDA_CHECK(cudaMemcpy(d->consts, plan.consts.data(), plan.consts.size() * 32, cudaMemcpyHostToDevice));
   d->spill_threads = (size_t)d->sms * t_max;
-  if (plan.n_spill) CUDA_CHECK(cudaMalloc(&d->spill, (size_t)plan.n_spill * 32 * d->spill_threads));
+  if (plan.n_spill || plan.n_spill_narrow) CUDA_CHECK(cudaMalloc(&d->spill, ((size_t)plan.n_spill * 32 + (size_t)plan.n_spill_narrow * 8) * d->spill_threads));
   devs[device] = d;
   return d;
 }
@@ -420,6 +469,7 @@ void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uin
   KParams p;
   p.code = d->code; p.n_slots = (uint32_t)plan.code.size(); p.consts = d->consts;
   p.inputs = (const uint4*)d_inputs; p.out = (uint4*)d_witness; p.spill = d->spill; p.status = d_status;
+  p.nspill = reinterpret_cast<uint2*>(d->spill + (size_t)plan.n_spill * 2 * d->spill_threads);
   p.B = B; p.I = plan.n_inputs; p.W = plan.n_witness;
   const int T = threads_for(B, d->sms, d->max_threads);
   size_t n_tiles = (B + T - 1) / T;

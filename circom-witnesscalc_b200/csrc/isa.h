@@ -22,6 +22,7 @@ enum Opcode : uint32_t {
   OP_NEG = 32, OP_ID = 33, OP_LNOT = 34, OP_BNOT = 35,
   OP_INV = 36,       // dst <- a^-1 mod M (0 -> 0); only produced by the plan compiler (batched Div)
   OP_NZ1 = 37,       // dst <- (a == 0) ? 1 : a;    only produced by the plan compiler (batched Div)
+  OP_WIDEN = 38,     // dst <- canonical 256-bit form of the NARROW value a; only produced by the plan compiler
   OP_TERN = 40,
   OP_INPUT = 48,     // dst <- inputs[w][a] mod M
   OP_SPILL_ST = 49,  // spill[b] <- reg a
@@ -38,7 +39,19 @@ enum Flags : uint32_t {
   F_B_CONST = 1u << 9,
   F_C_CONST = 1u << 10,
   F_OUT = 1u << 11,      // also store the result to witness position .w
+  F_NARROW = 1u << 12,   // narrow instruction: operands and result are signed 64-bit integers (see below)
 };
+
+// Narrow values.  The plan compiler proves, by interval arithmetic over the graph (sound for EVERY input:
+// inputs themselves are never assumed small), that some values always lie in (-2^62, 2^62) when read as
+// signed field elements (x > M/2 means x - M, the reading of the reference's comparisons, graph.rs:723-769).
+// Such a value is computed by a narrow instruction (F_NARROW) on a two's-complement int64 kept in limbs 0..1
+// of its register (limbs 2..7 are NOT written); add/sub/mul wrap mod 2^64, which is exact because the true
+// result fits.  A register written by a wide instruction whose value is provably in [0, 2^62) can be read by
+// a narrow instruction directly (canonical == zero-extended); a narrow register read by a wide instruction
+// goes through OP_WIDEN first.  Witness stores of narrow results convert to canonical (v < 0 -> M + v).
+// With F_NARROW: OP_DOT terms are (reg * c64 | +reg | -reg | c64) with plain (not pre-scaled) int64 constants
+// in limbs 0..1 of the constant table entry; OP_SPILL_ST / OP_SPILL_LD move 8 bytes; OP_OUT converts.
 
 // OP_DOT terms.  A term is (lo, hi): lo = kind[3:0] | register << 16, hi = constant-table index.
 // The accumulator P is a 512-bit integer; the result is P * 2^-256 mod M (Montgomery reduction), so

@@ -121,6 +121,158 @@ Graph rewrite_div_batches(const Graph& g, uint32_t kmax) {
   return ng;
 }
 
+// ---- narrow typing (isa.h: F_NARROW) -------------------------------------------------------------------
+// Interval arithmetic over the graph on the SIGNED reading of field elements (x > M/2 means x - M).  Nothing is
+// assumed about inputs; ranges enter through constants, comparisons ({0,1}), masks (Band with a small operand)
+// and right shifts, and propagate through Add/Sub/Mul/Neg/TernCond as long as they stay inside (-2^62, 2^62).
+// narrow[i] = 1: node i is computed by a narrow instruction (all its operands are readable as int64) and only
+// limbs 0..1 of its register are valid.  A wide node with a known range is readable by narrow instructions
+// only if the range is non-negative (canonical == zero-extended int64); otherwise its range is forgotten.
+struct VRange { bool known = false; int64_t lo = 0, hi = 0; };
+struct Typing { std::vector<VRange> rng; std::vector<uint8_t> narrow; };
+const int64_t NARROW_LIM = (int64_t)1 << 62;
+
+bool signed_small(const U256& c, int64_t* out) {
+  bool small = true;
+  for (int k = 2; k < 8; k++) small &= c.l[k] == 0;
+  uint64_t lo = (uint64_t)c.l[0] | ((uint64_t)c.l[1] << 32);
+  if (small && lo < (uint64_t)NARROW_LIM) { *out = (int64_t)lo; return true; }
+  // M - c small?
+  uint32_t d[8]; uint64_t borrow = 0;
+  for (int k = 0; k < 8; k++) { uint64_t t = (uint64_t)BN254_M.l[k] - c.l[k] - borrow; d[k] = (uint32_t)t; borrow = (t >> 32) & 1u; }
+  if (borrow) return false;                      // c > M: not canonical
+  for (int k = 2; k < 8; k++) if (d[k]) return false;
+  lo = (uint64_t)d[0] | ((uint64_t)d[1] << 32);
+  if (lo == 0 || lo >= (uint64_t)NARROW_LIM) return false;
+  *out = -(int64_t)lo;
+  return true;
+}
+// the int64 form narrow instructions read from the constant table (limbs 0..1; sign-extended above)
+U256 narrow_const(int64_t v) {
+  U256 r; const uint32_t ext = v < 0 ? 0xFFFFFFFFu : 0u;
+  r.l[0] = (uint32_t)(uint64_t)v; r.l[1] = (uint32_t)((uint64_t)v >> 32);
+  for (int k = 2; k < 8; k++) r.l[k] = ext;
+  return r;
+}
+
+Typing infer_types(const Graph& g, const std::vector<uint8_t>& needed, bool enable) {
+  const size_t N = g.nodes.size();
+  Typing ty; ty.rng.assign(N, VRange()); ty.narrow.assign(N, 0);
+  if (!enable) return ty;
+  typedef __int128 i128;
+  auto fits = [&](i128 lo, i128 hi) { return lo > -(i128)NARROW_LIM && hi < (i128)NARROW_LIM; };
+  auto bits_mask = [&](int64_t a, int64_t b) {     // smallest 2^k - 1 >= max(a, b), a, b >= 0
+    uint64_t m = (uint64_t)std::max(a, b), r = 0;
+    while (r < m) r = (r << 1) | 1u;
+    return (int64_t)r;
+  };
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i]) continue;
+    const Node& nd = g.nodes[i];
+    VRange r; bool nar = false;
+    auto set = [&](i128 lo, i128 hi) { if (fits(lo, hi)) { r.known = true; r.lo = (int64_t)lo; r.hi = (int64_t)hi; } };
+    if (nd.kind == N_CONST) {
+      int64_t v; if (signed_small(g.constants.at(nd.a), &v)) set(v, v);
+    } else if (nd.kind == N_INPUT) {
+      if (nd.a == 0) set(1, 1);                  // get_inputs_buffer forces slot 0 to 1 (lib.rs:177-181)
+    } else if (nd.kind == N_UNO) {
+      const VRange& a = ty.rng[nd.a];
+      const uint32_t op = OP_NEG + nd.op;
+      if (op == OP_NEG) { if (a.known) { set(-(i128)a.hi, -(i128)a.lo); nar = r.known; } }
+      else if (op == OP_NZ1) { if (a.known) { set(std::min<int64_t>(a.lo, 1), std::max<int64_t>(a.hi, 1)); nar = r.known; } }
+      else if (op == OP_WIDEN) { if (a.known) set(a.lo, a.hi); }
+      else if (op == OP_LNOT) set(0, 1);
+    } else if (nd.kind == N_DUO) {
+      const VRange& a = ty.rng[nd.a];
+      const VRange& b = ty.rng[nd.b];
+      const bool both = a.known && b.known;
+      const bool both_nn = both && a.lo >= 0 && b.lo >= 0;
+      switch (nd.op) {
+        case OP_ADD: if (both) { set((i128)a.lo + b.lo, (i128)a.hi + b.hi); nar = r.known; } break;
+        case OP_SUB: if (both) { set((i128)a.lo - b.hi, (i128)a.hi - b.lo); nar = r.known; } break;
+        case OP_MUL:
+          if (both) {
+            i128 p[4] = {(i128)a.lo * b.lo, (i128)a.lo * b.hi, (i128)a.hi * b.lo, (i128)a.hi * b.hi};
+            set(std::min(std::min(p[0], p[1]), std::min(p[2], p[3])), std::max(std::max(p[0], p[1]), std::max(p[2], p[3])));
+            nar = r.known;
+          }
+          break;
+        case OP_EQ: case OP_NEQ: case OP_LT: case OP_GT: case OP_LEQ: case OP_GEQ: case OP_LAND: case OP_LOR:
+          set(0, 1); nar = both; break;
+        case OP_BAND:
+          if (both_nn) { set(0, std::min(a.hi, b.hi)); nar = true; }
+          else if (a.known && a.lo >= 0) set(0, a.hi);
+          else if (b.known && b.lo >= 0) set(0, b.hi);
+          break;
+        case OP_BOR: case OP_BXOR:
+          if (both_nn) { set(0, bits_mask(a.hi, b.hi)); nar = r.known; }
+          break;
+        case OP_SHR:
+          if (b.known && b.lo == b.hi && b.lo >= 0) {
+            const int64_t k = b.lo;
+            if (a.known && a.lo >= 0) { set(0, k >= 63 ? 0 : (a.hi >> k)); nar = true; }
+            else if (k >= 254) set(0, 0);
+            else if (k >= 192) set(0, (int64_t)((((uint64_t)1 << 62) - 1) >> (k - 192)));   // a < 2^254
+          } else if (a.known && a.lo >= 0) {
+            set(0, a.hi);                        // a right shift never grows; b >= 254 gives 0
+            nar = b.known && b.lo >= 0;
+          }
+          break;
+        case OP_SHL:
+          if (a.known && a.lo >= 0 && b.known && b.lo == b.hi && b.lo >= 0 && b.lo < 62) { set(0, (i128)a.hi << b.lo); nar = r.known; }
+          break;
+        default: break;                          // Div, Pow, Idiv, Mod: wide, unknown
+      }
+    } else if (nd.kind == N_TRES) {
+      const VRange& c = ty.rng[nd.a];
+      const VRange& x = ty.rng[nd.b];
+      const VRange& y = ty.rng[nd.c];
+      if (x.known && y.known) { set(std::min(x.lo, y.lo), std::max(x.hi, y.hi)); nar = c.known && r.known; }
+    }
+    if (nd.kind >= N_UNO && !nar && r.known && r.lo < 0) r.known = false;
+    ty.rng[i] = r;
+    ty.narrow[i] = nar ? 1 : 0;
+  }
+  return ty;
+}
+
+// A narrow node read by a wide node goes through one OP_WIDEN node (shared by all its wide consumers).  Dead
+// nodes are dropped.  The typing of the new graph is carried over (it is what infer_types would compute).
+Graph rewrite_widen(const Graph& g, const std::vector<uint8_t>& needed, const Typing& ty, Typing* ty2) {
+  const size_t N = g.nodes.size();
+  Graph ng;
+  ng.constants = g.constants; ng.inputs = g.inputs; ng.inputs_size = g.inputs_size;
+  ng.nodes.reserve(N + N / 8);
+  ty2->rng.clear(); ty2->narrow.clear();
+  std::vector<uint32_t> map(N, 0xFFFFFFFFu), widened(N, 0xFFFFFFFFu);
+  auto push = [&](const Node& nd, const VRange& r, uint8_t nar) {
+    ng.nodes.push_back(nd); ty2->rng.push_back(r); ty2->narrow.push_back(nar);
+    return (uint32_t)ng.nodes.size() - 1;
+  };
+  for (size_t i = 0; i < N; i++) {
+    if (!needed[i]) continue;
+    Node nd = g.nodes[i];
+    uint32_t* ops[3] = {&nd.a, &nd.b, &nd.c};
+    for (int k = 0; k < n_operands(nd); k++) {
+      const uint32_t o = *ops[k];
+      if (!ty.narrow[i] && ty.narrow[o]) {
+        if (widened[o] == 0xFFFFFFFFu) {
+          Node w; w.kind = N_UNO; w.op = (uint8_t)(OP_WIDEN - OP_NEG); w.a = map[o]; w.b = w.c = 0;
+          VRange r = ty.rng[o]; if (r.lo < 0) r.known = false;
+          widened[o] = push(w, r, 0);
+        }
+        *ops[k] = widened[o];
+      } else {
+        *ops[k] = map[o];
+      }
+    }
+    map[i] = push(nd, ty.rng[i], ty.narrow[i]);
+  }
+  ng.witness_signals.reserve(g.witness_signals.size());
+  for (uint32_t s : g.witness_signals) ng.witness_signals.push_back(map[s]);
+  return ng;
+}
+
 // ---- macro ops -----------------------------------------------------------------------------------------
 struct PTerm { uint8_t kind; bool neg; uint32_t node; U256 c; };   // kind: 0 value*const, 1 value, 2 const
 struct MOp {
@@ -130,6 +282,7 @@ struct MOp {
   std::vector<PTerm> terms;       // OP_DOT
   uint32_t ncs = 1;
   uint32_t shift = 0; U256 mask;  // OP_SHRAND
+  bool narrow = false;            // F_NARROW: int64 operands and result
 };
 
 // bound of the Montgomery-reduced sum before the conditional subtractions, in units of M:
@@ -146,9 +299,11 @@ struct Allocator {
   std::vector<uint32_t> use_ptr;           // per value: index of its next unconsumed use
   std::vector<int32_t> reg_of, spill_of;   // per value
   std::vector<int32_t> reg_val;            // per register: value or -1
-  std::vector<uint32_t> free_regs, free_spill;
-  uint32_t n_spill = 0;
+  std::vector<uint32_t> free_regs, free_spill, free_spill_n;   // wide and narrow values spill to separate slot pools
+  uint32_t n_spill = 0, n_spill_n = 0;
   Plan& plan;
+  const std::vector<uint8_t>* val_narrow = nullptr;    // per value: narrow (8-byte spill moves)
+  uint32_t nflag(uint32_t v) const { return (val_narrow && (*val_narrow)[v]) ? (uint32_t)F_NARROW : 0u; }
 
   Allocator(size_t n, uint32_t n_regs, const std::vector<uint32_t>& us, const std::vector<uint32_t>& ul, Plan& p)
       : use_start(us), use_list(ul), use_ptr(n), reg_of(n, -1), spill_of(n, -1), reg_val(n_regs, -1), plan(p) {
@@ -175,10 +330,11 @@ struct Allocator {
     uint32_t v = (uint32_t)reg_val[best];
     if (spill_of[v] < 0) {                 // first eviction of this value: write it out once (SSA: never changes)
       uint32_t s;
-      if (!free_spill.empty()) { s = free_spill.back(); free_spill.pop_back(); }
-      else s = n_spill++;
+      std::vector<uint32_t>& pool = nflag(v) ? free_spill_n : free_spill;
+      if (!pool.empty()) { s = pool.back(); pool.pop_back(); }
+      else s = nflag(v) ? n_spill_n++ : n_spill++;
       spill_of[v] = (int32_t)s;
-      emit(make_instr(OP_SPILL_ST, 0, NO_DST, (uint32_t)best, s, 0));
+      emit(make_instr(OP_SPILL_ST, nflag(v), NO_DST, (uint32_t)best, s, 0));
       plan.stats.spill_st++;
     }
     reg_of[v] = -1;
@@ -188,7 +344,7 @@ struct Allocator {
   void bind(uint32_t v, uint32_t r) { reg_of[v] = (int32_t)r; reg_val[r] = (int32_t)v; }
   void release(uint32_t v) {               // value is dead
     if (reg_of[v] >= 0) { reg_val[reg_of[v]] = -1; free_regs.push_back((uint32_t)reg_of[v]); reg_of[v] = -1; }
-    if (spill_of[v] >= 0) { free_spill.push_back((uint32_t)spill_of[v]); spill_of[v] = -1; }
+    if (spill_of[v] >= 0) { (nflag(v) ? free_spill_n : free_spill).push_back((uint32_t)spill_of[v]); spill_of[v] = -1; }
   }
 };
 
@@ -214,9 +370,25 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
   Graph rewritten;
   const bool batch = opt.div_batch > 1 && plan.stats.div_nodes >= 2;
   if (batch) rewritten = rewrite_div_batches(g0, opt.div_batch);
-  const Graph& g = batch ? rewritten : g0;
+  const Graph& g1 = batch ? rewritten : g0;
+  // narrow typing; narrow values read by wide nodes get an explicit OP_WIDEN node
+  Typing ty;
+  Graph widened;
+  bool any_narrow = false;
+  {
+    const std::vector<uint8_t> nd1 = liveness(g1);
+    Typing t1 = infer_types(g1, nd1, opt.narrow);
+    for (uint8_t x : t1.narrow) any_narrow |= x != 0;
+    if (any_narrow) widened = rewrite_widen(g1, nd1, t1, &ty); else ty = std::move(t1);
+  }
+  const Graph& g = any_narrow ? widened : g1;
   const size_t N = g.nodes.size();
   const std::vector<uint8_t> needed = liveness(g);
+  auto nconst_of = [&](const U256& c, bool neg) {       // int64 table form of a small signed constant
+    int64_t v = 0;
+    if (!signed_small(c, &v)) throw Error("plan: narrow instruction with a wide constant");
+    return narrow_const(neg ? -v : v);
+  };
 
   // constants: N_CONST nodes, and Input(0) which get_inputs_buffer forces to 1 (lib.rs:177-181).  const_val is the
   // canonical value; table entries are interned on first use (raw for ordinary operands, pre-scaled for OP_DOT).
@@ -273,11 +445,12 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
     if (uses[s] != 1 || n_out(s) != 0 || !needed[consumer[s]]) return false;
     const Node& c = g.nodes[consumer[s]];
     if (!(c.kind == N_DUO && c.op == OP_BAND) || c.a == c.b) return false;
+    if (ty.narrow[s] && !ty.narrow[consumer[s]]) return false;
     return is_const[c.a == s ? c.b : c.a] != 0;
   };
   auto emit_dot = [&](uint32_t node, std::vector<PTerm>& terms) {
-    MOp m; m.node = node; m.opc = OP_DOT; m.terms = std::move(terms);
-    double b = dot_bound(m.terms);
+    MOp m; m.node = node; m.opc = OP_DOT; m.terms = std::move(terms); m.narrow = ty.narrow[node] != 0;
+    double b = m.narrow ? 1.0 : dot_bound(m.terms);
     m.ncs = b <= 2.0 ? 1 : b <= 4.0 ? 2 : 3;
     mops.push_back(std::move(m));
   };
@@ -309,7 +482,7 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
             else if (deferred[o]) { for (PTerm t : dterms[o]) { t.neg = (t.neg != neg); terms.push_back(t); } }
             else terms.push_back(PTerm{1, neg, o, U256()});
           }
-          if (terms.size() <= max_terms && dot_bound(terms) <= max_bound) break;
+          if (terms.size() <= max_terms && (ty.narrow[i] || dot_bound(terms) <= max_bound)) break;
           // over budget: turn the larger deferred operand into a plain value and retry
           uint32_t victim = 0xFFFFFFFFu; size_t vsz = 0;
           for (int k = 0; k < 2; k++) { uint32_t o = operand(nd, k); if (!is_const[o] && deferred[o] && dterms[o].size() >= vsz) { victim = o; vsz = dterms[o].size(); } }
@@ -323,8 +496,9 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       }
       bool has_mac = false;
       for (const PTerm& t : terms) has_mac |= (t.kind == 0);
-      if (has_mac) {
-        const bool can_defer = uses[i] == 1 && n_out(i) == 0 && is_addsub(consumer[i]) && needed[consumer[i]];
+      if (has_mac || ty.narrow[i]) {                   // narrow sums are always one instruction (no reduction to pay for)
+        const bool can_defer = uses[i] == 1 && n_out(i) == 0 && is_addsub(consumer[i]) && needed[consumer[i]] &&
+                               ty.narrow[consumer[i]] == ty.narrow[i];
         if (can_defer) { deferred[i] = 1; dterms[i] = std::move(terms); }
         else emit_dot(i, terms);
         continue;
@@ -336,10 +510,11 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       const uint32_t s = absorbed[nd.a] ? nd.a : nd.b, c = absorbed[nd.a] ? nd.b : nd.a;
       MOp m; m.node = i; m.opc = OP_SHRAND; m.n_in = 1; m.in[0] = g.nodes[s].a;
       m.shift = const_val[g.nodes[s].b].l[0]; m.mask = const_val[c];
+      m.narrow = ty.narrow[s] && ty.narrow[i];         // a wide SHRAND writes all 8 limbs: fine for narrow readers
       mops.push_back(m);
       continue;
     }
-    MOp m; m.node = i;
+    MOp m; m.node = i; m.narrow = ty.narrow[i] != 0;
     m.n_in = n_operands(nd);
     for (int k = 0; k < m.n_in; k++) { m.in[k] = operand(nd, k); if (deferred[m.in[k]]) materialize(m.in[k]); }
     if (nd.kind == N_INPUT) m.opc = OP_INPUT;
@@ -370,6 +545,7 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
 
   // constants that are witness signals themselves (e.g. witness[0] = Input(0) = 1)
   Allocator al(N, opt.n_regs, use_start, use_list, plan);
+  al.val_narrow = &ty.narrow;
   plan.code.reserve(mops.size() + mops.size() / 2);
   for (size_t i = 0; i < N; i++) {
     if (!needed[i] || !is_const[i]) continue;
@@ -389,7 +565,7 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       if (al.reg_of[x] < 0) {
         if (al.spill_of[x] < 0) throw Error("plan: operand neither resident nor spilled");
         uint32_t r = al.alloc_reg(pinned);
-        al.emit(make_instr(OP_SPILL_LD, 0, r, (uint32_t)al.spill_of[x], 0, 0));
+        al.emit(make_instr(OP_SPILL_LD, al.nflag(x), r, (uint32_t)al.spill_of[x], 0, 0));
         plan.stats.spill_ld++;
         al.bind(x, r);
       }
@@ -399,13 +575,14 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
     Enc encs[2];
     for (int u = 0; u < n_unit; u++) {
       const MOp& m = mops[p + u];
-      Enc& e = encs[u]; e.enc[0] = e.enc[1] = e.enc[2] = 0; e.flags = 0;
+      Enc& e = encs[u]; e.enc[0] = e.enc[1] = e.enc[2] = 0; e.flags = m.narrow ? (uint32_t)F_NARROW : 0u;
+      if (m.narrow) plan.stats.narrow_instrs++;
       if (m.opc == OP_DOT) {
         std::vector<uint32_t> words;
         for (const PTerm& t : m.terms) {
           uint32_t kind = t.kind == 0 ? (uint32_t)T_MAC : t.kind == 2 ? (uint32_t)T_CONST : (t.neg ? (uint32_t)T_SUBHI : (uint32_t)T_ADDHI);
           uint32_t reg = t.kind == 2 ? 0u : (uint32_t)al.reg_of[t.node];
-          uint32_t ci = t.kind == 1 ? 0u : intern(prescale(t.c, t.neg));
+          uint32_t ci = t.kind == 1 ? 0u : intern(m.narrow ? nconst_of(t.c, t.neg) : prescale(t.c, t.neg));
           words.push_back(kind | (reg << 16)); words.push_back(ci);
           plan.stats.dot_terms[kind]++;
         }
@@ -415,10 +592,10 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
         e.enc[0] = g.nodes[m.node].a;
       } else if (m.opc == OP_SHRAND) {
         e.enc[0] = (uint32_t)al.reg_of[m.in[0]];
-        e.enc[1] = m.shift | (intern(m.mask) << 8);
+        e.enc[1] = m.shift | (intern(m.narrow ? nconst_of(m.mask, false) : m.mask) << 8);
       } else {
         for (int k = 0; k < m.n_in; k++) {
-          if (is_const[m.in[k]]) { e.enc[k] = intern(const_val[m.in[k]]); e.flags |= (F_A_CONST << k); }
+          if (is_const[m.in[k]]) { e.enc[k] = intern(m.narrow ? nconst_of(const_val[m.in[k]], false) : const_val[m.in[k]]); e.flags |= (F_A_CONST << k); }
           else e.enc[k] = (uint32_t)al.reg_of[m.in[k]];
         }
       }
@@ -461,12 +638,13 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       const MOp& m = mops[p + u];
       const uint32_t no = n_out(m.node);
       const uint32_t* outs = &out_list[out_start[m.node]];
-      for (uint32_t k = out_inline[u] ? 1u : 0u; k < no; k++) { al.emit(make_instr(OP_OUT, 0, NO_DST, dsts[u], 0, outs[k])); plan.stats.outs++; }
+      for (uint32_t k = out_inline[u] ? 1u : 0u; k < no; k++) { al.emit(make_instr(OP_OUT, al.nflag(m.node), NO_DST, dsts[u], 0, outs[k])); plan.stats.outs++; }
       if (need_reg[u] && !has_uses[u]) { al.release(m.node); live--; }
     }
     p += n_unit;
   }
   plan.n_spill = al.n_spill;
+  plan.n_spill_narrow = al.n_spill_n;
   plan.stats.slots = plan.code.size();
   if (plan.consts.empty()) plan.consts.push_back(u256_from_u64(0));
 

@@ -25,6 +25,7 @@ struct PlanOptions {
   uint32_t div_batch = 8;    // max Div nodes sharing one inversion (1 = off)
   bool fuse_dot = true;      // fuse linear combinations into OP_DOT
   uint32_t max_terms = 8;    // max terms of one OP_DOT (<= DOT_MAX_TERMS, <= n_regs - 3)
+  bool narrow = true;        // narrow typing: provably small values are computed on int64 (isa.h: F_NARROW)
 };
 
 struct PlanStats {
@@ -37,12 +38,14 @@ struct PlanStats {
   uint64_t div_nodes = 0;                    // live Div nodes of the graph
   uint64_t mul_nodes = 0;                    // live Mul nodes of the graph
   uint32_t max_live = 0;                     // peak number of simultaneously live values
+  uint64_t narrow_instrs = 0;                // emitted narrow (int64) instructions, spill moves excluded
 };
 
 struct Plan {
   std::vector<Instr> code;   // slots
   std::vector<U256> consts;
   uint32_t n_regs = 0, n_spill = 0;
+  uint32_t n_spill_narrow = 0;   // 8-byte spill slots of narrow values (a pool of their own: [slot][thread] uint2)
   uint32_t n_inputs = 0;     // I: length of the input buffer incl. slot 0
   uint32_t n_witness = 0;    // W
   PlanStats stats;

@@ -75,7 +75,7 @@ typedef struct {
   uint32_t n_inversions;  /* modular inversions after Div batching */
   uint32_t threads;       /* threads per CTA */
   uint32_t sets_per_thread; /* input sets evaluated per thread */
-  uint32_t reserved;
+  uint32_t n_narrow_instr; /* instructions computed on int64 (values the plan compiler proves to be small, isa.h F_NARROW) */
 } gw_graph_info_t;
 
 /* replaces storage::deserialize_witnesscalc_graph (src/storage.rs:214-249) + upload; parse once */

@@ -21,7 +21,7 @@ static fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 
 extern "C" {
 
-// flags: bit 0 = fuse linear combinations (OP_DOT), bits 8.. = div_batch (0 -> default)
+// flags: bit 0 = fuse linear combinations (OP_DOT), bit 1 = narrow typing OFF, bits 8.. = div_batch (0 -> default)
 SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags, char* err, size_t errlen);
 SimGraph* sim_load(const uint8_t* data, size_t len, uint32_t n_regs, char* err, size_t errlen) {
   return sim_load2(data, len, n_regs, 1, err, errlen);
@@ -30,13 +30,14 @@ SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags,
   try {
     std::unique_ptr<SimGraph> s(new SimGraph());
     s->g = deserialize_witnesscalc_graph(data, len);
-    PlanOptions o; o.n_regs = n_regs; o.fuse_dot = (flags & 1) != 0;
+    PlanOptions o; o.n_regs = n_regs; o.fuse_dot = (flags & 1) != 0; o.narrow = (flags & 2) == 0;
     if (flags >> 8) o.div_batch = (uint32_t)(flags >> 8);
     s->plan = compile_plan(s->g, o);
     return s.release();
   } catch (const std::exception& e) { if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; } return nullptr; }
 }
 void sim_free(SimGraph* s) { delete s; }
+void sim_info2(SimGraph* s, uint64_t* out) { out[0] = s->plan.stats.narrow_instrs; out[1] = s->plan.stats.op_count[OP_WIDEN]; out[2] = s->plan.n_spill_narrow; }
 void sim_info(SimGraph* s, uint64_t* out) {
   const PlanStats& st = s->plan.stats;
   out[0] = s->g.nodes.size(); out[1] = s->plan.n_inputs; out[2] = s->plan.n_witness; out[3] = st.instrs;
@@ -49,6 +50,7 @@ void sim_info(SimGraph* s, uint64_t* out) {
 int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
   const Plan& p = s->plan;
   std::vector<fe> rf(p.n_regs, fe_zero()), spill(p.n_spill, fe_zero());
+  std::vector<int64_t> nspill(p.n_spill_narrow, 0);
   uint32_t st = 0;
   // value of one instruction from the CURRENT register file (no writes); false on a malformed instruction
   auto compute = [&](const Instr& ins, const Instr* tail, fe* out) {
@@ -92,6 +94,49 @@ int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
     if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
     return true;
   };
+  // narrow instructions (isa.h: F_NARROW): int64 in limbs 0..1; limbs 2..7 of a narrow register are poisoned here
+  // so that any wide read of a narrow value (a plan compiler bug) shows up as a wrong witness
+  auto nload = [&](uint32_t idx, bool is_const, int64_t* o) {
+    if (is_const) { if (idx >= p.consts.size()) return false; *o = narrow_of(to_fe(p.consts[idx])); }
+    else { if (idx >= p.n_regs) return false; *o = narrow_of(rf[idx]); }
+    return true;
+  };
+  auto poison = [&](int64_t v) { fe r; r.l[0] = (uint32_t)(uint64_t)v; r.l[1] = (uint32_t)((uint64_t)v >> 32); for (int i = 2; i < 8; i++) r.l[i] = 0xDEADBEEFu; return r; };
+  auto narrow_step = [&](const Instr& ins, const Instr* tail) {
+    const uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
+    int64_t r = 0, a = 0, b = 0, c = 0;
+    if (op == OP_SPILL_ST) { if (ins.y >= p.n_regs || ins.z >= p.n_spill_narrow) return false; nspill[ins.z] = narrow_of(rf[ins.y]); return true; }
+    if (op == OP_OUT) {
+      if (!nload(ins.y, false, &a) || ins.w >= p.n_witness) return false;
+      fe v = fe_from_narrow(a); memcpy(witness + 32 * (size_t)ins.w, v.l, 32); return true;
+    }
+    if (op == OP_SPILL_LD) { if (ins.y >= p.n_spill_narrow) return false; r = nspill[ins.y]; }
+    else if (op == OP_DOT) {
+      const uint32_t nt = ins.y & 0xFF;
+      if (nt == 0 || nt > DOT_MAX_TERMS) return false;
+      for (uint32_t t = 0; t < nt; t++) {
+        const Instr& sl = tail[t >> 1];
+        const uint32_t lo = (t & 1) ? sl.z : sl.x, ci = (t & 1) ? sl.w : sl.y;
+        const uint32_t kind = lo & 0xF, reg = lo >> 16;
+        int64_t x = 0, cc = 0;
+        if (kind > T_CONST) return false;
+        if (kind != T_CONST && !nload(reg, false, &x)) return false;
+        if ((kind == T_MAC || kind == T_CONST) && !nload(ci, true, &cc)) return false;
+        r = narrow_dot_term(r, kind, x, cc);
+      }
+    } else if (op == OP_SHRAND) {
+      if (!nload(ins.y, false, &a) || !nload(ins.z >> 8, true, &c)) return false;
+      r = narrow_shr_and(a, ins.z & 0xFF, c);
+    } else {
+      if (!nload(ins.y, ins.x & F_A_CONST, &a)) return false;
+      if (op_has_b(op) && !nload(ins.z, ins.x & F_B_CONST, &b)) return false;
+      if (op == OP_TERN && !nload(ins.w, ins.x & F_C_CONST, &c)) return false;
+      r = narrow_exec(op, a, b, c);
+    }
+    if (dst != NO_DST) { if (dst >= p.n_regs) return false; rf[dst] = poison(r); }
+    if (ins.x & F_OUT) { if (ins.w >= p.n_witness) return false; fe v = fe_from_narrow(r); memcpy(witness + 32 * (size_t)ins.w, v.l, 32); }
+    return true;
+  };
   for (size_t pc = 0; pc < p.code.size();) {
     const Instr& ins = p.code[pc];
     const uint32_t len = instr_slots(ins);
@@ -99,6 +144,7 @@ int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
     const uint32_t op = ins.x & 0xFF;
     pc += len;
     if (op == OP_NOP) continue;
+    if (ins.x & F_NARROW) { if (!narrow_step(ins, &p.code[pc - len + 1])) return -1; continue; }
     if (op == OP_SPILL_ST) { if (ins.y >= p.n_regs || ins.z >= p.n_spill) return -1; spill[ins.z] = rf[ins.y]; continue; }
     fe R;
     if (!compute(ins, &p.code[pc - len + 1], &R) || !commit(ins, R)) return -1;

@@ -147,3 +147,106 @@ def test_dot_worst_case_bounds():
             g = util.SimGraph(po.serialize_graph(nodes, wit, {"x": (1, 1)}), 16)
             for x in (M - 1, 0, 1, M - 2):
                 assert g.eval([1, x])[0] == po.evaluate(nodes, [1, x], wit, "circom"), (n_mac, n_plain, x)
+
+
+def _narrow_graph(rnd, n_ops=300, n_inputs=6):
+    """Graphs that live mostly in the plan compiler's narrow domain (isa.h: F_NARROW): bits and small words cut
+    out of arbitrary inputs (Shr+Band, Band with a small mask, Shr by >= 192, comparisons), then sums, products,
+    negations, selects, bitwise ops and shifts over them -- with ranges that grow until they leave (-2^62, 2^62)
+    and fall back to wide instructions, negative intermediates, wide consumers of narrow values (OP_WIDEN) and
+    narrow consumers of wide non-negative values."""
+    D = po.DUO
+    nodes = [(po.K_INPUT, i) for i in range(n_inputs + 1)]
+    consts = {}
+    for v in [0, 1, 2, 3, 5, 7, 31, 32, 62, 63, 64, 100, 192, 200, 253, 254, 255, 0xFF, 0xFFFF, 0xFFFFFFFF, (1 << 61) - 1, (1 << 62) - 1,
+              1 << 62, (1 << 64) - 1, po.M - 1, po.M - 2, po.M - 5, po.M - (1 << 40), po.M - (1 << 62) + 1, po.M - (1 << 62), (po.M >> 1),
+              (po.M >> 1) + 1, 1 << 20, 1 << 31, 1 << 40] + [util.random_value(rnd) for _ in range(4)]:
+        consts[v % po.M] = len(nodes)
+        nodes.append((po.K_CONST, v % po.M))
+    cl = list(consts.values())
+    small_c = [consts[v] for v in (0, 1, 2, 3, 5, 7, 31, 0xFF, 0xFFFF, 0xFFFFFFFF, po.M - 1, po.M - 2, po.M - 5)]
+    shift_c = [consts[v] for v in (0, 1, 2, 3, 5, 7, 31, 32, 62, 63, 64, 100, 192, 200, 253, 254, 255)]
+    wide = list(range(1, n_inputs + 1))
+    narrow = []
+    for _ in range(n_ops):
+        n = len(nodes)
+        r = rnd.random()
+        pn = lambda: (rnd.choice(narrow[-10:]) if rnd.random() < 0.6 else rnd.choice(narrow)) if narrow and rnd.random() < 0.9 else rnd.choice(small_c)
+        pw = lambda: rnd.choice(wide[-8:]) if rnd.random() < 0.6 else rnd.choice(wide)
+        if r < 0.12 or not narrow:     # sources of narrow values
+            k = rnd.random()
+            if k < 0.4:
+                nodes.append((po.K_DUO, D["Shr"], pw(), rnd.choice(shift_c)))
+                nodes.append((po.K_DUO, D["Band"], n, rnd.choice([consts[1], consts[0xFF], consts[0xFFFF], consts[0xFFFFFFFF], consts[(1 << 61) - 1]])))
+                n += 1
+            elif k < 0.55:
+                nodes.append((po.K_DUO, D["Band"], rnd.choice([consts[0xFFFF], consts[(1 << 62) - 1], consts[1 << 62], consts[7]]), pw()))
+            elif k < 0.7:
+                nodes.append((po.K_DUO, D["Shr"], pw(), rnd.choice([consts[192], consts[200], consts[253], consts[254], consts[255], consts[100]])))
+            else:
+                nodes.append((po.K_DUO, rnd.choice([D["Eq"], D["Neq"], D["Lt"], D["Gt"], D["Leq"], D["Geq"], D["Land"], D["Lor"]]), pw(), pw()))
+            narrow.append(n)
+        elif r < 0.50:
+            nodes.append((po.K_DUO, D["Add" if rnd.random() < 0.55 else "Sub"], pn(), pn())); narrow.append(n)
+        elif r < 0.62:
+            nodes.append((po.K_DUO, D["Mul"], pn(), pn() if rnd.random() < 0.6 else rnd.choice(small_c + [consts[1 << 20], consts[1 << 31], consts[1 << 40]]))); narrow.append(n)
+        elif r < 0.66:
+            nodes.append((po.K_UNO, 0, pn())); narrow.append(n)
+        elif r < 0.72:
+            nodes.append((po.K_TRES, 0, pn() if rnd.random() < 0.7 else pw(), pn(), pn())); narrow.append(n)
+        elif r < 0.80:
+            nodes.append((po.K_DUO, rnd.choice([D["Band"], D["Bor"], D["Bxor"]]), pn(), pn())); narrow.append(n)
+        elif r < 0.86:
+            op = rnd.choice([D["Shr"], D["Shl"]])
+            nodes.append((po.K_DUO, op, pn(), rnd.choice(shift_c[:10]) if rnd.random() < 0.8 else pn())); narrow.append(n)
+        elif r < 0.92:
+            nodes.append((po.K_DUO, rnd.choice([D["Eq"], D["Neq"], D["Lt"], D["Gt"], D["Leq"], D["Geq"], D["Land"], D["Lor"]]), pn(), pn())); narrow.append(n)
+        else:                          # wide consumers of narrow values, results are wide values again
+            op = rnd.choice([D["Mul"], D["Add"], D["Sub"], D["Div"], D["Band"], D["Bxor"], D["Lt"], D["Idiv"], D["Mod"], D["Shr"]])
+            a, b = (pn(), pw()) if rnd.random() < 0.5 else (pw(), pn())
+            if rnd.random() < 0.2:
+                b = rnd.choice(cl)
+            nodes.append((po.K_DUO, op, a, b)); wide.append(n)
+    n = len(nodes)
+    wit = [0] + [rnd.randrange(n) for _ in range(40)] + list(range(n - 10, n))
+    return nodes, wit, {"x": (1, n_inputs)}
+
+
+@pytest.mark.parametrize("n_regs,fuse", [(4, True), (6, True), (12, True), (12, False), (32, True)])
+def test_narrow_typing(n_regs, fuse):
+    rnd = random.Random(9100 + n_regs + int(fuse))
+    n_narrow = n_widen = 0
+    for t in range(30):
+        nodes, wit, imap = _narrow_graph(rnd)
+        data = po.serialize_graph(nodes, wit, imap)
+        g = util.SimGraph(data, n_regs, fuse=fuse)
+        off = util.SimGraph(data, n_regs, fuse=fuse, narrow=False)
+        assert off.info["narrow_instrs"] == 0 and off.info["widen"] == 0
+        for row in range(4):
+            inp = [1] + [rnd.choice([0, 1, po.M - 1, po.M - 2, (1 << 256) - 1, (1 << 62) - 1, 1 << 62, (1 << 64) - 1]) if rnd.random() < 0.3
+                         else util.random_value(rnd) for _ in range(6)]
+            want = po.evaluate(nodes, inp, wit, "circom")
+            assert g.eval(inp)[0] == want, (t, row)
+            assert off.eval(inp)[0] == want, (t, row)
+        n_narrow += g.info["narrow_instrs"]
+        n_widen += g.info["widen"]
+    assert n_narrow > 1000 and n_widen > 0
+
+
+def test_narrow_range_limits():
+    """sums and products right at the +-2^62 boundary of the narrow domain, and negative results as witness values"""
+    M = po.M
+    D = po.DUO
+    for bits in (30, 31, 32, 40, 61, 62):
+        mask = (1 << bits) - 1
+        nodes = [(po.K_INPUT, 0), (po.K_INPUT, 1), (po.K_INPUT, 2), (po.K_CONST, mask), (po.K_CONST, 0), (po.K_CONST, 1)]
+        nodes.append((po.K_DUO, D["Band"], 1, 3)); a = 6
+        nodes.append((po.K_DUO, D["Band"], 2, 3)); b = 7
+        nodes += [(po.K_DUO, D["Mul"], a, b), (po.K_DUO, D["Sub"], 4, a), (po.K_DUO, D["Sub"], b, a), (po.K_DUO, D["Mul"], 9, b),
+                  (po.K_DUO, D["Add"], a, b), (po.K_DUO, D["Add"], 12, 12), (po.K_DUO, D["Mul"], 10, 10), (po.K_UNO, 0, 8),
+                  (po.K_DUO, D["Lt"], 9, 10), (po.K_DUO, D["Geq"], 10, 4), (po.K_TRES, 0, 10, 9, 13), (po.K_DUO, D["Sub"], 18, 5)]
+        wit = list(range(len(nodes)))
+        g = util.SimGraph(po.serialize_graph(nodes, wit, {"x": (1, 2)}), 8)
+        assert g.info["narrow_instrs"] > 0
+        for x, y in [(mask, mask), (0, mask), (mask, 0), (0, 0), (1, mask), (M - 1, M - 2), ((1 << 256) - 1, 12345), (mask + 1, mask >> 1)]:
+            assert g.eval([1, x, y])[0] == po.evaluate(nodes, [1, x, y], wit, "circom"), (bits, x, y)
