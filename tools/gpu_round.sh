@@ -26,5 +26,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:eval
   python tools/gpu_probe.py --circuits circuit7_poseidon4 --batch 75776 --reps 1 --no-imad > $OUT/ncu_full_p4.log 2>&1; echo "ncu full p4 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:eval_batch -s 1 -c 1 -o $OUT/prof_sha256 \
   python tools/gpu_probe.py --circuits circuit8_sha256_512 --batch 16384 --reps 1 --no-imad > $OUT/ncu_full_sha.log 2>&1; echo "ncu full sha rc=$?"
+timeout 300 python tools/pcie_probe.py > $OUT/pcie.jsonl 2>&1; cat $OUT/pcie.jsonl
 timeout 600 python tools/gpu_latency.py --reps 50 > $OUT/latency.jsonl 2> $OUT/latency.err; echo "latency rc=$?"; cat $OUT/latency.jsonl
 ls -la $OUT
