@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--batch", type=int, default=262144, help="input sets per GPU and step")
     ap.add_argument("--chunk", type=int, default=0, help="input sets per kernel launch (0 = auto)")
     ap.add_argument("--unique", type=int, default=16384, help="distinct synthetic input sets (tiled to --batch)")
-    ap.add_argument("--e2e-sets", type=int, default=8192)
+    ap.add_argument("--e2e-sets", type=int, default=16384)
     ap.add_argument("--cpu-sample", type=int, default=0, help="input sets for the cpu_baseline leg (0 = 96 x cores)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

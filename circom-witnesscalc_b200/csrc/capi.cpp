@@ -51,7 +51,15 @@ static void calc_one(Engine& eng, const char* json, void** wtns_data, size_t* wt
     // GW_SINGLE_MODE=batch asks for the throughput kernel with a batch of one
     const char* mode = getenv("GW_SINGLE_MODE");
     if (mode && !strcmp(mode, "batch")) eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, 0);
-    else eng.run_latency(0, (const uint8_t*)buf.data(), out + WTNS_HEADER_BYTES, nullptr, nullptr);
+    else {
+      // a graph whose live values do not fit the latency kernel's shared-memory value file still gets its witness from
+      // the GPU: the throughput kernel with a batch of one
+      try { eng.run_latency(0, (const uint8_t*)buf.data(), out + WTNS_HEADER_BYTES, nullptr, nullptr); }
+      catch (const Error& e) {
+        if (strncmp(e.what(), "latency plan:", 13) != 0) throw;
+        eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, 0);
+      }
+    }
   } catch (...) { free(out); throw; }
   *wtns_data = out; *wtns_len = n;
 }

@@ -227,74 +227,191 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
 }
 
 // ---- single-witness latency mode ------------------------------------------------------------------------
-// One CTA evaluates ONE witness: the instructions of a dependency level are spread over the threads
-// (intra-level node parallelism), values live in one shared-memory slot file, a CTA barrier separates
-// levels.  Each thread prefetches its instruction of the next level while it executes the current one.
+// One CTA evaluates ONE witness (plan.hpp: LatencyPlan).  MAIN warps run the plan level by level: every lane takes
+// one instruction of the level (instructions of one class share a warp, different classes sit in different warps and
+// therefore on different SM sub-partitions), values live in one shared-memory slot file, a named barrier over the
+// main warps separates levels.  SLOW warps run the long operations (Div/Inv/Pow/Idiv/Mod) asynchronously: a job
+// starts when the main warps have published the level that produces its operands, and its readers sit behind an
+// OP_WAIT on the job counter of that slow warp.  Headers of level L+2, tails/constants of level L+1 are in flight
+// while level L executes.
 struct LParams {
-  const uint4* code; const uint32_t* level_count; uint32_t n_levels;
-  const uint4* consts;
+  const uint4* code; const uint4* first; uint32_t n_levels, n_warps;
+  const uint4* jobs; const uint32_t* n_jobs; uint32_t max_jobs, n_slow;
+  const uint4* waits; uint32_t n_waits;
   const uint4* inputs;     // [I][2]
   uint4* out;              // [W][2]
   uint32_t* status;        // [1] or null
+  uint32_t n_slots;
+  uint32_t dbg;            // GW_LAT_DBG, timing experiments only: 1 = no witness stores, 16 = no instructions (level skeleton alone)
+  unsigned long long* level_clock;   // profiling aid (GW_LAT_CLOCKS): clock64 at the end of every level, or null
 };
 
-template <int T>
-__global__ void __launch_bounds__(T) eval_latency_kernel(const LParams p) {
-  extern __shared__ uint4 slots[];     // [n_slots][2]
-  const uint32_t tid = threadIdx.x;
-  auto slot_load = [&](uint32_t r) { return fe_from(slots[2 * r], slots[2 * r + 1]); };
-  auto const_load = [&](uint32_t c) { return fe_from(__ldg(p.consts + 2 * (size_t)c), __ldg(p.consts + 2 * (size_t)c + 1)); };
+static const int LAT_MAX_THREADS = 384;     // main + control + slow warps <= 12: 170 registers per thread
+static const uint32_t LAT_RING_SLOTS = 128; // packet ring: 3 stages x 2 KB per main warp (plan.hpp: LatencyOptions::packet_slots)
+
+// Shared memory is addressed with 32-bit shared-window addresses and explicit ld/st.shared: a generic pointer costs a
+// window lookup (S2R) per access in this kernel's dependent chains.
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ fe lds_fe(uint32_t a) { return fe_from(lds128(a), lds128(a + 16)); }
+
+// The rare operations live in one out-of-line function so that the code a main warp walks every level (Mul, Sqr,
+// OP_DOT, Add/Sub, stores) stays small; the slow warps call nothing else.
+__device__ __noinline__ void lat_exec_rare(uint32_t op, const fe& A, const fe& Bv, const fe& C, uint32_t* st, fe* R) {
+  uint32_t s = 0;
+  *R = alu_exec(op, A, Bv, C, s);
+  *st |= s;
+}
+struct LatCtx {
+  const uint4* inputs; uint4* out;
+  uint32_t slots_s;        // shared-window address of the value file
+  uint32_t dbg;
+};
+// one instruction of the packet at shared address pk_s (a stage of the warp's packet ring)
+__device__ __forceinline__ void lat_exec(const LatCtx& cx, uint32_t pk_s, const uint4 ins, uint32_t* st) {
+  auto slot_load = [&](uint32_t r) { return lds_fe(cx.slots_s + 32u * r); };
+  auto const_load = [&](uint32_t rel) { return lds_fe(pk_s + 16u * rel); };
   auto operand = [&](uint32_t is_const, uint32_t idx) { return is_const ? const_load(idx) : slot_load(idx); };
-  uint32_t st = 0;
-  auto exec = [&](const uint4 ins) {
-    const uint32_t op = ins.x & 0xFFu, dst = ins.x >> 16;
-    fe R;
-    if (op == OP_NOP) return;
-    if (op == OP_OUT) { fe v = operand(ins.x & F_A_CONST, ins.y); p.out[2 * (size_t)ins.w] = fe_lo(v); p.out[2 * (size_t)ins.w + 1] = fe_hi(v); return; }
-    if (op == OP_INPUT) {
-      R = fe_reduce256(fe_from(__ldg(p.inputs + 2 * (size_t)ins.y), __ldg(p.inputs + 2 * (size_t)ins.y + 1)));
-    } else if (op == OP_MUL || op == OP_SQR) {
-      fe A = operand(ins.x & F_A_CONST, ins.y);
-      R = (op == OP_SQR) ? fe_sqr(A) : fe_mul(A, operand(ins.x & F_B_CONST, ins.z));
-    } else if (op == OP_ADD || op == OP_SUB) {
-      fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
-      R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);
-    } else {
-      fe A = operand(ins.x & F_A_CONST, ins.y), Bv = fe_zero(), C = fe_zero();
-      if (op_has_b(op)) Bv = operand(ins.x & F_B_CONST, ins.z);
-      if (op == OP_TERN) C = operand(ins.x & F_C_CONST, ins.w);
-      R = alu_exec(op, A, Bv, C, st);
+  const uint32_t op = ins.x & 0xFFu, dst = ins.x >> 16;
+  fe R;
+  if (op == OP_NOP) return;
+  if (op == OP_OUT) { fe v = operand(ins.x & F_A_CONST, ins.y); cx.out[2 * (size_t)ins.w] = fe_lo(v); cx.out[2 * (size_t)ins.w + 1] = fe_hi(v); return; }
+  if (op == OP_DOT) {
+    const uint32_t nt = ins.y & 0xFFu;
+    const uint32_t tail_s = pk_s + 16u * ins.z;
+    dot_acc P;
+    dot_init(P);
+#pragma unroll 1
+    for (uint32_t t = 0; t < nt; t++) {
+      const uint4 sl = lds128(tail_s + 16u * (t >> 1));
+      const uint32_t lo = (t & 1) ? sl.z : sl.x, ci = (t & 1) ? sl.w : sl.y;
+      const uint32_t kind = lo & 0xFu, reg = lo >> 16;
+      if (kind == T_MAC) {
+        const fe c = const_load(ci);
+        const fe x = slot_load(reg);
+        dot_mac(P, x.l, c.l);
+      } else if (kind == T_CONST) {
+        const fe c = const_load(ci);
+        dot_add256(P, c.l, 0);
+      } else {
+        dot_term(P, kind, slot_load(reg), fe_zero());
+      }
     }
-    if (dst != NO_DST) { slots[2 * dst] = fe_lo(R); slots[2 * dst + 1] = fe_hi(R); }
-    if (ins.x & F_OUT) { p.out[2 * (size_t)ins.w] = fe_lo(R); p.out[2 * (size_t)ins.w + 1] = fe_hi(R); }
-  };
-  const uint4 nop = make_uint4(OP_NOP, 0, 0, 0);
-  const uint32_t nl = p.n_levels;
-  uint32_t pos = 0;
-  // software pipeline over levels: the instruction of level L+2 is being fetched and the constants of level L+1
-  // are being pulled into L1 while level L executes, so a level starts with everything it needs already on the SM
-  uint32_t c0 = __ldg(p.level_count), c1 = nl > 1 ? __ldg(p.level_count + 1) : 0, c2 = nl > 2 ? __ldg(p.level_count + 2) : 0;
-  uint4 nxt = tid < c0 ? __ldg(p.code + tid) : nop;
-  uint4 nxt2 = tid < c1 ? __ldg(p.code + c0 + tid) : nop;
-  auto prefetch_consts = [&](const uint4& in) {
-    const uint32_t o = in.x & 0xFFu;
-    if (o == OP_NOP || o == OP_INPUT) return;
-    if (in.x & F_A_CONST) prefetch_l1(p.consts + 2 * (size_t)in.y);
-    if ((in.x & F_B_CONST) && op_has_b(o)) prefetch_l1(p.consts + 2 * (size_t)in.z);
-    if ((in.x & F_C_CONST) && o == OP_TERN) prefetch_l1(p.consts + 2 * (size_t)in.w);
-  };
-  prefetch_consts(nxt);
-  for (uint32_t L = 0; L < nl; L++) {
-    const uint4 ins = nxt;
-    const uint32_t c = c0, npos = pos + c;
-    nxt = nxt2;
-    prefetch_consts(nxt);                                                  // level L+1: a whole level of slack
-    nxt2 = tid < c2 ? __ldg(p.code + npos + c1 + tid) : nop;               // level L+2
-    const uint32_t c3 = (L + 3 < nl) ? __ldg(p.level_count + L + 3) : 0;
-    if (tid < c) exec(ins);
-    for (uint32_t i = tid + T; i < c; i += T) exec(__ldg(p.code + pos + i));   // wide levels
-    __syncthreads();
-    pos = npos; c0 = c1; c1 = c2; c2 = c3;
+    R = fe_mont_reduce(P, (int)((ins.y >> 8) & 0xFFu));
+  } else if (op == OP_INPUT) {
+    R = fe_reduce256(fe_from(__ldg(cx.inputs + 2 * (size_t)ins.y), __ldg(cx.inputs + 2 * (size_t)ins.y + 1)));
+  } else if (op == OP_MUL || op == OP_SQR) {
+    const fe A = operand(ins.x & F_A_CONST, ins.y);
+    R = (op == OP_SQR) ? fe_sqr(A) : fe_mul(A, operand(ins.x & F_B_CONST, ins.z));
+  } else if (op == OP_ADD || op == OP_SUB) {
+    const fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
+    R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);
+  } else if (op == OP_SHRAND) {
+    R = fe_shr_and(slot_load(ins.y), ins.z & 0xFFu, const_load(ins.z >> 8));
+  } else {
+    fe A = operand(ins.x & F_A_CONST, ins.y), Bv = fe_zero(), C = fe_zero();
+    if (op_has_b(op)) Bv = operand(ins.x & F_B_CONST, ins.z);
+    if (op == OP_TERN) C = operand(ins.x & F_C_CONST, ins.w);
+    fe Rr;                      // its address is taken: keep R itself in registers on the common paths
+    lat_exec_rare(op, A, Bv, C, st, &Rr);
+    R = Rr;
+  }
+  if (dst != NO_DST) { sts128(cx.slots_s + 32u * dst, fe_lo(R)); sts128(cx.slots_s + 32u * dst + 16u, fe_hi(R)); }
+  if ((ins.x & F_OUT) && op != OP_TERN && !(cx.dbg & 1u)) { cx.out[2 * (size_t)ins.w] = fe_lo(R); cx.out[2 * (size_t)ins.w + 1] = fe_hi(R); }
+}
+// one instruction of a slow-warp job: its packet stays in global memory, only the rare operations occur
+__device__ __forceinline__ void lat_exec_slow(const LatCtx& cx, const uint4* pk, const uint4 ins, uint32_t* st) {
+  const uint32_t op = ins.x & 0xFFu, dst = ins.x >> 16;
+  if (op == OP_NOP) return;
+  auto operand = [&](uint32_t is_const, uint32_t idx) { return is_const ? fe_from(__ldg(pk + idx), __ldg(pk + idx + 1)) : lds_fe(cx.slots_s + 32u * idx); };
+  fe A = operand(ins.x & F_A_CONST, ins.y), Bv = fe_zero(), C = fe_zero(), R;
+  if (op_has_b(op)) Bv = operand(ins.x & F_B_CONST, ins.z);
+  if (op == OP_TERN) C = operand(ins.x & F_C_CONST, ins.w);
+  lat_exec_rare(op, A, Bv, C, st, &R);
+  if (dst != NO_DST) { sts128(cx.slots_s + 32u * dst, fe_lo(R)); sts128(cx.slots_s + 32u * dst + 16u, fe_hi(R)); }
+  if ((ins.x & F_OUT) && op != OP_TERN) { cx.out[2 * (size_t)ins.w] = fe_lo(R); cx.out[2 * (size_t)ins.w + 1] = fe_hi(R); }
+}
+
+// Dynamic shared memory: [2 uint4 control words][n_slots][2] value file | [n_warps][3][LAT_RING_SLOTS] packet rings
+__global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LParams p) {
+  extern __shared__ uint4 lat_smem[];
+  volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(lat_smem);   // [0] = completed levels, [1 + w] = jobs done by slow warp w
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid < 8) ctrl[tid] = 0;
+  __syncthreads();
+  uint32_t st = 0;
+  const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(lat_smem);
+  LatCtx cx;
+  cx.inputs = p.inputs; cx.out = p.out; cx.slots_s = smem_s + 32u; cx.dbg = p.dbg;
+
+  if (warp < p.n_warps) {
+    const uint32_t nl = p.n_levels;
+    const uint32_t bar_threads = (p.n_warps + 1u) * 32u;        // the control warp joins every level barrier
+    const uint32_t ring_s = cx.slots_s + 32u * p.n_slots + warp * (3u * LAT_RING_SLOTS * 16u);
+    // a packet {offset, slots, headers, lanes} -> ring stage: asynchronous 16-byte copies, lane-strided
+    auto fetch = [&](const uint4 info, uint32_t stage) {
+      uint32_t d = ring_s + (stage * LAT_RING_SLOTS + lane) * 16u;
+      const uint4* g = p.code + info.x + lane;
+      for (uint32_t k = lane; k < info.y; k += 32, d += 512u, g += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint4 cur = __ldg(p.first + 2 * warp), nxt = __ldg(p.first + 2 * warp + 1);
+    fetch(cur, 0);
+    fetch(nxt, 1);
+    uint32_t stage = 0;
+    for (uint32_t L = 0; L < nl; L++) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");        // this level's packet has landed (the next one may be in flight)
+      __syncwarp();
+      const uint32_t pk_s = ring_s + stage * (LAT_RING_SLOTS * 16u);
+      const uint4 desc = lds128(pk_s);                             // names the packet two levels ahead
+      fetch(desc, stage == 0 ? 2u : stage - 1u);                   // stage + 2 mod 3
+      // header k belongs to lane k mod cur.w; a lane runs its headers in order (a chain: program order, no barrier)
+      if (!(p.dbg & 16u) && lane < cur.w) for (uint32_t i = lane; i < cur.z; i += cur.w) lat_exec(cx, pk_s, lds128(pk_s + 16u * (1u + i)), &st);
+      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      cur = nxt; nxt = desc;
+      stage = stage == 2 ? 0u : stage + 1u;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == p.n_warps) {
+    // control warp: before the barrier that ends level L it waits for the slow-warp jobs whose readers start at level
+    // L + 1; after the barrier it publishes that L + 1 levels are complete (slow-warp jobs issued at <= L + 1 may start)
+    const uint32_t nl = p.n_levels, bar_threads = (p.n_warps + 1u) * 32u;
+    uint32_t wi = 0;
+    uint4 nw = p.n_waits ? __ldg(p.waits) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+    for (uint32_t L = 0; L < nl; L++) {
+      while (nw.x == L) {
+        while (ctrl[1 + nw.y] < nw.z) __nanosleep(40);
+        wi++;
+        nw = wi < p.n_waits ? __ldg(p.waits + wi) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+      }
+      __threadfence_block();
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      __threadfence_block();
+      if (lane == 0) { ctrl[0] = L + 1; if (p.level_clock) p.level_clock[L] = clock64(); }
+    }
+  } else if (warp - p.n_warps - 1u < p.n_slow) {
+    const uint32_t ws = warp - p.n_warps - 1u;
+    const uint32_t nj = __ldg(p.n_jobs + ws);
+    const uint4* jq = p.jobs + (size_t)ws * p.max_jobs;
+    for (uint32_t j = 0; j < nj; j++) {
+      const uint4 job = __ldg(jq + j);                             // {issue level, packet offset, headers, 0}
+      const uint4* pk = p.code + job.y;
+      const uint4 ins = lane < job.z ? __ldg(pk + 1 + lane) : make_uint4(OP_NOP, 0, 0, 0);
+      while (ctrl[0] < job.x) __nanosleep(100);
+      __threadfence_block();
+      lat_exec_slow(cx, pk, ins, &st);
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ctrl[1 + ws] = j + 1;
+    }
   }
   if (p.status != nullptr && st) atomicOr(p.status, st);
 }
@@ -386,7 +503,8 @@ struct Engine::Dev {
   uint32_t* d_status[2] = {nullptr, nullptr};
   size_t chunk = 0;
   // single-witness latency mode
-  uint4* lat_code = nullptr; uint32_t* lat_levels = nullptr; uint4* lat_consts = nullptr;
+  uint4* lat_code = nullptr; uint4* lat_first = nullptr; uint4* lat_jobs = nullptr; uint32_t* lat_njobs = nullptr; uint4* lat_waits = nullptr;
+  unsigned long long* lat_clock = nullptr;
   uint4* lat_in = nullptr; uint4* lat_out = nullptr; uint32_t* lat_status = nullptr;
   std::mutex mu;
 };
@@ -428,7 +546,7 @@ Engine::~Engine() {
     Dev* d = kv.second;
     cudaSetDevice(d->device);
     cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
-    cudaFree(d->lat_code); cudaFree(d->lat_levels); cudaFree(d->lat_consts); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
+    cudaFree(d->lat_code); cudaFree(d->lat_first); cudaFree(d->lat_jobs); cudaFree(d->lat_njobs); cudaFree(d->lat_waits); cudaFree(d->lat_clock); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
     for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
     delete d;
   }
@@ -454,6 +572,7 @@ Engine::Dev* Engine::dev(int device) {
   if (t_max < 32) throw Error("register file does not fit shared memory: lower GW_REGS");
   d->max_threads = t_max;
   CUDA_CHECK(cudaFuncSetAttribute(eval_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+  CUDA_CHECK(cudaFuncSetAttribute(eval_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));   // per device, not per graph
   CUDA_CHECK(cudaMalloc(&d->code, plan.code.size() * sizeof(Instr)));
   CUDA_CHECK(cudaMemcpy(d->code, plan.code.data(), plan.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMalloc(&d->consts, plan.consts.size() * 32));
@@ -563,8 +682,6 @@ void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_
   for (auto& e : errs) if (!e.empty()) throw Error(e);
 }
 
-static const int LAT_THREADS = 128;
-
 // one witness, host buffers: inputs I x 32 B, witness W x 32 B; returns the kernel time in ms if asked
 void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms) {
   Dev* d = dev(device);
@@ -574,39 +691,70 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     std::lock_guard<std::mutex> lk2(mu);
     if (!lat_ready) {
       cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-      lat_plan = compile_latency_plan(graph, (uint32_t)(prop.sharedMemPerBlockOptin / 32));
+      LatencyOptions lo;
+      lo.n_warps = (uint32_t)env_int("GW_LAT_WARPS", (int)lo.n_warps);
+      lo.packet_slots = LAT_RING_SLOTS;
+      lo.max_slots = (uint32_t)std::min<size_t>((prop.sharedMemPerBlockOptin / 16 - 2 - (size_t)lo.n_warps * 3 * LAT_RING_SLOTS) / 2, 0xFFFF);
+      lo.n_slow_warps = (uint32_t)env_int("GW_LAT_SLOW_WARPS", (int)lo.n_slow_warps);
+      lo.slow_levels = (uint32_t)env_int("GW_LAT_D", 0);
+      lo.split_dot = env_int("GW_LAT_SPLIT", 1) != 0;
+      lo.fuse = env_int("GW_LAT_FUSE", 1) != 0;
+      lo.chain = env_int("GW_LAT_CHAIN", 1) != 0;
+      if ((lo.n_warps + 1 + lo.n_slow_warps) * 32 > (uint32_t)LAT_MAX_THREADS) throw Error("GW_LAT_WARPS + GW_LAT_SLOW_WARPS must not exceed 11");
+      lat_plan = compile_latency_plan(graph, lo);
       lat_ready = true;
     }
   }
   const LatencyPlan& lp = lat_plan;
   const size_t in_b = (size_t)lp.n_inputs * 32, out_b = std::max<size_t>((size_t)lp.n_witness * 32, 32);
+  const size_t smem = ((size_t)lp.n_slots * 2 + 2 + (size_t)lp.n_warps * 3 * LAT_RING_SLOTS) * 16;
+  const bool clocks = env_int("GW_LAT_CLOCKS", 0) != 0;
   if (!d->lat_code) {
     CUDA_CHECK(cudaMalloc(&d->lat_code, std::max<size_t>(lp.code.size(), 1) * sizeof(Instr)));
     CUDA_CHECK(cudaMemcpy(d->lat_code, lp.code.data(), lp.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMalloc(&d->lat_levels, std::max<size_t>(lp.level_count.size(), 1) * 4));
-    CUDA_CHECK(cudaMemcpy(d->lat_levels, lp.level_count.data(), lp.level_count.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMalloc(&d->lat_consts, lp.consts.size() * 32));
-    CUDA_CHECK(cudaMemcpy(d->lat_consts, lp.consts.data(), lp.consts.size() * 32, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMalloc(&d->lat_in, in_b));
+    CUDA_CHECK(cudaMalloc(&d->lat_first, std::max<size_t>(lp.first.size(), 4) * 4));
+    CUDA_CHECK(cudaMemcpy(d->lat_first, lp.first.data(), lp.first.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->lat_jobs, std::max<size_t>(lp.jobs.size(), 4) * 4));
+    CUDA_CHECK(cudaMemcpy(d->lat_jobs, lp.jobs.data(), lp.jobs.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->lat_njobs, std::max<size_t>(lp.n_jobs.size(), 1) * 4));
+    CUDA_CHECK(cudaMemcpy(d->lat_njobs, lp.n_jobs.data(), lp.n_jobs.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->lat_waits, std::max<size_t>(lp.waits.size(), 4) * 4));
+    CUDA_CHECK(cudaMemcpy(d->lat_waits, lp.waits.data(), lp.waits.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->lat_in, std::max<size_t>(in_b, 32)));
     CUDA_CHECK(cudaMalloc(&d->lat_out, out_b));
     CUDA_CHECK(cudaMalloc(&d->lat_status, 4));
-    CUDA_CHECK(cudaFuncSetAttribute(eval_latency_kernel<LAT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)lp.n_slots * 32)));
+    if (clocks) CUDA_CHECK(cudaMalloc(&d->lat_clock, ((size_t)lp.n_levels + 1) * 8));
   }
-  if (lp.level_count.empty()) return;
+  if (lp.n_levels == 0) return;
   LParams p;
-  p.code = d->lat_code; p.level_count = d->lat_levels; p.n_levels = (uint32_t)lp.level_count.size();
-  p.consts = d->lat_consts; p.inputs = d->lat_in; p.out = d->lat_out; p.status = status ? d->lat_status : nullptr;
+  p.code = d->lat_code; p.first = d->lat_first; p.n_levels = lp.n_levels; p.n_warps = lp.n_warps; p.n_slots = lp.n_slots;
+  p.jobs = d->lat_jobs; p.n_jobs = d->lat_njobs; p.max_jobs = lp.max_jobs; p.n_slow = lp.n_slow_warps;
+  p.waits = d->lat_waits; p.n_waits = (uint32_t)(lp.waits.size() / 4);
+  p.inputs = d->lat_in; p.out = d->lat_out; p.status = status ? d->lat_status : nullptr;
+  p.level_clock = d->lat_clock;
+  p.dbg = (uint32_t)env_int("GW_LAT_DBG", 0);
   CUDA_CHECK(cudaMemcpyAsync(d->lat_in, inputs, in_b, cudaMemcpyHostToDevice, 0));
   if (status) CUDA_CHECK(cudaMemsetAsync(d->lat_status, 0, 4, 0));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (kernel_ms) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventRecord(e0, 0)); }
-  eval_latency_kernel<LAT_THREADS><<<1, LAT_THREADS, (size_t)lp.n_slots * 32, 0>>>(p);
+  eval_latency_kernel<<<1, (lp.n_warps + 1 + lp.n_slow_warps) * 32, smem, 0>>>(p);
   CUDA_CHECK(cudaGetLastError());
   if (kernel_ms) CUDA_CHECK(cudaEventRecord(e1, 0));
   CUDA_CHECK(cudaMemcpyAsync(witness, d->lat_out, (size_t)lp.n_witness * 32, cudaMemcpyDeviceToHost, 0));
   if (status) CUDA_CHECK(cudaMemcpyAsync(status, d->lat_status, 4, cudaMemcpyDeviceToHost, 0));
   CUDA_CHECK(cudaStreamSynchronize(0));
   if (kernel_ms) { CUDA_CHECK(cudaEventElapsedTime(kernel_ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  if (clocks && d->lat_clock) {
+    // GW_LAT_CLOCKS=1: cycles per level to stderr-readable file gw_lat_clocks.txt (tools/gpu_latency.py reads it)
+    std::vector<unsigned long long> c((size_t)lp.n_levels);
+    CUDA_CHECK(cudaMemcpy(c.data(), d->lat_clock, c.size() * 8, cudaMemcpyDeviceToHost));
+    const char* path = getenv("GW_LAT_CLOCKS_FILE");
+    FILE* f = fopen(path && *path ? path : "gw_lat_clocks.txt", "w");
+    if (f) {            // cycles per level
+      for (size_t k = 1; k < lp.n_levels; k++) fprintf(f, "%llu\n", c[k] - c[k - 1]);
+      fclose(f);
+    }
+  }
 }
 
 int cuda_device_count() {

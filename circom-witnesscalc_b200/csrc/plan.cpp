@@ -1,8 +1,11 @@
 #include "plan.hpp"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <map>
 #include <set>
 
@@ -348,31 +351,36 @@ struct Allocator {
   }
 };
 
-}  // namespace
+// what build_macro_program hands to the two back ends
+struct MacroProgram {
+  Graph g;                               // the rewritten graph the macro ops refer to (node ids = value ids)
+  std::vector<uint8_t> needed, is_const;
+  std::vector<U256> const_val;           // canonical value of constant nodes
+  Typing ty;
+  std::vector<uint32_t> out_start, out_list;   // witness positions per node (CSR)
+  std::vector<MOp> mops;
+};
 
-Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
-  if (opt.n_regs < 4 || opt.n_regs > 4096) throw Error("plan: n_regs out of range");
-  Plan plan;
-  plan.n_regs = opt.n_regs;
-  plan.n_inputs = g0.inputs_size;
-  plan.n_witness = (uint32_t)g0.witness_signals.size();
-  plan.stats.graph_nodes = g0.nodes.size();
-  plan.stats.graph_ops = g0.n_ops();
+// Front half of both plan compilers (throughput and latency mode): graph rewrites, typing, constants, witness
+// positions and the macro-op list (linear-combination fusion, Shr+Band fusion).
+void build_macro_program(const Graph& g0, const PlanOptions& opt, PlanStats& stats, MacroProgram& mp) {
+  stats.graph_nodes = g0.nodes.size();
+  stats.graph_ops = g0.n_ops();
   {
     std::vector<uint8_t> nd0 = liveness(g0);
     for (size_t i = 0; i < g0.nodes.size(); i++) {
       if (!nd0[i]) continue;
-      plan.stats.live_ops += g0.nodes[i].kind >= N_UNO;
-      plan.stats.div_nodes += g0.nodes[i].kind == N_DUO && g0.nodes[i].op == OP_DIV;
-      plan.stats.mul_nodes += g0.nodes[i].kind == N_DUO && g0.nodes[i].op == OP_MUL;
+      stats.live_ops += g0.nodes[i].kind >= N_UNO;
+      stats.div_nodes += g0.nodes[i].kind == N_DUO && g0.nodes[i].op == OP_DIV;
+      stats.mul_nodes += g0.nodes[i].kind == N_DUO && g0.nodes[i].op == OP_MUL;
     }
   }
   Graph rewritten;
-  const bool batch = opt.div_batch > 1 && plan.stats.div_nodes >= 2;
+  const bool batch = opt.div_batch > 1 && stats.div_nodes >= 2;
   if (batch) rewritten = rewrite_div_batches(g0, opt.div_batch);
   const Graph& g1 = batch ? rewritten : g0;
   // narrow typing; narrow values read by wide nodes get an explicit OP_WIDEN node
-  Typing ty;
+  Typing& ty = mp.ty;
   Graph widened;
   bool any_narrow = false;
   {
@@ -381,19 +389,16 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
     for (uint8_t x : t1.narrow) any_narrow |= x != 0;
     if (any_narrow) widened = rewrite_widen(g1, nd1, t1, &ty); else ty = std::move(t1);
   }
-  const Graph& g = any_narrow ? widened : g1;
+  if (any_narrow) mp.g = std::move(widened); else if (batch) mp.g = std::move(rewritten); else mp.g = g0;
+  const Graph& g = mp.g;
   const size_t N = g.nodes.size();
-  const std::vector<uint8_t> needed = liveness(g);
-  auto nconst_of = [&](const U256& c, bool neg) {       // int64 table form of a small signed constant
-    int64_t v = 0;
-    if (!signed_small(c, &v)) throw Error("plan: narrow instruction with a wide constant");
-    return narrow_const(neg ? -v : v);
-  };
+  mp.needed = liveness(g);
+  const std::vector<uint8_t>& needed = mp.needed;
 
   // constants: N_CONST nodes, and Input(0) which get_inputs_buffer forces to 1 (lib.rs:177-181).  const_val is the
   // canonical value; table entries are interned on first use (raw for ordinary operands, pre-scaled for OP_DOT).
-  std::vector<uint8_t> is_const(N, 0);
-  std::vector<U256> const_val(N);
+  std::vector<uint8_t>& is_const = mp.is_const; is_const.assign(N, 0);
+  std::vector<U256>& const_val = mp.const_val; const_val.assign(N, U256());
   for (size_t i = 0; i < N; i++) {
     if (!needed[i]) continue;
     const Node& nd = g.nodes[i];
@@ -401,15 +406,10 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
     else if (nd.kind == N_INPUT && nd.a == 0) { is_const[i] = 1; const_val[i] = u256_from_u64(1); }
     else if (nd.kind == N_INPUT && nd.a >= g.inputs_size) throw Error("plan: input index out of range");
   }
-  std::map<U256, uint32_t> cix;
-  auto intern = [&](const U256& v) {
-    auto it = cix.find(v);
-    if (it == cix.end()) { it = cix.emplace(v, (uint32_t)plan.consts.size()).first; plan.consts.push_back(v); }
-    return it->second;
-  };
 
   // witness positions per node (CSR), use counts and the single consumer of single-use values
-  std::vector<uint32_t> out_start(N + 1, 0), out_list(g.witness_signals.size());
+  std::vector<uint32_t>& out_start = mp.out_start; out_start.assign(N + 1, 0);
+  std::vector<uint32_t>& out_list = mp.out_list; out_list.assign(g.witness_signals.size(), 0);
   for (uint32_t s : g.witness_signals) out_start[s + 1]++;
   for (size_t i = 0; i < N; i++) out_start[i + 1] += out_start[i];
   {
@@ -428,8 +428,8 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
   // ---- macro-op list: linear-combination fusion ---------------------------------------------------------
   const uint32_t max_terms = std::max(1u, std::min(std::min(opt.max_terms, DOT_MAX_TERMS), opt.n_regs - 3));
   const double max_bound = 5.25;                       // 2^256 / M = 5.29: the reduced sum must fit 256 bits
-  std::vector<MOp> mops; mops.reserve(N);
-  std::vector<uint8_t> deferred(N, 0), absorbed(N, 0);
+  std::vector<MOp>& mops = mp.mops; mops.clear(); mops.reserve(N);
+  std::vector<uint8_t> deferred(N, 0), absorbed(N, 0), addc(N, 0);
   std::map<uint32_t, std::vector<PTerm>> dterms;       // term lists of deferred nodes
   // Shr(x, k) with a constant 0 <= k < 254 whose only consumer is Band(., constant): one OP_SHRAND (Num2Bits, BinSum)
   auto small_const = [&](uint32_t o, uint32_t* v) {
@@ -471,7 +471,17 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       std::vector<PTerm> terms;
       if (mul_rc) {
         const uint32_t x = is_const[nd.a] ? nd.b : nd.a, c = is_const[nd.a] ? nd.a : nd.b;
-        terms.push_back(PTerm{0, false, x, const_val[c]});
+        if (addc[x] && !ty.narrow[i]) {
+          // S * (y +- C) = S*y +- S*C: the product does not wait for the Add (Poseidon: lc += S * (sigma.out + C))
+          const Node& xn = g.nodes[x];
+          const bool c_first = is_const[xn.a] != 0;
+          const uint32_t y = c_first ? xn.b : xn.a, cc = c_first ? xn.a : xn.b;
+          const bool sub = xn.op == OP_SUB;
+          terms.push_back(PTerm{0, sub && c_first, y, const_val[c]});
+          terms.push_back(PTerm{2, sub && !c_first, 0, to_u256(fe_mul(to_fe(const_val[c]), to_fe(const_val[cc])))});
+        } else {
+          terms.push_back(PTerm{0, false, x, const_val[c]});
+        }
       } else {
         for (int pass = 0; pass < 3; pass++) {
           terms.clear();
@@ -503,7 +513,14 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
         else emit_dot(i, terms);
         continue;
       }
-      // a plain Add/Sub of two values: regular op below
+      // a plain Add/Sub of two values: regular op below.  value +- constant read by Mul(constant, .): see mul_rc
+      if (opt.fold_addc && !ty.narrow[i] && (is_const[nd.a] != is_const[nd.b])) {
+        addc[i] = 1;
+        const Node& cn = g.nodes[consumer[i]];
+        const bool only_mulc = uses[i] == 1 && n_out(i) == 0 && needed[consumer[i]] && !ty.narrow[consumer[i]] && cn.kind == N_DUO &&
+                               cn.op == OP_MUL && cn.a != cn.b && is_const[cn.a == i ? cn.b : cn.a];
+        if (only_mulc) continue;                       // its only reader folds it: never materialised
+      }
     }
     if (opt.fuse_dot && shr_absorbable(i)) { absorbed[i] = 1; continue; }
     if (nd.kind == N_DUO && nd.op == OP_BAND && (absorbed[nd.a] || absorbed[nd.b])) {
@@ -524,6 +541,41 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
     mops.push_back(m);
   }
   if (!dterms.empty()) throw Error("plan: dangling deferred linear combination");
+
+}
+
+}  // namespace
+
+Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
+  if (opt.n_regs < 4 || opt.n_regs > 4096) throw Error("plan: n_regs out of range");
+  Plan plan;
+  plan.n_regs = opt.n_regs;
+  plan.n_inputs = g0.inputs_size;
+  plan.n_witness = (uint32_t)g0.witness_signals.size();
+  MacroProgram mp;
+  build_macro_program(g0, opt, plan.stats, mp);
+  const Graph& g = mp.g;
+  const size_t N = g.nodes.size();
+  const std::vector<uint8_t>& needed = mp.needed;
+  const std::vector<uint8_t>& is_const = mp.is_const;
+  const std::vector<U256>& const_val = mp.const_val;
+  const Typing& ty = mp.ty;
+  const std::vector<uint32_t>& out_start = mp.out_start;
+  const std::vector<uint32_t>& out_list = mp.out_list;
+  const std::vector<MOp>& mops = mp.mops;
+  auto n_out = [&](uint32_t i) { return out_start[i + 1] - out_start[i]; };
+  auto nconst_of = [&](const U256& c, bool neg) {       // int64 table form of a small signed constant
+    int64_t v = 0;
+    if (!signed_small(c, &v)) throw Error("plan: narrow instruction with a wide constant");
+    return narrow_const(neg ? -v : v);
+  };
+  // table entries are interned on first use (raw for ordinary operands, pre-scaled for OP_DOT)
+  std::map<U256, uint32_t> cix;
+  auto intern = [&](const U256& v) {
+    auto it = cix.find(v);
+    if (it == cix.end()) { it = cix.emplace(v, (uint32_t)plan.consts.size()).first; plan.consts.push_back(v); }
+    return it->second;
+  };
 
   // value operands (non-constant nodes) of a macro op, without duplicates
   auto value_operands = [&](const MOp& m, std::vector<uint32_t>& v) {
@@ -689,133 +741,464 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
 
 namespace gw {
 
-LatencyPlan compile_latency_plan(const Graph& g, uint32_t max_slots) {
+namespace {
+
+// one instruction of the latency plan before slots are assigned
+struct LOp {
+  uint32_t opc = OP_NOP;
+  uint32_t val = 0xFFFFFFFFu;          // value it defines: a graph node, or N + k for the early part of a split OP_DOT
+  uint32_t in[3] = {0, 0, 0}; int n_in = 0;   // operands of a regular op (graph nodes, constants included); OP_OUT: in[0]
+  std::vector<PTerm> terms; uint32_t ncs = 1; // OP_DOT
+  uint32_t shift = 0; U256 mask;       // OP_SHRAND
+  uint32_t input = 0;                  // OP_INPUT
+  uint32_t level = 0;
+  bool has_out = false; uint32_t out_pos = 0;  // inline witness store (F_OUT), or the position of an OP_OUT
+  bool slow = false;
+  int32_t chain_prev = -1, chain_next = -1;    // a chain runs in ONE lane, back to back, inside one level
+};
+
+inline bool lat_is_slow(uint32_t opc) { return opc == OP_DIV || opc == OP_INV || opc == OP_POW || opc == OP_IDIV || opc == OP_MOD; }
+
+// cycles of one instruction in one lane of the latency kernel, measured in place on a B200 (profiles/r01n/latency.md):
+// the arithmetic (tools/ubench/oplat.cu: Mul 920, Sqr 780, one OP_DOT product 800, inversion 41 750) plus what every
+// instruction pays around it -- header and operand fetch from shared memory, dispatch, result and witness stores
+uint32_t lat_cost(const LOp& o) {
+  const uint32_t around = 450;
+  switch (o.opc) {
+    case OP_MUL: return 1100 + around;
+    case OP_SQR: return 950 + around;
+    case OP_DOT: {
+      uint32_t c = 1500;
+      for (const PTerm& t : o.terms) c += t.kind == 0 ? 800u : 100u;
+      return c;
+    }
+    case OP_ADD: case OP_SUB: return 80 + 300;
+    case OP_DIV: return 42700;
+    case OP_INV: return 41750;
+    case OP_POW: return 450000;
+    case OP_IDIV: case OP_MOD: return 40000;
+    default: return 60 + 300;
+  }
+}
+// instructions with the same key run the same code path: they can share the lanes of one warp
+uint64_t lat_class(const LOp& o) {
+  uint64_t k = o.opc;
+  if (o.opc == OP_DOT) {
+    uint32_t n[3] = {0, 0, 0};
+    for (const PTerm& t : o.terms) n[t.kind]++;
+    k |= (uint64_t)n[0] << 8 | (uint64_t)n[1] << 16 | (uint64_t)n[2] << 24;
+  }
+  return k;
+}
+
+const uint32_t LAT_LEVEL_OVERHEAD = 500;   // cycles per level around the instructions: packet fetch, descriptor, barrier
+
+}  // namespace
+
+LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
+  if (lo.n_warps < 1 || lo.n_warps > 16 || lo.n_slow_warps < 1 || lo.n_slow_warps > 6) throw Error("latency plan: warp counts out of range");
+  if (lo.max_slots > 0xFFFFu) throw Error("latency plan: value file too large for 16-bit slot numbers");
+  PlanOptions po;
+  po.n_regs = 64; po.div_batch = 1; po.narrow = false; po.fuse_dot = lo.fuse; po.fold_addc = lo.fuse; po.max_terms = 8;
+  PlanStats pst;
+  MacroProgram mp;
+  build_macro_program(g0, po, pst, mp);
+  const Graph& g = mp.g;
   const size_t N = g.nodes.size();
-  LatencyPlan lp;
-  lp.n_inputs = g.inputs_size;
-  lp.n_witness = (uint32_t)g.witness_signals.size();
+  const std::vector<uint8_t>& is_const = mp.is_const;
+  auto n_out = [&](uint32_t i) { return mp.out_start[i + 1] - mp.out_start[i]; };
 
-  std::vector<uint8_t> needed(N, 0);
-  for (uint32_t s : g.witness_signals) needed[s] = 1;
-  for (size_t i = N; i-- > 0;) {
-    if (!needed[i]) continue;
-    const Node& nd = g.nodes[i];
-    if (nd.kind >= N_UNO) needed[nd.a] = 1;
-    if (nd.kind >= N_DUO) needed[nd.b] = 1;
-    if (nd.kind == N_TRES) needed[nd.c] = 1;
-  }
-  std::vector<int32_t> const_of(N, -1);
-  std::map<U256, uint32_t> cix;
-  auto intern = [&](const U256& v) {
-    auto it = cix.find(v);
-    if (it == cix.end()) { it = cix.emplace(v, (uint32_t)lp.consts.size()).first; lp.consts.push_back(v); }
-    return (int32_t)it->second;
-  };
-  for (size_t i = 0; i < N; i++) {
-    if (!needed[i]) continue;
-    const Node& nd = g.nodes[i];
-    if (nd.kind == N_CONST) const_of[i] = intern(g.constants.at(nd.a));
-    else if (nd.kind == N_INPUT && nd.a == 0) const_of[i] = intern(u256_from_u64(1));
-    else if (nd.kind == N_INPUT && nd.a >= g.inputs_size) throw Error("plan: input index out of range");
-  }
-  auto operands = [&](const Node& nd, uint32_t* ops) {
-    int n = 0;
-    if (nd.kind >= N_UNO) ops[n++] = nd.a;
-    if (nd.kind >= N_DUO) ops[n++] = nd.b;
-    if (nd.kind == N_TRES) ops[n++] = nd.c;
-    return n;
-  };
-  // dependency levels (inputs are level 0), last level at which every value is read
-  std::vector<uint32_t> level(N, 0), last_use(N, 0);
-  uint32_t n_levels = 1;
-  for (size_t i = 0; i < N; i++) {
-    if (!needed[i] || const_of[i] >= 0) continue;
-    const Node& nd = g.nodes[i];
-    uint32_t ops[3]; int n = operands(nd, ops);
-    uint32_t lv = 0;
-    for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) lv = std::max(lv, level[ops[k]] + 1);
-    if (nd.kind >= N_UNO && lv == 0) lv = 1;            // constant-only operands: still after the input level
-    level[i] = lv;
-    for (int k = 0; k < n; k++) if (const_of[ops[k]] < 0) last_use[ops[k]] = std::max(last_use[ops[k]], lv);
-    n_levels = std::max(n_levels, lv + 1);
-  }
-  // witness positions per node
-  std::vector<uint32_t> out_start(N + 1, 0), out_list(g.witness_signals.size());
-  for (uint32_t s : g.witness_signals) out_start[s + 1]++;
-  for (size_t i = 0; i < N; i++) out_start[i + 1] += out_start[i];
-  {
-    std::vector<uint32_t> fill(out_start.begin(), out_start.end() - 1);
-    for (uint32_t j = 0; j < g.witness_signals.size(); j++) out_list[fill[g.witness_signals[j]]++] = j;
-  }
-  // extra OUT instructions (second and later witness positions, TernCond results) run one level later
-  for (size_t i = 0; i < N; i++) {
-    if (!needed[i] || const_of[i] >= 0) continue;
-    uint32_t n_out = out_start[i + 1] - out_start[i];
-    bool inline_out = n_out >= 1 && g.nodes[i].kind != N_TRES;
-    if (n_out > (inline_out ? 1u : 0u)) { last_use[i] = std::max(last_use[i], level[i] + 1); n_levels = std::max(n_levels, level[i] + 2); }
-  }
-  // bucket nodes by level, inside a level by opcode (keeps warps uniform)
-  std::vector<std::vector<uint32_t>> by_level(n_levels);
-  for (size_t i = 0; i < N; i++) if (needed[i] && const_of[i] < 0) by_level[level[i]].push_back((uint32_t)i);
-  auto opkey = [&](uint32_t i) { const Node& nd = g.nodes[i]; return (uint32_t)nd.kind * 64u + nd.op; };
-  for (auto& v : by_level) std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return opkey(a) < opkey(b); });
-
-  std::vector<int32_t> slot_of(N, -1);
-  std::vector<uint32_t> free_slots;
-  std::vector<std::vector<uint32_t>> dying(n_levels + 1);       // values whose last read happens at this level
-  uint32_t n_slots = 0;
-  std::vector<Instr> pending_outs;                              // OUT instructions for the next level
-  for (uint32_t L = 0; L < n_levels; L++) {
-    uint32_t count = 0;
-    for (const Instr& in : pending_outs) { lp.code.push_back(in); count++; }
-    pending_outs.clear();
-    if (L == 0) {
-      for (size_t i = 0; i < N; i++) {
-        if (!needed[i] || const_of[i] < 0) continue;
-        for (uint32_t k = out_start[i]; k < out_start[i + 1]; k++) { lp.code.push_back(make_instr(OP_OUT, F_A_CONST, NO_DST, (uint32_t)const_of[i], 0, out_list[k])); count++; }
+  bool use_chain = lo.chain;
+  const int dbg_level = getenv("GW_LAT_DEBUG") ? atoi(getenv("GW_LAT_DEBUG")) : -1;
+  auto schedule = [&](const uint32_t D) {
+    LatencyPlan lp;
+    lp.n_inputs = g0.inputs_size;
+    lp.n_witness = (uint32_t)g0.witness_signals.size();
+    lp.n_warps = lo.n_warps; lp.n_slow_warps = lo.n_slow_warps; lp.slow_levels = D;
+    // ---- 1. instructions and their levels (ASAP; a long op delivers D levels after its issue) -------------
+    std::vector<LOp> ops; ops.reserve(mp.mops.size() + mp.mops.size() / 4);
+    std::vector<uint32_t> chain_len, chain_head;      // per op: the head of its chain; per head: the chain's length
+    std::vector<uint32_t> chain_slots;                // per head: packet slots of the chain (headers + tails + constants)
+    auto mop_slots = [&](const MOp& m) {
+      uint32_t n = 1;
+      if (m.opc == OP_DOT) { n += ((uint32_t)m.terms.size() + 1) / 2; for (const PTerm& t : m.terms) n += t.kind != 1 ? 2u : 0u; }
+      else if (m.opc == OP_SHRAND) n += 2;
+      else for (int k = 0; k < m.n_in; k++) n += is_const[m.in[k]] ? 2u : 0u;
+      return n;
+    };
+    std::vector<uint32_t> avail(N, 0);               // first level that may read the value
+    uint32_t n_levels = 1;
+    for (size_t i = 0; i < N; i++) {                 // constants that are witness signals themselves (witness[0] = 1)
+      if (!mp.needed[i] || !is_const[i]) continue;
+      for (uint32_t k = mp.out_start[i]; k < mp.out_start[i + 1]; k++) {
+        LOp o; o.opc = OP_OUT; o.n_in = 1; o.in[0] = (uint32_t)i; o.level = 0; o.has_out = true; o.out_pos = mp.out_list[k];
+        chain_len.push_back(1); chain_head.push_back((uint32_t)ops.size()); chain_slots.push_back(8);
+        ops.push_back(o);
       }
     }
-    for (uint32_t i : by_level[L]) {
-      const Node& nd = g.nodes[i];
-      uint32_t ops[3]; int n = operands(nd, ops);
-      uint32_t enc[3] = {0, 0, 0}, flags = 0;
-      for (int k = 0; k < n; k++) {
-        if (const_of[ops[k]] >= 0) { enc[k] = (uint32_t)const_of[ops[k]]; flags |= (F_A_CONST << k); }
-        else { if (slot_of[ops[k]] < 0) throw Error("latency plan: operand without a slot"); enc[k] = (uint32_t)slot_of[ops[k]]; }
+    // readers per value: macro ops that read it (+ the separate OP_OUT stores).  A value with ONE reader whose other
+    // operands are older is chained to it: the reader runs in the same lane right after its producer, inside the same
+    // level (program order replaces the barrier), e.g. the x^2, x^4, x^5 of a Poseidon S-box become one level.
+    std::vector<uint32_t> n_readers(N, 0);
+    {
+      std::vector<uint32_t> seen;
+      for (const MOp& m : mp.mops) {
+        seen.clear();
+        auto rd = [&](uint32_t v) { if (std::find(seen.begin(), seen.end(), v) == seen.end()) { seen.push_back(v); n_readers[v]++; } };
+        if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) rd(t.node); }
+        else for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]]) rd(m.in[k]);
+        const uint32_t no = n_out(m.node);
+        if (no > ((no >= 1 && m.opc != OP_TERN) ? 1u : 0u)) n_readers[m.node] += 2;      // separate stores read the slot later
       }
-      const uint32_t n_out = out_start[i + 1] - out_start[i];
-      const uint32_t* outs = &out_list[out_start[i]];
-      const bool inline_out = n_out >= 1 && nd.kind != N_TRES;
+    }
+    std::vector<int32_t> def_op(N, -1);
+    for (const MOp& m : mp.mops) {
+      LOp o; o.opc = m.opc; o.val = m.node; o.n_in = m.n_in; o.shift = m.shift; o.mask = m.mask; o.ncs = m.ncs;
+      for (int k = 0; k < m.n_in; k++) o.in[k] = m.in[k];
+      if (m.opc == OP_INPUT) o.input = g.nodes[m.node].a;
+      uint32_t lv = 0;
+      // chain candidate: the single newest operand, produced one level earlier by an ordinary instruction that nobody else reads
+      int32_t chain_to = -1;
+      // (only multiplication-class instructions: a chain of cheap ones would serialise what the lanes of a warp run in parallel)
+      if (use_chain && (m.opc == OP_MUL || m.opc == OP_SQR || m.opc == OP_DOT)) {
+        uint32_t newest = 0xFFFFFFFFu, amax = 0, n_at_max = 0;
+        auto look = [&](uint32_t v) { if (avail[v] > amax) { amax = avail[v]; newest = v; n_at_max = 1; } else if (avail[v] == amax && v != newest) n_at_max++; };
+        if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) look(t.node); }
+        else for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]]) look(m.in[k]);
+        if (amax > 0 && n_at_max == 1 && newest < N && def_op[newest] >= 0 && n_readers[newest] == 1) {
+          const LOp& pr = ops[(size_t)def_op[newest]];
+          bool ok = (pr.opc == OP_MUL || pr.opc == OP_SQR || pr.opc == OP_DOT) && pr.level + 1 == amax && chain_len[chain_head[(size_t)def_op[newest]]] < lo.max_chain &&
+                    1 + chain_slots[chain_head[(size_t)def_op[newest]]] + mop_slots(m) <= lo.packet_slots;     // a chain lives in one packet
+          auto older = [&](uint32_t v) { if (v != newest && avail[v] > pr.level) ok = false; };
+          if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) older(t.node); }
+          else for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]]) older(m.in[k]);
+          if (ok) chain_to = def_op[newest];
+        }
+      }
+      if (m.opc == OP_DOT) {
+        o.terms = m.terms;
+        uint32_t rmax = 0;
+        for (const PTerm& t : o.terms) if (t.kind != 2) rmax = std::max(rmax, avail[t.node]);
+        if (lo.split_dot && rmax > 0 && chain_to < 0) {
+          // operands known before rmax go to an early OP_DOT whose reduced sum enters the late one as a plain value
+          std::vector<PTerm> early, late;
+          bool early_mac = false;
+          for (const PTerm& t : o.terms) {
+            const bool e = t.kind == 2 || avail[t.node] < rmax;
+            (e ? early : late).push_back(t);
+            early_mac |= e && t.kind == 0;
+          }
+          if (early_mac && !late.empty()) {
+            const uint32_t ev = (uint32_t)avail.size();
+            late.push_back(PTerm{1, false, ev, U256()});
+            if (dot_bound(late) <= 5.25) {
+              LOp e; e.opc = OP_DOT; e.val = ev; e.terms = std::move(early);
+              const double b = dot_bound(e.terms); e.ncs = b <= 2.0 ? 1 : b <= 4.0 ? 2 : 3;
+              uint32_t el = 0;
+              for (const PTerm& t : e.terms) if (t.kind != 2) el = std::max(el, avail[t.node]);
+              e.level = el;
+              avail.push_back(el + 1);
+              chain_len.resize(ops.size() + 1, 1); chain_head.resize(ops.size() + 1, 0); chain_slots.resize(ops.size() + 1, 8); chain_head[ops.size()] = (uint32_t)ops.size();
+              ops.push_back(std::move(e));
+              o.terms = std::move(late);
+              const double bl = dot_bound(o.terms); o.ncs = bl <= 2.0 ? 1 : bl <= 4.0 ? 2 : 3;
+              lp.n_split++;
+            }
+          }
+        }
+        for (const PTerm& t : o.terms) if (t.kind != 2) lv = std::max(lv, avail[t.node]);
+      } else {
+        for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]]) lv = std::max(lv, avail[m.in[k]]);
+      }
+      if (chain_to >= 0) { lv = ops[(size_t)chain_to].level; o.chain_prev = chain_to; ops[(size_t)chain_to].chain_next = (int32_t)ops.size(); lp.n_chained++; }
+      o.level = lv;
+      o.slow = lat_is_slow(m.opc);
+      avail[m.node] = lv + (o.slow ? D : 1u);
+      def_op[m.node] = (int32_t)ops.size();
+      chain_len.resize(ops.size() + 1, 1); chain_head.resize(ops.size() + 1, 0); chain_slots.resize(ops.size() + 1, 8);
+      if (chain_to >= 0) { chain_head[ops.size()] = chain_head[(size_t)chain_to]; chain_len[chain_head[ops.size()]]++; chain_slots[chain_head[ops.size()]] += mop_slots(m); }
+      else { chain_head[ops.size()] = (uint32_t)ops.size(); chain_slots[ops.size()] = mop_slots(m); }
+      if (o.slow) { lp.n_slow++; n_levels = std::max(n_levels, lv + D); }
+      const uint32_t no = n_out(m.node);
+      const bool inline_out = no >= 1 && m.opc != OP_TERN;     // .w is operand c for TernCond
+      if (inline_out) { o.has_out = true; o.out_pos = mp.out_list[mp.out_start[m.node]]; }
+      n_levels = std::max(n_levels, lv + 1);
+      ops.push_back(std::move(o));
+      for (uint32_t k = inline_out ? 1u : 0u; k < no; k++) {
+        LOp w; w.opc = OP_OUT; w.n_in = 1; w.in[0] = m.node; w.level = avail[m.node]; w.has_out = true;
+        w.out_pos = mp.out_list[mp.out_start[m.node] + k];
+        n_levels = std::max(n_levels, w.level + 1);
+        chain_len.resize(ops.size() + 1, 1); chain_head.resize(ops.size() + 1, 0); chain_slots.resize(ops.size() + 1, 8); chain_head[ops.size()] = (uint32_t)ops.size();
+        ops.push_back(w);
+      }
+    }
+    const size_t NV = avail.size();
+
+    // ---- 2. last level that reads each value (a long op may read its operands until its OP_WAIT level) -----
+    std::vector<int64_t> last_use(NV, -1);
+    auto for_operands = [&](const LOp& o, auto&& fn) {
+      if (o.opc == OP_DOT) { for (const PTerm& t : o.terms) if (t.kind != 2) fn(t.node); }
+      else for (int k = 0; k < o.n_in; k++) if (o.in[k] >= N || !is_const[o.in[k]]) fn(o.in[k]);
+    };
+    for (const LOp& o : ops) {
+      const int64_t rd = o.slow ? (int64_t)o.level + D - 1 : (int64_t)o.level;
+      for_operands(o, [&](uint32_t v) { last_use[v] = std::max(last_use[v], rd); });
+    }
+    std::vector<std::vector<uint32_t>> by_level(n_levels);
+    for (size_t k = 0; k < ops.size(); k++) by_level[ops[k].level].push_back((uint32_t)k);
+
+    // ---- 3. level by level: slots, jobs of the slow warps, warp assignment, headers ------------------------
+    std::vector<int32_t> slot_of(NV, -1);
+    std::vector<uint32_t> free_slots;
+    std::vector<std::vector<uint32_t>> dying(n_levels);
+    uint32_t n_slots = 0;
+    // A packet is what one warp needs for one level (or one slow-warp job), contiguous: slot 0 = descriptor, then the
+    // headers, then what the headers point at with packet-relative slot offsets: OP_DOT tails and every constant
+    // (two slots each) -- so one asynchronous copy brings a level's instructions AND their constants on chip.
+    std::vector<std::vector<std::array<uint32_t, 2>>> pending_waits(n_levels);
+    std::vector<std::vector<std::array<uint32_t, 3>>> jobq(lo.n_slow_warps);
+    std::vector<uint64_t> busy(lo.n_slow_warps, 0);
+    std::vector<std::array<uint32_t, 4>> pinfo;      // per (physical level, warp): offset, slots, headers, lanes
+    uint32_t n_phys = 0;
+
+    auto header = [&](const LOp& o, std::vector<Instr>& pk) {
+      uint32_t flags = o.has_out && o.opc != OP_OUT ? (uint32_t)F_OUT : 0u;
       uint32_t dst = NO_DST;
-      if (last_use[i] > L) {
-        if (!free_slots.empty()) { dst = free_slots.back(); free_slots.pop_back(); }
-        else { dst = n_slots++; if (n_slots > max_slots) throw Error("latency plan: graph is too wide for the shared-memory value file"); }
-        slot_of[i] = (int32_t)dst;
-        dying[last_use[i]].push_back(i);
+      if (o.val != 0xFFFFFFFFu && slot_of[o.val] >= 0) dst = (uint32_t)slot_of[o.val];
+      auto slot = [&](uint32_t v) {
+        if (slot_of[v] < 0) throw Error("latency plan: operand without a slot");
+        return (uint32_t)slot_of[v];
+      };
+      auto inline_const = [&](const U256& v) {
+        const uint32_t off = (uint32_t)pk.size();
+        Instr lo4, hi4;
+        lo4.x = v.l[0]; lo4.y = v.l[1]; lo4.z = v.l[2]; lo4.w = v.l[3];
+        hi4.x = v.l[4]; hi4.y = v.l[5]; hi4.z = v.l[6]; hi4.w = v.l[7];
+        pk.push_back(lo4); pk.push_back(hi4);
+        return off;
+      };
+      if (o.opc == OP_INPUT) return make_instr(OP_INPUT, flags, dst, o.input, 0, o.out_pos);
+      if (o.opc == OP_OUT) {
+        if (o.in[0] < N && is_const[o.in[0]]) return make_instr(OP_OUT, F_A_CONST, NO_DST, inline_const(mp.const_val[o.in[0]]), 0, o.out_pos);
+        return make_instr(OP_OUT, 0, NO_DST, slot(o.in[0]), 0, o.out_pos);
       }
-      uint32_t op;
-      if (nd.kind == N_INPUT) { op = OP_INPUT; enc[0] = nd.a; }
-      else if (nd.kind == N_UNO) op = OP_NEG + nd.op;
-      else if (nd.kind == N_TRES) op = OP_TERN;
-      else op = (nd.op == OP_MUL && nd.a == nd.b && !(flags & F_A_CONST)) ? (uint32_t)OP_SQR : nd.op;
-      uint32_t w = nd.kind == N_TRES ? enc[2] : (inline_out ? outs[0] : 0);
-      if (inline_out) flags |= F_OUT;
-      lp.code.push_back(make_instr(op, flags, dst, enc[0], enc[1], w));
-      count++;
-      for (uint32_t k = inline_out ? 1u : 0u; k < n_out; k++) pending_outs.push_back(make_instr(OP_OUT, 0, NO_DST, dst, 0, outs[k]));
+      if (o.opc == OP_SHRAND) return make_instr(OP_SHRAND, flags, dst, slot(o.in[0]), o.shift | (inline_const(o.mask) << 8), o.out_pos);
+      if (o.opc == OP_DOT) {
+        // terms ordered by kind so that the lanes of a warp walk the same code path
+        std::vector<PTerm> ts = o.terms;
+        std::stable_sort(ts.begin(), ts.end(), [](const PTerm& a, const PTerm& b) {
+          auto key = [](const PTerm& t) { return t.kind == 0 ? 0 : t.kind == 1 ? (t.neg ? 2 : 1) : 3; };
+          return key(a) < key(b);
+        });
+        const uint32_t tail = (uint32_t)pk.size();
+        pk.resize(pk.size() + (ts.size() + 1) / 2, make_instr(OP_NOP, 0, 0, 0, 0, 0));
+        std::vector<uint32_t> words;
+        for (const PTerm& t : ts) {
+          const uint32_t kind = t.kind == 0 ? (uint32_t)T_MAC : t.kind == 2 ? (uint32_t)T_CONST : (t.neg ? (uint32_t)T_SUBHI : (uint32_t)T_ADDHI);
+          const uint32_t reg = t.kind == 2 ? 0u : slot(t.node);
+          const uint32_t ci = t.kind == 1 ? 0u : inline_const(prescale(t.c, t.neg));
+          words.push_back(kind | (reg << 16)); words.push_back(ci);
+        }
+        if (words.size() & 2) { words.push_back(0); words.push_back(0); }
+        for (size_t k = 0; k < words.size(); k += 4) { Instr& sl = pk[tail + k / 4]; sl.x = words[k]; sl.y = words[k + 1]; sl.z = words[k + 2]; sl.w = words[k + 3]; }
+        return make_instr(OP_DOT, flags, dst, (uint32_t)ts.size() | (o.ncs << 8), tail, o.out_pos);
+      }
+      uint32_t enc[3] = {0, 0, 0};
+      for (int k = 0; k < o.n_in; k++) {
+        if (o.in[k] < N && is_const[o.in[k]]) { enc[k] = inline_const(mp.const_val[o.in[k]]); flags |= (F_A_CONST << k); }
+        else enc[k] = slot(o.in[k]);
+      }
+      return make_instr(o.opc, flags, dst, enc[0], enc[1], o.opc == OP_TERN ? enc[2] : o.out_pos);
+    };
+    // header() emits offsets relative to the start of the instruction's own extras; a packet places them at `rb`
+    auto rebase_header = [&](Instr h, uint32_t rb) {
+      const uint32_t op = h.x & 0xFFu;
+      if (op == OP_DOT) { h.z += rb; return h; }
+      if (op == OP_SHRAND) { h.z = (h.z & 0xFFu) | (((h.z >> 8) + rb) << 8); return h; }
+      if (op == OP_INPUT) return h;
+      if (h.x & F_A_CONST) h.y += rb;
+      if ((h.x & F_B_CONST) && op_has_b_host(op)) h.z += rb;
+      if ((h.x & F_C_CONST) && op == OP_TERN) h.w += rb;
+      return h;
+    };
+    // appends a packet with the chains headed by list[from ..] to lp.code: at most 32 of them (one lane each), fewer
+    // if the packet would exceed `cap` slots (0 = no limit).  Header k belongs to lane k mod lanes, so a lane finds the
+    // instructions of its chain at k = lane, lane + lanes, ...; shorter chains are padded with OP_NOP.
+    // returns {offset, slots, headers, lanes}
+    auto emit_packet = [&](const std::vector<const LOp*>& list, size_t from, uint32_t cap) {
+      size_t n = std::min<size_t>(32, list.size() - from);
+      std::vector<Instr> pk;
+      for (;; n = (n + 1) / 2) {
+        size_t rows = n ? 1 : 0;
+        for (size_t k = 0; k < n; k++) { size_t len = 0; for (const LOp* o = list[from + k]; o; o = o->chain_next >= 0 ? &ops[(size_t)o->chain_next] : nullptr) len++; rows = std::max(rows, len); }
+        const uint32_t nh = (uint32_t)(rows * n);
+        std::vector<Instr> hs(nh, make_instr(OP_NOP, 0, 0, 0, 0, 0)), extra, tmp;
+        std::vector<uint32_t> ebase(nh, 0);
+        for (size_t k = 0; k < n; k++) {
+          size_t r = 0;
+          for (const LOp* o = list[from + k]; o; o = o->chain_next >= 0 ? &ops[(size_t)o->chain_next] : nullptr, r++) {
+            tmp.clear();
+            hs[r * n + k] = header(*o, tmp);
+            ebase[r * n + k] = (uint32_t)extra.size();
+            extra.insert(extra.end(), tmp.begin(), tmp.end());
+          }
+        }
+        pk.assign(1 + nh, make_instr(OP_NOP, 0, 0, 0, 0, 0));
+        for (uint32_t i = 0; i < nh; i++) {
+          const uint32_t rb = 1 + nh + ebase[i];       // where this header's extras start in the packet
+          pk[1 + i] = rebase_header(hs[i], rb);
+          if ((hs[i].x & 0xFFu) == OP_DOT) {            // the term slots of an OP_DOT tail carry constant offsets too
+            const uint32_t nt = hs[i].y & 0xFFu;
+            for (uint32_t t = 0; t < nt; t++) {
+              Instr& sl = extra[ebase[i] + hs[i].z + (t >> 1)];
+              uint32_t& lo_w = (t & 1) ? sl.z : sl.x; uint32_t& ci = (t & 1) ? sl.w : sl.y;
+              const uint32_t kind = lo_w & 0xFu;
+              if (kind == T_MAC || kind == T_CONST) ci += rb;
+            }
+          }
+        }
+        pk.insert(pk.end(), extra.begin(), extra.end());
+        if (!cap || pk.size() <= cap || n <= 1) {
+          if (cap && pk.size() > cap) throw Error("latency plan: one chain does not fit a packet");
+          const uint32_t off = (uint32_t)lp.code.size();
+          lp.code.insert(lp.code.end(), pk.begin(), pk.end());
+          for (uint32_t i = 0; i < nh; i++) lp.n_instrs += (hs[i].x & 0xFFu) != OP_NOP;
+          return std::array<uint32_t, 5>{off, (uint32_t)pk.size(), nh, (uint32_t)n, (uint32_t)n};
+        }
+      }
+    };
+
+    std::vector<uint32_t> mains, slows;
+    for (uint32_t L = 0; L < n_levels; L++) {
+      mains.clear(); slows.clear();
+      for (uint32_t k : by_level[L]) { if (ops[k].slow) slows.push_back(k); else if (ops[k].chain_prev < 0) mains.push_back(k); }
+      // destination slots of everything issued at this level
+      for (uint32_t k : by_level[L]) {
+        const LOp& o = ops[k];
+        if (o.val == 0xFFFFFFFFu || last_use[o.val] < 0) continue;
+        uint32_t s;
+        if (!free_slots.empty()) { s = free_slots.back(); free_slots.pop_back(); }
+        else { s = n_slots++; if (n_slots > lo.max_slots) throw Error("latency plan: graph is too wide for the shared-memory value file"); }
+        slot_of[o.val] = (int32_t)s;
+        dying[(size_t)last_use[o.val]].push_back(o.val);
+      }
+      // long ops: jobs of up to 32 lanes of one opcode, queued to the least busy slow warp
+      std::stable_sort(slows.begin(), slows.end(), [&](uint32_t a, uint32_t b) { return ops[a].opc < ops[b].opc; });
+      for (size_t a = 0; a < slows.size();) {
+        size_t b = a;
+        while (b < slows.size() && b - a < 32 && ops[slows[b]].opc == ops[slows[a]].opc) b++;
+        uint32_t w = 0;
+        for (uint32_t x = 1; x < lo.n_slow_warps; x++) if (busy[x] < busy[w]) w = x;
+        busy[w] = std::max<uint64_t>(busy[w], L) + D;
+        std::vector<const LOp*> jl;
+        for (size_t k = a; k < b; k++) jl.push_back(&ops[slows[k]]);
+        const auto jp = emit_packet(jl, 0, 0);
+        if (jp[3] != b - a) throw Error("latency plan: slow job packet");
+        jobq[w].push_back({n_phys, jp[0], (uint32_t)(b - a)});
+        const uint32_t wl = L + D - 1;
+        if (wl >= n_levels) throw Error("latency plan: wait level out of range");
+        pending_waits[wl].push_back({w, (uint32_t)jobq[w].size()});
+        a = b;
+      }
+      // bundles: <= 32 instructions of one class; longest bundle first onto the least loaded warp.  Two warps on the
+      // same SM sub-partition (warp index mod 4) share one multiplier pipe, which is counted as partial contention.
+      struct Item { uint64_t cls; uint32_t cost; const LOp* op; };
+      std::vector<Item> items;
+      for (uint32_t k : mains) {
+        uint64_t cls = 0; uint32_t cost = 0;
+        for (const LOp* o = &ops[k]; o; o = o->chain_next >= 0 ? &ops[(size_t)o->chain_next] : nullptr) { cls = cls * 0x9E3779B97F4A7C15ull + lat_class(*o) + 1; cost += lat_cost(*o); }
+        items.push_back({cls, cost, &ops[k]});
+      }
+      std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost != b.cost ? a.cost > b.cost : a.cls < b.cls; });
+      std::vector<std::vector<const LOp*>> per_warp(lo.n_warps);
+      std::vector<double> load(lo.n_warps, 0.0);
+      for (size_t a = 0; a < items.size();) {
+        size_t b = a;
+        while (b < items.size() && b - a < 32 && items[b].cls == items[a].cls) b++;
+        uint32_t best = 0; double best_t = 1e300;
+        for (uint32_t w = 0; w < lo.n_warps; w++) {
+          double t = load[w] + items[a].cost;
+          for (uint32_t x = w & 3u; x < lo.n_warps; x += 4) if (x != w) t += 0.4 * std::min<double>(load[x], items[a].cost);
+          if (t < best_t) { best_t = t; best = w; }
+        }
+        load[best] += items[a].cost;
+        for (size_t k = a; k < b; k++) per_warp[best].push_back(items[k].op);
+        a = b;
+      }
+      double worst = 0;
+      uint32_t width = 0;
+      for (uint32_t w = 0; w < lo.n_warps; w++) { worst = std::max(worst, load[w]); width += (uint32_t)per_warp[w].size(); }
+      // physical levels: every packet must fit one stage of the kernel's shared-memory ring, so a wide level is cut
+      // into several consecutive ones (all its operands are older, all its destinations are fresh: no hazard)
+      {
+        std::vector<size_t> done(lo.n_warps, 0);
+        bool more = true;
+        while (more) {
+          more = false;
+          for (uint32_t w = 0; w < lo.n_warps; w++) {
+            const auto pp = emit_packet(per_warp[w], done[w], lo.packet_slots);
+            done[w] += pp[4];
+            pinfo.push_back({pp[0], pp[1], pp[2], pp[3]});
+            more |= done[w] < per_warp[w].size();
+          }
+          n_phys++;
+        }
+      }
+      for (const auto& pw : pending_waits[L]) { lp.waits.push_back(n_phys - 1); lp.waits.push_back(pw[0]); lp.waits.push_back(pw[1]); lp.waits.push_back(0); }
+      lp.est_cycles += (uint64_t)worst + LAT_LEVEL_OVERHEAD;
+      if (dbg_level >= 0 && L >= (uint32_t)dbg_level && L < (uint32_t)dbg_level + 24) {      // GW_LAT_DEBUG=<level>: dump 24 levels of the schedule
+        fprintf(stderr, "L%u worst %.0f:", L, worst);
+        for (uint32_t w = 0; w < lo.n_warps; w++) { fprintf(stderr, " w%u[", w); for (const LOp* o : per_warp[w]) fprintf(stderr, "%llx ", (unsigned long long)lat_class(*o)); fprintf(stderr, "]"); }
+        fprintf(stderr, "\n");
+      }
+      lp.max_level_width = std::max(lp.max_level_width, width);
+      // slots read for the last time in this level become reusable from the next level on
+      for (uint32_t v : dying[L]) free_slots.push_back((uint32_t)slot_of[v]);
     }
-    // slots read for the last time in this level become reusable from the next level on
-    for (uint32_t v : dying[L]) { free_slots.push_back((uint32_t)slot_of[v]); }
-    lp.level_count.push_back(count);
-    lp.max_level_width = std::max(lp.max_level_width, count);
-  }
-  if (!pending_outs.empty()) {
-    for (const Instr& in : pending_outs) lp.code.push_back(in);
-    lp.level_count.push_back((uint32_t)pending_outs.size());
-  }
-  lp.n_slots = std::max(n_slots, 1u);
-  if (lp.consts.empty()) lp.consts.push_back(u256_from_u64(0));
-  return lp;
+
+    // ---- 4. descriptors: the packet of (L, w) names the packet of (L + 2, w); the first two come from `first` ----
+    for (uint32_t L = 0; L < n_phys; L++)
+      for (uint32_t w = 0; w < lo.n_warps; w++) {
+        Instr& d = lp.code[pinfo[(size_t)L * lo.n_warps + w][0]];
+        if (L + 2 < n_phys) { const auto& nx = pinfo[(size_t)(L + 2) * lo.n_warps + w]; d.x = nx[0]; d.y = nx[1]; d.z = nx[2]; d.w = nx[3]; }
+        else { d.x = d.y = d.z = d.w = 0; }
+      }
+    lp.first.assign((size_t)lo.n_warps * 8, 0);
+    for (uint32_t w = 0; w < lo.n_warps; w++)
+      for (uint32_t j = 0; j < 2 && j < n_phys; j++)
+        for (int k = 0; k < 4; k++) lp.first[(size_t)w * 8 + j * 4 + k] = pinfo[(size_t)j * lo.n_warps + w][k];
+    lp.max_jobs = 1;
+    for (const auto& q : jobq) lp.max_jobs = std::max<uint32_t>(lp.max_jobs, (uint32_t)q.size());
+    lp.jobs.assign((size_t)lo.n_slow_warps * lp.max_jobs * 4, 0);
+    lp.n_jobs.assign(lo.n_slow_warps, 0);
+    for (uint32_t w = 0; w < lo.n_slow_warps; w++) {
+      lp.n_jobs[w] = (uint32_t)jobq[w].size();
+      for (size_t j = 0; j < jobq[w].size(); j++) {
+        uint32_t* e = &lp.jobs[((size_t)w * lp.max_jobs + j) * 4];
+        e[0] = jobq[w][j][0]; e[1] = jobq[w][j][1]; e[2] = jobq[w][j][2]; e[3] = 0;
+      }
+    }
+    lp.n_levels = n_phys;
+    lp.n_slots = std::max(n_slots, 1u);
+    return lp;
+  };
+
+  // D from the cost model: one inversion spans about (its cycles / an average level) levels
+  auto plan_for = [&](bool chain) {
+    use_chain = chain;
+    if (lo.slow_levels) return schedule(lo.slow_levels);
+    LatencyPlan first = schedule(24);
+    if (first.n_slow == 0) return first;
+    const double avg = std::max(200.0, (double)first.est_cycles / std::max(1u, first.n_levels));
+    const uint32_t D = (uint32_t)std::min(4096.0, std::max(2.0, 42000.0 / avg + 2.0));
+    return schedule(D);
+  };
+  // chains trade levels for lane parallelism (instructions of different shapes cannot share a warp): keep whichever
+  // schedule the cost model likes better (Poseidon / EdDSA graphs: chains; bit-level graphs like SHA-256: none)
+  LatencyPlan a = plan_for(false);
+  if (!lo.chain) return a;
+  LatencyPlan b = plan_for(true);
+  return b.est_cycles < a.est_cycles ? b : a;
 }
 
 }  // namespace gw

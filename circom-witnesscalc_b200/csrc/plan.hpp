@@ -26,6 +26,7 @@ struct PlanOptions {
   bool fuse_dot = true;      // fuse linear combinations into OP_DOT
   uint32_t max_terms = 8;    // max terms of one OP_DOT (<= DOT_MAX_TERMS, <= n_regs - 3)
   bool narrow = true;        // narrow typing: provably small values are computed on int64 (isa.h: F_NARROW)
+  bool fold_addc = false;    // Mul(constant, value +- constant) -> OP_DOT terms that do not wait for the Add (latency mode)
 };
 
 struct PlanStats {
@@ -53,17 +54,50 @@ struct Plan {
 
 Plan compile_plan(const Graph& g, const PlanOptions& opt);
 
-// Single-witness ("latency") mode: the same instruction format, but instructions are grouped into
-// dependency levels; all instructions of a level are independent and are executed by different threads
-// of ONE CTA, with a CTA barrier between levels.  Operands name slots of one shared-memory value file
-// (slots are recycled only at level boundaries, so there are no hazards inside a level).
+// Single-witness ("latency") mode.  The macro ops (fused linear combinations included) are scheduled level by
+// level: all instructions of a level are independent.  A level's instructions are spread over `n_warps` MAIN
+// warps of one CTA -- instructions of the same class share a warp (SIMT lanes), different classes go to different
+// warps (different SM sub-partitions) -- and a named barrier over the main warps separates levels.  The long
+// operations (Div/Inv/Pow/Idiv/Mod: tens of thousands of cycles) do not hold a level up: they are queued, in groups
+// of up to 32 of the same opcode, to `n_slow_warps` SLOW warps that run asynchronously; a job starts when the main
+// warps have published the level that produces its operands and its readers are scheduled `slow_levels` levels
+// later, behind a wait on the job's completion counter that a CONTROL warp performs before it joins the barrier of
+// the level in front of them (the control warp also publishes the completed levels: it has no asynchronous copies
+// in flight, so its fences are cheap).  Operands name slots of one shared-memory value file;
+// a slot is recycled only at a level boundary after its last reader (for a slow reader: after its OP_WAIT level).
+//
+//   code   : packets.  A packet is what ONE warp needs for ONE level (or one slow-warp job), contiguous: slot 0 =
+//            descriptor {offset, slots, headers, lanes of the same warp's packet two levels later}, then the headers
+//            (header k belongs to lane k mod lanes; a lane runs its headers in order: a chain), then
+//            what the headers point at with packet-relative slot offsets: OP_DOT tails (.z) and every constant operand
+//            (two slots each; OP_DOT terms carry the offset of their constant) -- one asynchronous global->shared
+//            copy brings a level's instructions and constants on chip, with no register in flight across a barrier.
+//   first  : [n_warps][2] {offset, slots, headers, lanes} of the packets of levels 0 and 1
+//   jobs   : [n_slow_warps][max_jobs] {issue level, packet offset, number of headers, 0}
+//   waits  : {level, slow warp, number of jobs of that warp that must be complete before the level ends, 0}
+struct LatencyOptions {
+  uint32_t max_slots = 7000;     // capacity of the shared-memory value file (32 B slots)
+  uint32_t packet_slots = 128;   // capacity of one stage of the kernel's packet ring (16 B slots): wide levels are cut to fit
+  uint32_t n_warps = 7;          // main warps that execute instructions (one more warp publishes levels and waits for jobs)
+  uint32_t n_slow_warps = 4;
+  uint32_t slow_levels = 0;      // levels between the issue of a long op and its first reader; 0 = from the cost model
+  bool split_dot = true;         // split a linear combination into an early part (operands known early) and a late part
+  bool fuse = true;              // OP_DOT / OP_SHRAND fusion (off: one instruction per graph node)
+  bool chain = true;             // run single-reader chains (x^2 -> x^4 -> x^5) in one lane inside one level
+  uint32_t max_chain = 4;        // instructions per chain
+};
 struct LatencyPlan {
-  std::vector<Instr> code;            // level after level
-  std::vector<uint32_t> level_count;  // instructions per level
-  std::vector<U256> consts;
+  std::vector<Instr> code;
+  std::vector<uint32_t> first;        // 8 words per main warp
+  std::vector<uint32_t> jobs;         // 4 words per (slow warp, job)
+  std::vector<uint32_t> n_jobs;       // per slow warp
+  std::vector<uint32_t> waits;        // 4 words per wait, ascending levels: {level, slow warp, jobs that must be complete, 0}
+  uint32_t n_levels = 0, n_warps = 0, n_slow_warps = 0, max_jobs = 0, slow_levels = 0;
   uint32_t n_slots = 0, n_inputs = 0, n_witness = 0;
   uint32_t max_level_width = 0;
+  uint64_t n_instrs = 0, n_slow = 0, n_split = 0, n_chained = 0;
+  uint64_t est_cycles = 0;            // cost model: sum over levels of the slowest warp + per-level overhead
 };
-LatencyPlan compile_latency_plan(const Graph& g, uint32_t max_slots);
+LatencyPlan compile_latency_plan(const Graph& g, const LatencyOptions& opt);
 
 }  // namespace gw

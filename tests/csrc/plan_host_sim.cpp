@@ -5,6 +5,7 @@
 // CPU fallback); the same alu_exec() runs on the device inside eval_batch_kernel.
 #include <string.h>
 
+#include <map>
 #include <memory>
 
 #include "../../circom-witnesscalc_b200/csrc/alu.cuh"
@@ -168,39 +169,126 @@ size_t sim_reserialize(SimGraph* s, uint8_t* out, size_t cap) {
 }
 void sim_wtns_header(uint32_t n, uint8_t* dst) { wtns_write_header(dst, n); }
 
-// latency plan: level by level; inside a level every instruction reads its operands before ANY
-// instruction of the level writes (the kernel runs them concurrently), which exposes slot hazards.
-// out5: n_levels, n_slots, n_instrs, max level width, status
-int64_t sim_eval_latency(SimGraph* s, const uint8_t* inputs, uint8_t* witness, uint64_t* out5) {
+// latency plan (plan.hpp: LatencyPlan): the main warps run level by level; inside a level every instruction reads
+// its operands before ANY instruction of the level writes (the kernel runs them concurrently), which exposes slot
+// hazards.  The slow warps are asynchronous on the device; the simulator runs each job at one of the two extremes
+// the protocol allows -- mode 0: as soon as its issue level starts, mode 1: just before the OP_WAIT that guards its
+// readers -- so a slot recycled too early (or a reader scheduled before the wait) shows up as a wrong witness.
+// opts: {n_warps, n_slow_warps, slow_levels, split_dot, fuse, packet_slots} (0 = default except for the two flags)
+// out8: n_levels, n_slots, n_instrs, max level width, status, est_cycles, n_split, slow_levels
+int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, uint64_t* out8, int mode, const uint32_t* opts) {
   LatencyPlan lp;
-  try { lp = compile_latency_plan(s->g, 7264); } catch (const std::exception&) { return -2; }
+  try {
+    LatencyOptions o;
+    if (opts) { if (opts[0]) o.n_warps = opts[0]; if (opts[1]) o.n_slow_warps = opts[1]; o.slow_levels = opts[2]; o.split_dot = opts[3] != 0; o.fuse = opts[4] != 0; if (opts[5]) o.packet_slots = opts[5]; o.chain = opts[6] != 0; }
+    lp = compile_latency_plan(s->g, o);
+  } catch (const std::exception& e) { s->err = e.what(); return -2; }
   std::vector<fe> slots(lp.n_slots, fe_zero());
   uint32_t st = 0;
-  size_t pos = 0;
   struct W { uint32_t dst; fe v; };
-  for (uint32_t cnt : lp.level_count) {
-    std::vector<W> writes;
-    for (size_t k = pos; k < pos + cnt; k++) {
-      const Instr& ins = lp.code[k];
-      uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
-      if (op == OP_NOP) continue;
-      auto load = [&](uint32_t idx, bool is_const, fe* o) { if (is_const) { if (idx >= lp.consts.size()) return false; *o = to_fe(lp.consts[idx]); } else { if (idx >= lp.n_slots) return false; *o = slots[idx]; } return true; };
-      fe A = fe_zero(), B = fe_zero(), C = fe_zero(), R;
-      if (op == OP_INPUT) { if (ins.y >= lp.n_inputs) return -1; fe v; memcpy(v.l, inputs + 32 * (size_t)ins.y, 32); R = fe_reduce256(v); }
-      else {
-        if (!load(ins.y, ins.x & F_A_CONST, &A)) return -1;
-        if (op == OP_OUT) { if (ins.w >= lp.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, A.l, 32); continue; }
-        if (op_has_b(op) && !load(ins.z, ins.x & F_B_CONST, &B)) return -1;
-        if (op == OP_TERN && !load(ins.w, ins.x & F_C_CONST, &C)) return -1;
-        R = alu_exec(op, A, B, C, st);
+  // operands: a slot of the value file, or a constant stored inline in the packet (two slots at a packet-relative offset)
+  auto pconst = [&](size_t pk, uint32_t rel, fe* o) {
+    if (pk + rel + 1 >= lp.code.size()) return false;
+    const Instr& a = lp.code[pk + rel]; const Instr& b = lp.code[pk + rel + 1];
+    o->l[0] = a.x; o->l[1] = a.y; o->l[2] = a.z; o->l[3] = a.w; o->l[4] = b.x; o->l[5] = b.y; o->l[6] = b.z; o->l[7] = b.w;
+    return true;
+  };
+  // a lane sees its own earlier writes of the level (program order); everybody else's only after the level barrier
+  std::map<uint32_t, fe> overlay;
+  auto rslot = [&](uint32_t idx) { auto it = overlay.find(idx); return it != overlay.end() ? it->second : slots[idx]; };
+  auto load = [&](size_t pk, uint32_t idx, bool is_const, fe* o) { if (is_const) return pconst(pk, idx, o); if (idx >= lp.n_slots) return false; *o = rslot(idx); return true; };
+  // value of one header of the packet at `pk` from the current slot file; writes go to `writes`
+  auto exec = [&](size_t pk, const Instr& ins, std::vector<W>& writes) {
+    const uint32_t op = ins.x & 0xFF, dst = ins.x >> 16;
+    if (op == OP_NOP) return true;
+    fe A = fe_zero(), B = fe_zero(), C = fe_zero(), R;
+    if (op == OP_INPUT) { if (ins.y >= lp.n_inputs) return false; fe v; memcpy(v.l, inputs + 32 * (size_t)ins.y, 32); R = fe_reduce256(v); }
+    else if (op == OP_DOT) {
+      const uint32_t nt = ins.y & 0xFF, ncs = (ins.y >> 8) & 0xFF;
+      if (nt == 0 || nt > DOT_MAX_TERMS || ncs < 1 || ncs > 3 || pk + ins.z + ((nt + 1) >> 1) > lp.code.size()) return false;
+      dot_acc P; dot_init(P);
+      for (uint32_t t = 0; t < nt; t++) {
+        const Instr& sl = lp.code[pk + ins.z + (t >> 1)];
+        const uint32_t lo = (t & 1) ? sl.z : sl.x, ci = (t & 1) ? sl.w : sl.y;
+        const uint32_t kind = lo & 0xF, reg = lo >> 16;
+        fe c = fe_zero();
+        if (kind > T_CONST || reg >= lp.n_slots) return false;
+        if ((kind == T_MAC || kind == T_CONST) && !pconst(pk, ci, &c)) return false;
+        dot_term(P, kind, rslot(reg), c);
       }
-      if (dst != NO_DST) { if (dst >= lp.n_slots) return -1; writes.push_back({dst, R}); }
-      if (ins.x & F_OUT) { if (ins.w >= lp.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
+      R = fe_mont_reduce(P, (int)ncs);
+    } else if (op == OP_SHRAND) {
+      fe c;
+      if (ins.y >= lp.n_slots || !pconst(pk, ins.z >> 8, &c)) return false;
+      R = fe_shr_and(rslot(ins.y), ins.z & 0xFF, c);
+    } else {
+      if (!load(pk, ins.y, ins.x & F_A_CONST, &A)) return false;
+      if (op == OP_OUT) { if (ins.w >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, A.l, 32); return true; }
+      if (op_has_b(op) && !load(pk, ins.z, ins.x & F_B_CONST, &B)) return false;
+      if (op == OP_TERN && !load(pk, ins.w, ins.x & F_C_CONST, &C)) return false;
+      R = alu_exec(op, A, B, C, st);
     }
-    for (const W& w : writes) slots[w.dst] = w.v;
-    pos += cnt;
+    if (dst != NO_DST) { if (dst >= lp.n_slots) return false; writes.push_back({dst, R}); overlay[dst] = R; }
+    if ((ins.x & F_OUT) && op != OP_TERN) { if (ins.w >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
+    return true;
+  };
+  std::vector<uint32_t> next_job(lp.n_slow_warps, 0);
+  auto run_job = [&](uint32_t w, uint32_t j) {
+    const uint32_t* e = &lp.jobs[((size_t)w * lp.max_jobs + j) * 4];
+    std::vector<W> writes;
+    for (uint32_t k = 0; k < e[2]; k++) { overlay.clear(); if ((size_t)e[1] + 1 + k >= lp.code.size() || !exec(e[1], lp.code[e[1] + 1 + k], writes)) return false; }
+    overlay.clear();
+    for (const W& x : writes) slots[x.dst] = x.v;
+    return true;
+  };
+  // packets of the main warps: levels 0 and 1 from `first`, level L + 2 from the descriptor of level L (what the kernel walks)
+  std::vector<uint32_t> cur(lp.n_warps * 4), nxt(lp.n_warps * 4);
+  for (uint32_t w = 0; w < lp.n_warps; w++) for (int k = 0; k < 4; k++) { cur[w * 4 + k] = lp.first[w * 8 + k]; nxt[w * 4 + k] = lp.first[w * 8 + 4 + k]; }
+  uint64_t n_headers = 0;
+  size_t next_wait = 0;
+  for (uint32_t L = 0; L < lp.n_levels; L++) {
+    for (uint32_t w = 0; w < lp.n_warps; w++) if ((size_t)cur[w * 4] + cur[w * 4 + 1] > lp.code.size() || cur[w * 4 + 2] + 1 > cur[w * 4 + 1] || cur[w * 4 + 3] > 32 || (cur[w * 4 + 2] && !cur[w * 4 + 3])) return -1;
+    // slow jobs first: mode 0 = every job issued at this level, mode 1 = the jobs this level's OP_WAITs wait for
+    if (mode == 0) {
+      for (uint32_t w = 0; w < lp.n_slow_warps; w++)
+        while (next_job[w] < lp.n_jobs[w] && lp.jobs[((size_t)w * lp.max_jobs + next_job[w]) * 4] <= L) { if (!run_job(w, next_job[w])) return -1; next_job[w]++; }
+    } else {
+      for (; next_wait * 4 < lp.waits.size() && lp.waits[next_wait * 4] == L; next_wait++) {
+        const uint32_t ws = lp.waits[next_wait * 4 + 1], seq = lp.waits[next_wait * 4 + 2];
+        if (ws >= lp.n_slow_warps || seq > lp.n_jobs[ws]) return -1;
+        while (next_job[ws] < seq) {
+          if (lp.jobs[((size_t)ws * lp.max_jobs + next_job[ws]) * 4] > L) return -3;     // waits for a job that cannot have started
+          if (!run_job(ws, next_job[ws])) return -1;
+          next_job[ws]++;
+        }
+      }
+    }
+    std::vector<W> writes;
+    for (uint32_t w = 0; w < lp.n_warps; w++) {
+      const size_t pk = cur[w * 4];
+      const uint32_t nh = cur[w * 4 + 2], lanes = cur[w * 4 + 3];
+      for (uint32_t lane = 0; lane < lanes; lane++) {
+        overlay.clear();
+        for (uint32_t k = lane; k < nh; k += lanes) { if (!exec(pk, lp.code[pk + 1 + k], writes)) return -1; n_headers++; }
+      }
+    }
+    overlay.clear();
+    for (const W& x : writes) slots[x.dst] = x.v;
+    for (uint32_t w = 0; w < lp.n_warps; w++) {
+      const Instr d = lp.code[cur[w * 4]];
+      for (int k = 0; k < 4; k++) cur[w * 4 + k] = nxt[w * 4 + k];
+      nxt[w * 4] = d.x; nxt[w * 4 + 1] = d.y; nxt[w * 4 + 2] = d.z; nxt[w * 4 + 3] = d.w;
+    }
   }
-  out5[0] = lp.level_count.size(); out5[1] = lp.n_slots; out5[2] = lp.code.size(); out5[3] = lp.max_level_width; out5[4] = st;
+  for (uint32_t w = 0; w < lp.n_slow_warps; w++) while (next_job[w] < lp.n_jobs[w]) { if (!run_job(w, next_job[w])) return -1; next_job[w]++; }
+  out8[0] = lp.n_levels; out8[1] = lp.n_slots; out8[2] = lp.n_instrs; out8[3] = lp.max_level_width; out8[4] = st;
+  out8[5] = lp.est_cycles; out8[6] = lp.n_split; out8[7] = lp.slow_levels; out8[8] = lp.n_chained;
   return 0;
+}
+int64_t sim_eval_latency(SimGraph* s, const uint8_t* inputs, uint8_t* witness, uint64_t* out5) {
+  uint64_t o8[9];
+  int64_t rc = sim_eval_latency2(s, inputs, witness, o8, 0, nullptr);
+  if (rc == 0) for (int k = 0; k < 5; k++) out5[k] = o8[k];
+  return rc;
 }
 }

@@ -160,6 +160,9 @@ def sim_lib():
         L.sim_eval.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.sim_eval_latency.restype = ctypes.c_int64
         L.sim_eval_latency.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)]
+        L.sim_eval_latency2.restype = ctypes.c_int64
+        L.sim_eval_latency2.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_uint32)]
         L.sim_inputs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
         L.sim_reserialize.restype = ctypes.c_size_t
         L.sim_reserialize.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
@@ -193,13 +196,16 @@ class SimGraph:
         assert st >= 0, "malformed plan"
         return unpack_u256(out.raw), int(st)
 
-    def eval_latency(self, inputs):
-        """latency-mode plan on the host simulator -> (witness list, info dict)"""
+    def eval_latency(self, inputs, mode=0, n_warps=0, n_slow_warps=0, slow_levels=0, split_dot=True, fuse=True, packet_slots=0, chain=True):
+        """latency-mode plan on the host simulator -> (witness list, info dict).  mode 0 / 1: the slow-warp jobs
+        run as early / as late as the protocol allows (tests/csrc/plan_host_sim.cpp)."""
         out = ctypes.create_string_buffer(32 * self.info["W"])
-        o5 = (ctypes.c_uint64 * 5)()
-        rc = self.L.sim_eval_latency(self.h, pack_u256(inputs), out, o5)
+        o8 = (ctypes.c_uint64 * 9)()
+        opts = (ctypes.c_uint32 * 7)(n_warps, n_slow_warps, slow_levels, int(split_dot), int(fuse), packet_slots, int(chain))
+        rc = self.L.sim_eval_latency2(self.h, pack_u256(inputs), out, o8, mode, opts)
         assert rc == 0, f"latency plan failed ({rc})"
-        return unpack_u256(out.raw), dict(zip(["n_levels", "n_slots", "n_instrs", "max_width", "status"], [int(x) for x in o5]))
+        keys = ["n_levels", "n_slots", "n_instrs", "max_width", "status", "est_cycles", "n_split", "slow_levels", "n_chained"]
+        return unpack_u256(out.raw), dict(zip(keys, [int(x) for x in o8]))
 
     def inputs_from_json(self, js: str):
         buf = ctypes.create_string_buffer(32 * self.info["I"])

@@ -1,0 +1,2 @@
+mkdir -p gpurun_out/lat
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -40
