@@ -285,8 +285,27 @@ __device__ __forceinline__ void lat_exec(const LatCtx& cx, uint32_t pk_s, const 
   if (op == OP_DOT) {
     const uint32_t nt = ins.y & 0xFFu;
     const uint32_t tail_s = pk_s + 16u * ins.z;
+    const uint32_t shape = ins.y >> 16;
     dot_acc P;
     dot_init(P);
+    if (shape & 1u) {
+      // straight-line path for the Poseidon mix shapes (plan.cpp: shape hint): every operand fetch is issued up front,
+      // no term loop, no per-term dispatch
+      const uint32_t n_mac = (shape >> 1) & 3u;
+      const uint4 t01 = lds128(tail_s), t23 = lds128(tail_s + 16u);
+      const fe x0 = slot_load(t01.x >> 16), c0 = const_load(t01.y);
+      // term 1 is the second product, or the added value, or the constant; term 2 / 3 follow in that order
+      uint32_t k = 1;
+      fe x1 = x0, c1 = c0;
+      if (n_mac == 2) { x1 = slot_load(t01.z >> 16); c1 = const_load(t01.w); k = 2; }
+      fe av = x0, cv = c0;
+      if (shape & 8u) { av = slot_load((k == 1 ? t01.z : t23.x) >> 16); k++; }
+      if (shape & 16u) cv = const_load(k == 1 ? t01.w : k == 2 ? t23.y : t23.w);
+      dot_mac(P, x0.l, c0.l);
+      if (n_mac == 2) dot_mac(P, x1.l, c1.l);
+      if (shape & 8u) dot_add256(P, av.l, 8);
+      if (shape & 16u) dot_add256(P, cv.l, 0);
+    } else
 #pragma unroll 1
     for (uint32_t t = 0; t < nt; t++) {
       const uint4 sl = lds128(tail_s + 16u * (t >> 1));

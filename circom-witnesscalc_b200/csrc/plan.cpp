@@ -1001,7 +1001,14 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
         }
         if (words.size() & 2) { words.push_back(0); words.push_back(0); }
         for (size_t k = 0; k < words.size(); k += 4) { Instr& sl = pk[tail + k / 4]; sl.x = words[k]; sl.y = words[k + 1]; sl.z = words[k + 2]; sl.w = words[k + 3]; }
-        return make_instr(OP_DOT, flags, dst, (uint32_t)ts.size() | (o.ncs << 8), tail, o.out_pos);
+        // shape hint for the kernel's straight-line path (.y bits 16..): 1-2 products, at most one added value, no
+        // subtracted value, at most one constant -- the Poseidon mix layers; bit 0 = applies, bits 1-2 = number of
+        // products, bit 3 = has an added value, bit 4 = has a constant.  Terms are already ordered MAC, +value, constant.
+        uint32_t n_k[4] = {0, 0, 0, 0};
+        for (const PTerm& t : ts) n_k[t.kind == 0 ? 0 : t.kind == 2 ? 3 : (t.neg ? 2 : 1)]++;
+        uint32_t shape = 0;
+        if (n_k[0] >= 1 && n_k[0] <= 2 && n_k[1] <= 1 && n_k[2] == 0 && n_k[3] <= 1) shape = 1u | (n_k[0] << 1) | (n_k[1] << 3) | (n_k[3] << 4);
+        return make_instr(OP_DOT, flags, dst, (uint32_t)ts.size() | (o.ncs << 8) | (shape << 16), tail, o.out_pos);
       }
       uint32_t enc[3] = {0, 0, 0};
       for (int k = 0; k < o.n_in; k++) {
@@ -1087,8 +1094,10 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       for (size_t a = 0; a < slows.size();) {
         size_t b = a;
         while (b < slows.size() && b - a < 32 && ops[slows[b]].opc == ops[slows[a]].opc) b++;
-        uint32_t w = 0;
-        for (uint32_t x = 1; x < lo.n_slow_warps; x++) if (busy[x] < busy[w]) w = x;
+        // least busy slow warp; ties go to the highest index: the heaviest instruction classes of a level sit on main
+        // warps 0, 1, .. and a warp's SM sub-partition is its index mod 4, so the long jobs keep away from them
+        uint32_t w = lo.n_slow_warps - 1;
+        for (uint32_t x = lo.n_slow_warps - 1; x-- > 0;) if (busy[x] < busy[w]) w = x;
         busy[w] = std::max<uint64_t>(busy[w], L) + D;
         std::vector<const LOp*> jl;
         for (size_t k = a; k < b; k++) jl.push_back(&ops[slows[k]]);
