@@ -271,7 +271,14 @@ def main():
     # end to end through the C ABI with HOST buffers (pinned), H2D + kernel + D2H inside the timed region
     e2e = None
     if not a.no_e2e:
-        n_e = min(a.e2e_sets, B)
+        # per-rank sample: the ranks of one box share its host memory (pinned) and its PCIe root, so the sample is
+        # divided among them and bounded by a third of the memory that is available right now
+        n_e = min(max(a.e2e_sets // world, 1024), B)
+        try:
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable:")][0]
+            n_e = max(256, min(n_e, int(avail / 3 / world / (W * 32))))
+        except (OSError, IndexError, ValueError):
+            pass
         del d_out
         torch.cuda.empty_cache()
         h_in = torch.from_numpy(host_in[:min(n_unique, n_e)].reshape(-1, I * 32)).repeat((n_e + n_unique - 1) // n_unique, 1)[:n_e].contiguous().pin_memory()

@@ -104,10 +104,13 @@ int gw_calc_witness_batch(gw_graph_t *graph, const uint8_t *inputs, size_t n_set
 int gw_calc_witness_batch_device(gw_graph_t *graph, int device, const void *d_inputs, size_t n_sets,
                                  void *d_witness, uint32_t *d_flags, void *cuda_stream, gw_status_t *status);
 
-/* single-witness latency mode (BASELINE config 5): ONE input set (n_inputs x 32 B, host) is evaluated by
- * one CTA that spreads the independent nodes of every dependency level over its threads; witness is
- * n_witness x 32 B (host).  *kernel_ms (optional) receives the device time of the kernel alone.
- * gw_calc_witness / gw_graph_calc_witness use this mode for their single witness. */
+/* single-witness latency mode (BASELINE config 5): ONE input set (n_inputs x 32 B, host) is evaluated by one
+ * CTA: the graph is scheduled into dependency levels, the independent instructions of a level are spread over
+ * the lanes of the main warps, the long operations (Div, Pow, Idiv, Mod) run asynchronously on dedicated warps;
+ * witness is n_witness x 32 B (host).  *kernel_ms (optional) receives the device time of the kernel alone.
+ * Fails with "latency plan: graph is too wide ..." when the values alive at one level do not fit the shared
+ * memory of one SM.  gw_calc_witness / gw_graph_calc_witness use this mode for their single witness and fall
+ * back to the throughput kernel with a batch of one in that case. */
 int gw_calc_witness_latency(gw_graph_t *graph, int device, const uint8_t *inputs, uint8_t *witness, uint32_t *flags,
                             float *kernel_ms, gw_status_t *status);
 
