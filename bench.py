@@ -273,7 +273,7 @@ def main():
     if not a.no_e2e:
         # per-rank sample: the ranks of one box share its host memory (pinned) and its PCIe root, so the sample is
         # divided among them and bounded by a third of the memory that is available right now
-        n_e = min(max(a.e2e_sets // world, 1024), B)
+        n_e = min(max(a.e2e_sets // world, 4096), B)
         try:
             avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable:")][0]
             n_e = max(256, min(n_e, int(avail / 3 / world / (W * 32))))
@@ -283,13 +283,13 @@ def main():
         torch.cuda.empty_cache()
         h_in = torch.from_numpy(host_in[:min(n_unique, n_e)].reshape(-1, I * 32)).repeat((n_e + n_unique - 1) // n_unique, 1)[:n_e].contiguous().pin_memory()
         h_out = torch.empty((n_e, W * 32), dtype=torch.uint8).pin_memory()
-        g.calc_witness_batch_ptr(h_in.data_ptr(), min(n_e, 512), h_out.data_ptr())          # warm-up (allocates staging)
-        g.calc_witness_batch_ptr(h_in.data_ptr(), n_e, h_out.data_ptr())
+        g.calc_witness_batch_ptr(h_in.data_ptr(), min(n_e, 512), h_out.data_ptr(), first_device=local_rank)          # warm-up (allocates staging)
+        g.calc_witness_batch_ptr(h_in.data_ptr(), n_e, h_out.data_ptr(), first_device=local_rank)
         barrier()
         reps = 2
         t0 = time.perf_counter()
         for _ in range(reps):
-            g.calc_witness_batch_ptr(h_in.data_ptr(), n_e, h_out.data_ptr())
+            g.calc_witness_batch_ptr(h_in.data_ptr(), n_e, h_out.data_ptr(), first_device=local_rank)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -53,6 +53,7 @@ _L.gw_graph_info.argtypes = [_vp, ctypes.POINTER(gw_graph_info_t)]
 _L.gw_graph_input_signal.argtypes = [_vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
 _L.gw_graph_calc_witness.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_vp), ctypes.POINTER(_sz), ctypes.POINTER(gw_status_t)]
 _L.gw_calc_witness_batch.argtypes = [_vp, _vp, _sz, _vp, _vp, ctypes.c_int, ctypes.POINTER(gw_status_t)]
+_L.gw_calc_witness_batch_on.argtypes = [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, ctypes.c_int, ctypes.POINTER(gw_status_t)]
 _L.gw_calc_witness_batch_device.argtypes = [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, ctypes.POINTER(gw_status_t)]
 _L.gw_calc_witness_latency.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(gw_status_t)]
 _L.gw_wtns_header.argtypes = [ctypes.c_uint32, _vp]
@@ -66,7 +67,7 @@ _L.gw_microbench_imad.restype = ctypes.c_double
 _L.gw_microbench_imad.argtypes = [ctypes.c_int, ctypes.c_int]
 
 EXPORTS = ["gw_calc_witness", "gw_graph_load", "gw_graph_free", "gw_graph_info", "gw_graph_input_signal",
-           "gw_graph_calc_witness", "gw_calc_witness_batch", "gw_calc_witness_batch_device", "gw_calc_witness_latency", "gw_wtns_header",
+           "gw_graph_calc_witness", "gw_calc_witness_batch", "gw_calc_witness_batch_on", "gw_calc_witness_batch_device", "gw_calc_witness_latency", "gw_wtns_header",
            "gw_device_count", "gw_microbench_imad", "gw_inputs_parse_batch", "gw_wtns_file_size", "gw_calc_witness_batch_wtns",
            "gw_graph_select"]
 
@@ -235,10 +236,11 @@ class Graph:
         _check(rc, st)
         return out, float(ms.value)
 
-    def calc_witness_batch_ptr(self, inputs_ptr, n_sets, witness_ptr, flags_ptr=None, n_gpus=1):
-        """HOST pointers (e.g. pinned torch tensors): no allocation, no copies besides the DMA."""
+    def calc_witness_batch_ptr(self, inputs_ptr, n_sets, witness_ptr, flags_ptr=None, n_gpus=1, first_device=0):
+        """HOST pointers (e.g. pinned torch tensors): no allocation, no copies besides the DMA.  The sets are sharded
+        over devices first_device .. first_device + n_gpus - 1 (gw_calc_witness_batch_on)."""
         st = gw_status_t()
-        rc = _L.gw_calc_witness_batch(self._h, inputs_ptr, n_sets, witness_ptr, flags_ptr, n_gpus, ctypes.byref(st))
+        rc = _L.gw_calc_witness_batch_on(self._h, first_device, inputs_ptr, n_sets, witness_ptr, flags_ptr, n_gpus, ctypes.byref(st))
         _check(rc, st)
 
     def calc_witness_batch_device(self, device, d_inputs_ptr, n_sets, d_witness_ptr, d_flags_ptr=None, stream=None):

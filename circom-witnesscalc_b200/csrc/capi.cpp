@@ -138,16 +138,22 @@ int gw_graph_calc_witness(gw_graph_t* graph, const char* inputs_json, void** wtn
   return guarded(status, [&]() { calc_one(*graph->engine, inputs_json, wtns_data, wtns_len); });
 }
 
-int gw_calc_witness_batch(gw_graph_t* graph, const uint8_t* inputs, size_t n_sets, uint8_t* witness, uint32_t* flags,
-                          int n_gpus, gw_status_t* status) {
+int gw_calc_witness_batch_on(gw_graph_t* graph, int first_device, const uint8_t* inputs, size_t n_sets, uint8_t* witness,
+                             uint32_t* flags, int n_gpus, gw_status_t* status) {
   if (!graph || (n_sets && (!inputs || !witness))) { set_status(status, ERROR, "null argument"); return 1; }
   return guarded(status, [&]() {
     int ndev = cuda_device_count();
     if (ndev == 0) throw Error("no CUDA device available: this library has no CPU fallback");
     if (n_gpus < 1) n_gpus = 1;
-    if (n_gpus > ndev) throw Error("n_gpus exceeds the number of visible CUDA devices");
-    graph->engine->run_host(inputs, n_sets, witness, flags, n_gpus, 0);
+    if (first_device < 0 || first_device + n_gpus > ndev) throw Error("device range exceeds the visible CUDA devices");
+    graph->engine->run_host(inputs, n_sets, witness, flags, n_gpus, first_device);
   });
+}
+
+int gw_calc_witness_batch(gw_graph_t* graph, const uint8_t* inputs, size_t n_sets, uint8_t* witness, uint32_t* flags,
+                          int n_gpus, gw_status_t* status) {
+  if (graph && n_gpus > cuda_device_count() && cuda_device_count() > 0) { set_status(status, ERROR, "n_gpus exceeds the number of visible CUDA devices"); return 1; }
+  return gw_calc_witness_batch_on(graph, 0, inputs, n_sets, witness, flags, n_gpus, status);
 }
 
 int gw_calc_witness_batch_device(gw_graph_t* graph, int device, const void* d_inputs, size_t n_sets, void* d_witness,

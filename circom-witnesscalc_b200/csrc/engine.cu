@@ -664,20 +664,34 @@ void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* w
   // Both streams share the spill area, so kernels of consecutive chunks must not overlap: an event
   // chains kernel k+1 behind kernel k while the copies of the two streams overlap with it.
   cudaEvent_t kdone[2]; CUDA_CHECK(cudaEventCreateWithFlags(&kdone[0], cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&kdone[1], cudaEventDisableTiming));
+  // GW_TRACE_HOST=1: device-side timeline of the call (per chunk: start, inputs landed, kernel done, witness landed)
+  const bool trace = env_int("GW_TRACE_HOST", 0) != 0;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   int k = 0;
   for (size_t off = 0; off < B; off += chunk, k ^= 1) {
     size_t nb = std::min(chunk, B - off);
     cudaStream_t s = d->stream[k];
+    mark(s);
     CUDA_CHECK(cudaMemcpyAsync(d->d_in[k], inputs + off * in_b, nb * in_b, cudaMemcpyHostToDevice, s));
+    mark(s);
     if (off) CUDA_CHECK(cudaStreamWaitEvent(s, kdone[k ^ 1], 0));
     launch(d, d->d_in[k], nb, d->d_out[k], status ? d->d_status[k] : nullptr, s);
     CUDA_CHECK(cudaEventRecord(kdone[k], s));
+    mark(s);
     if (out_pitch == out_b) CUDA_CHECK(cudaMemcpyAsync(witness + off * out_b, d->d_out[k], nb * out_b, cudaMemcpyDeviceToHost, s));
     else if (out_b) CUDA_CHECK(cudaMemcpy2DAsync(witness + off * out_pitch, out_pitch, d->d_out[k], out_b, out_b, nb, cudaMemcpyDeviceToHost, s));
     if (status) CUDA_CHECK(cudaMemcpyAsync(status + off, d->d_status[k], nb * 4, cudaMemcpyDeviceToHost, s));
+    mark(s);
   }
   CUDA_CHECK(cudaStreamSynchronize(d->stream[0]));
   CUDA_CHECK(cudaStreamSynchronize(d->stream[1]));
+  if (trace) {
+    fprintf(stderr, "[gw trace] device %d: %zu sets, chunk %zu:", device, B, chunk);
+    for (size_t i = 0; i < tev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, "%s%.1f", i % 4 == 0 ? " | " : " ", ms); }
+    fprintf(stderr, " ms\n");
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
   cudaEventDestroy(kdone[0]); cudaEventDestroy(kdone[1]);
 }
 

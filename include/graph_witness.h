@@ -99,6 +99,11 @@ int gw_graph_calc_witness(gw_graph_t *graph, const char *inputs_json, void **wtn
 int gw_calc_witness_batch(gw_graph_t *graph, const uint8_t *inputs, size_t n_sets, uint8_t *witness,
                           uint32_t *flags, int n_gpus, gw_status_t *status);
 
+/* same on devices first_device .. first_device + n_gpus - 1: for hosts that run one process per GPU (each process
+ * passes its own device) or that keep some devices for other work. */
+int gw_calc_witness_batch_on(gw_graph_t *graph, int first_device, const uint8_t *inputs, size_t n_sets,
+                             uint8_t *witness, uint32_t *flags, int n_gpus, gw_status_t *status);
+
 /* same, buffers already resident on CUDA device `device`; enqueued on `cuda_stream` (a cudaStream_t,
  * NULL = default stream) and asynchronous with respect to the host. */
 int gw_calc_witness_batch_device(gw_graph_t *graph, int device, const void *d_inputs, size_t n_sets,
