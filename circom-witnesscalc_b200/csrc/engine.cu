@@ -179,6 +179,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
           u256_mul_wide(Pm, A.l, Bv.l);
         }
         R = fe_barrett(Pm);
+      } else if (op == OP_POW5) {
+        // Poseidon S-box in one instruction: x^2 and x^4 go straight to their witness positions (isa.h)
+        const fe A = rf_load(ins.y & 0xFFFFu);
+        const uint32_t d4 = ins.y >> 16;
+        uint32_t Pm[16];
+        u256_sqr_wide(Pm, A.l);
+        const fe x2 = fe_barrett(Pm);
+        if (ins.z != NO_POS) out_store(ins.z, x2);
+        u256_sqr_wide(Pm, x2.l);
+        const fe x4 = fe_barrett(Pm);
+        if (d4 != 0xFFFFu) out_store(ins.z + d4, x4);
+        u256_mul_wide(Pm, x4.l, A.l);
+        R = fe_barrett(Pm);
       } else if (op == OP_ADD || op == OP_SUB) {
         const fe A = (ins.x & F_A_CONST) ? const_load(ins.y) : rf_load(ins.y);
         const fe Bv = (ins.x & F_B_CONST) ? const_load(ins.z) : rf_load(ins.z);
@@ -543,6 +556,7 @@ void Engine::init_plan() {
   opt.div_batch = (uint32_t)env_int("GW_DIV_BATCH", (int)opt.div_batch);
   opt.fuse_dot = env_int("GW_FUSE_DOT", 1) != 0;
   opt.narrow = env_int("GW_NARROW", 1) != 0;
+  opt.fuse_pow5 = env_int("GW_FUSE_POW5", 1) != 0;
   opt.max_terms = (uint32_t)env_int("GW_MAX_TERMS", (int)opt.max_terms);
   plan = compile_plan(graph, opt);
 }

@@ -31,6 +31,9 @@ enum Opcode : uint32_t {
   OP_SQR = 52,       // dst <- a*a   (Mul with both operands the same node)
   OP_DOT = 53,       // dst <- sum of terms mod M with ONE Montgomery reduction; y = n_terms | n_cond_sub << 8
   OP_SHRAND = 54,    // dst <- (a >> k) & const;  z = k[7:0] | constant index << 8  (Num2Bits: Band(Shr(x, k), 1))
+  OP_POW5 = 55,      // dst <- a^5 with a^2, a^4 also stored as witness values (Poseidon S-box: x2 = x*x; x4 = x2*x2; x5 = x4*x);
+                     // .y = register of a | d4 << 16, .z = witness position of a^2 (NO_POS: none), a^4 goes to position
+                     // .z + d4 (d4 = 0xFFFF: none), .w = position of a^5 (F_OUT).  Throughput plan only.
   OP_NOP = 63,
 };
 
@@ -65,6 +68,7 @@ enum TermKind : uint32_t {
 static const uint32_t DOT_MAX_TERMS = 16;
 
 static const uint32_t NO_DST = 0xFFFFu;
+static const uint32_t NO_POS = 0xFFFFFFFFu;
 
 struct Instr { uint32_t x, y, z, w; };
 

@@ -286,6 +286,7 @@ struct MOp {
   uint32_t ncs = 1;
   uint32_t shift = 0; U256 mask;  // OP_SHRAND
   bool narrow = false;            // F_NARROW: int64 operands and result
+  uint32_t pos2 = NO_POS, pos4 = NO_POS;   // OP_POW5: witness positions of a^2 and a^4
 };
 
 // bound of the Montgomery-reduced sum before the conditional subtractions, in units of M:
@@ -562,8 +563,39 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
   const Typing& ty = mp.ty;
   const std::vector<uint32_t>& out_start = mp.out_start;
   const std::vector<uint32_t>& out_list = mp.out_list;
-  const std::vector<MOp>& mops = mp.mops;
   auto n_out = [&](uint32_t i) { return out_start[i + 1] - out_start[i]; };
+  // Poseidon S-box: Sqr(x) -> Sqr(.) -> Mul(., x) with single-reader intermediates becomes ONE OP_POW5: x stays in
+  // registers, x^2 and x^4 go straight to their witness positions and never enter the register file
+  if (opt.fuse_pow5) {
+    std::vector<uint32_t> readers(N, 0);
+    for (const MOp& m : mp.mops) {
+      if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) readers[t.node]++; }
+      else for (int k = 0; k < m.n_in; k++) if (!mp.is_const[m.in[k]] && (k == 0 || m.in[k] != m.in[0]) && (k < 2 || m.in[k] != m.in[1])) readers[m.in[k]]++;   // distinct operands
+    }
+    std::vector<MOp> fused; fused.reserve(mp.mops.size());
+    for (size_t q = 0; q < mp.mops.size(); q++) {
+      const MOp& a = mp.mops[q];
+      if (q + 2 < mp.mops.size() && a.opc == OP_SQR && !a.narrow && !mp.is_const[a.in[0]]) {
+        const MOp& b = mp.mops[q + 1]; const MOp& c = mp.mops[q + 2];
+        const bool chain = b.opc == OP_SQR && !b.narrow && b.in[0] == a.node && c.opc == OP_MUL && !c.narrow &&
+                           ((c.in[0] == b.node && c.in[1] == a.in[0]) || (c.in[1] == b.node && c.in[0] == a.in[0])) &&
+                           readers[a.node] == 1 && readers[b.node] == 1 && n_out(a.node) <= 1 && n_out(b.node) <= 1;
+        const uint32_t p2 = chain && n_out(a.node) ? out_list[out_start[a.node]] : NO_POS, p4 = chain && n_out(b.node) ? out_list[out_start[b.node]] : NO_POS;
+        // the position of a^4 is encoded relative to that of a^2 (circom numbers in2, in4 consecutively)
+        if (chain && (p4 == NO_POS || (p2 != NO_POS && p4 >= p2 && p4 - p2 < 0xFFFFu))) {
+          MOp f = c; f.opc = OP_POW5; f.n_in = 1; f.in[0] = a.in[0];
+          f.pos2 = p2; f.pos4 = p4;
+          fused.push_back(f);
+          plan.stats.pow5++;
+          q += 2;
+          continue;
+        }
+      }
+      fused.push_back(a);
+    }
+    mp.mops.swap(fused);
+  }
+  const std::vector<MOp>& mops = mp.mops;
   auto nconst_of = [&](const U256& c, bool neg) {       // int64 table form of a small signed constant
     int64_t v = 0;
     if (!signed_small(c, &v)) throw Error("plan: narrow instruction with a wide constant");
@@ -680,6 +712,9 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       if (m.opc == OP_DOT) {
         al.emit(make_instr(OP_DOT, e.flags, dsts[u], (uint32_t)m.terms.size() | (m.ncs << 8), 0, out_inline[u] ? outs[0] : 0));
         for (const Instr& sl : e.term_slots) plan.code.push_back(sl);
+      } else if (m.opc == OP_POW5) {
+        al.emit(make_instr(OP_POW5, e.flags, dsts[u], e.enc[0] | ((m.pos4 == NO_POS ? 0xFFFFu : m.pos4 - m.pos2) << 16), m.pos2, out_inline[u] ? outs[0] : 0));
+        plan.stats.outs += (m.pos2 != NO_POS) + (m.pos4 != NO_POS);
       } else {
         const uint32_t w = m.opc == OP_TERN ? e.enc[2] : (out_inline[u] ? outs[0] : 0);
         al.emit(make_instr(m.opc, e.flags, dsts[u], e.enc[0], e.enc[1], w));

@@ -26,6 +26,7 @@ struct PlanOptions {
   bool fuse_dot = true;      // fuse linear combinations into OP_DOT
   uint32_t max_terms = 8;    // max terms of one OP_DOT (<= DOT_MAX_TERMS, <= n_regs - 3)
   bool narrow = true;        // narrow typing: provably small values are computed on int64 (isa.h: F_NARROW)
+  bool fuse_pow5 = true;     // Sqr -> Sqr -> Mul S-box chains become one OP_POW5 (throughput plan)
   bool fold_addc = false;    // Mul(constant, value +- constant) -> OP_DOT terms that do not wait for the Add (latency mode)
 };
 
@@ -40,6 +41,7 @@ struct PlanStats {
   uint64_t mul_nodes = 0;                    // live Mul nodes of the graph
   uint32_t max_live = 0;                     // peak number of simultaneously live values
   uint64_t narrow_instrs = 0;                // emitted narrow (int64) instructions, spill moves excluded
+  uint64_t pow5 = 0;                         // S-box chains fused into OP_POW5
 };
 
 struct Plan {

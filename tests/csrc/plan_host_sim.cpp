@@ -22,7 +22,7 @@ static fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 
 extern "C" {
 
-// flags: bit 0 = fuse linear combinations (OP_DOT), bit 1 = narrow typing OFF, bits 8.. = div_batch (0 -> default)
+// flags: bit 0 = fuse linear combinations (OP_DOT), bit 1 = narrow typing OFF, bit 2 = OP_POW5 fusion OFF, bits 8.. = div_batch (0 -> default)
 SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags, char* err, size_t errlen);
 SimGraph* sim_load(const uint8_t* data, size_t len, uint32_t n_regs, char* err, size_t errlen) {
   return sim_load2(data, len, n_regs, 1, err, errlen);
@@ -31,14 +31,14 @@ SimGraph* sim_load2(const uint8_t* data, size_t len, uint32_t n_regs, int flags,
   try {
     std::unique_ptr<SimGraph> s(new SimGraph());
     s->g = deserialize_witnesscalc_graph(data, len);
-    PlanOptions o; o.n_regs = n_regs; o.fuse_dot = (flags & 1) != 0; o.narrow = (flags & 2) == 0;
+    PlanOptions o; o.n_regs = n_regs; o.fuse_dot = (flags & 1) != 0; o.narrow = (flags & 2) == 0; o.fuse_pow5 = (flags & 4) == 0;
     if (flags >> 8) o.div_batch = (uint32_t)(flags >> 8);
     s->plan = compile_plan(s->g, o);
     return s.release();
   } catch (const std::exception& e) { if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; } return nullptr; }
 }
 void sim_free(SimGraph* s) { delete s; }
-void sim_info2(SimGraph* s, uint64_t* out) { out[0] = s->plan.stats.narrow_instrs; out[1] = s->plan.stats.op_count[OP_WIDEN]; out[2] = s->plan.n_spill_narrow; }
+void sim_info2(SimGraph* s, uint64_t* out) { out[0] = s->plan.stats.narrow_instrs; out[1] = s->plan.stats.op_count[OP_WIDEN]; out[2] = s->plan.n_spill_narrow; out[3] = s->plan.stats.pow5; }
 void sim_info(SimGraph* s, uint64_t* out) {
   const PlanStats& st = s->plan.stats;
   out[0] = s->g.nodes.size(); out[1] = s->plan.n_inputs; out[2] = s->plan.n_witness; out[3] = st.instrs;
@@ -147,6 +147,15 @@ int64_t sim_eval(SimGraph* s, const uint8_t* inputs, uint8_t* witness) {
     if (op == OP_NOP) continue;
     if (ins.x & F_NARROW) { if (!narrow_step(ins, &p.code[pc - len + 1])) return -1; continue; }
     if (op == OP_SPILL_ST) { if (ins.y >= p.n_regs || ins.z >= p.n_spill) return -1; spill[ins.z] = rf[ins.y]; continue; }
+    if (op == OP_POW5) {
+      const uint32_t reg = ins.y & 0xFFFF, d4 = ins.y >> 16;
+      if (reg >= p.n_regs) return -1;
+      const fe x2 = fe_sqr(rf[reg]), x4 = fe_sqr(x2), x5 = fe_mul(x4, rf[reg]);
+      if (ins.z != NO_POS) { if (ins.z >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)ins.z, x2.l, 32); }
+      if (d4 != 0xFFFF) { if (ins.z == NO_POS || ins.z + d4 >= p.n_witness) return -1; memcpy(witness + 32 * (size_t)(ins.z + d4), x4.l, 32); }
+      if (!commit(ins, x5)) return -1;
+      continue;
+    }
     fe R;
     if (!compute(ins, &p.code[pc - len + 1], &R) || !commit(ins, R)) return -1;
   }

@@ -156,6 +156,14 @@ def test_multi_gpu_shards_host_api(cwc):
     for b in sorted({0, B // n - 1, min(B // n, B - 1), B - 1}):
         assert util.unpack_u256(many[b].tobytes()) == po.evaluate(nodes, util.limbs_to_ints(vals[b]), wit)
     print(f"sharded over {n} GPU(s)")
+    # gw_calc_witness_batch_on: the same call on an explicit device range (one process per GPU passes its own device)
+    out = np.empty_like(one)
+    g.calc_witness_batch_ptr(inp.ctypes.data, B, out.ctypes.data, n_gpus=1, first_device=n - 1)
+    assert (out == one).all()
+    with pytest.raises(cwc.WitnessCalcError, match="device range"):
+        g.calc_witness_batch_ptr(inp.ctypes.data, B, out.ctypes.data, n_gpus=1, first_device=n)
+    with pytest.raises(cwc.WitnessCalcError, match="exceeds"):
+        g.calc_witness_batch(inp, n_gpus=n + 1)
 
 
 def test_batch_wtns_framing_select_and_batch_cli(cwc, tmp_path):

@@ -250,3 +250,39 @@ def test_narrow_range_limits():
         assert g.info["narrow_instrs"] > 0
         for x, y in [(mask, mask), (0, mask), (mask, 0), (0, 0), (1, mask), (M - 1, M - 2), ((1 << 256) - 1, 12345), (mask + 1, mask >> 1)]:
             assert g.eval([1, x, y])[0] == po.evaluate(nodes, [1, x, y], wit, "circom"), (bits, x, y)
+
+
+def test_pow5_sbox_fusion():
+    """Sqr -> Sqr -> Mul(., x) chains (Poseidon S-box) become one OP_POW5 when the intermediates have a single reader and
+    their witness positions are encodable; every other shape stays three instructions.  Values are bit-exact either way."""
+    rnd = random.Random(55)
+    base = [(po.K_INPUT, i) for i in range(3)]
+    a, b, c = 3, 4, 5
+    sbox = [(po.K_DUO, 0, 1, 1), (po.K_DUO, 0, a, a), (po.K_DUO, 0, b, 1)]          # x = input 1
+    cases = [
+        (sbox, [0, a, b, c], 1),                 # in2, in4, out consecutive: fused
+        (sbox, [0, a, c, b], 1),                 # a^4 after a^5: delta 2, fused
+        (sbox, [0, c, b, a], 0),                 # a^4 before a^2: not encodable
+        (sbox, [0, c], 1),                       # intermediates are not witness signals
+        (sbox, [0, a, c], 1),
+        (sbox, [0, b, c], 0),                    # a^4 stored but a^2 not: not encodable
+        (sbox, [0, a, a, b, c], 0),              # a^2 at two positions
+        (sbox + [(po.K_DUO, 2, a, 2)], [0, a, b, c, 6], 0),          # a^2 has a second reader
+        (sbox + [(po.K_DUO, 2, b, 2)], [0, a, b, c, 6], 0),          # a^4 has a second reader
+        ([(po.K_DUO, 0, 1, 1), (po.K_DUO, 0, a, a), (po.K_DUO, 0, b, 2)], [0, a, b, c], 0),   # last factor is not x
+        ([(po.K_DUO, 0, 1, 1), (po.K_DUO, 0, a, a), (po.K_DUO, 0, 1, b)], [0, a, b, c], 1),   # operands swapped
+    ]
+    for extra, wit, want_fused in cases:
+        nodes = base + extra
+        g = util.SimGraph(po.serialize_graph(nodes, wit, {"x": (1, 2)}), 8)
+        assert g.info["pow5"] == want_fused, (wit, extra)
+        g0 = util.SimGraph(po.serialize_graph(nodes, wit, {"x": (1, 2)}), 8, pow5=False)
+        assert g0.info["pow5"] == 0
+        for _ in range(3):
+            inp = [1, util.random_value(rnd), rnd.randrange(1 << 256)]
+            want = po.evaluate(nodes, inp, wit, "circom")
+            assert g.eval(inp)[0] == want and g0.eval(inp)[0] == want
+    # the golden Poseidon graphs are where it matters
+    for name, n in (("circuit5_poseidon", 71), ("poseidon2", None)):
+        g = util.SimGraph(util.golden_graph(name), 12)
+        assert g.info["pow5"] == n if n is not None else g.info["pow5"] > 0

@@ -173,10 +173,10 @@ def sim_lib():
 class SimGraph:
     """ctypes wrapper over tests/csrc/plan_host_sim.cpp"""
 
-    def __init__(self, data: bytes, n_regs=24, fuse=True, div_batch=0, narrow=True):
+    def __init__(self, data: bytes, n_regs=24, fuse=True, div_batch=0, narrow=True, pow5=True):
         self.L = sim_lib()
         err = ctypes.create_string_buffer(512)
-        self.h = self.L.sim_load2(data, len(data), n_regs, int(bool(fuse)) | (0 if narrow else 2) | (int(div_batch) << 8), err, 512)
+        self.h = self.L.sim_load2(data, len(data), n_regs, int(bool(fuse)) | (0 if narrow else 2) | (0 if pow5 else 4) | (int(div_batch) << 8), err, 512)
         if not self.h:
             raise ValueError(err.value.decode())
         info = (ctypes.c_uint64 * 19)()
@@ -184,9 +184,10 @@ class SimGraph:
         keys = ["n_nodes", "I", "W", "n_instrs", "n_regs", "n_spill", "spill_ld", "spill_st", "max_live", "n_consts",
                 "live_ops", "graph_ops", "n_dot", "n_dot_mac", "inversions", "div_nodes", "slots", "n_mul", "n_addsub"]
         self.info = dict(zip(keys, [int(x) for x in info]))
-        info2 = (ctypes.c_uint64 * 3)()
+        info2 = (ctypes.c_uint64 * 4)()
         self.L.sim_info2(self.h, info2)
         self.info["narrow_instrs"], self.info["widen"], self.info["n_spill_narrow"] = int(info2[0]), int(info2[1]), int(info2[2])
+        self.info["pow5"] = int(info2[3])
 
     def eval(self, inputs):
         """inputs: list of I ints -> (witness list, status bits)"""
