@@ -341,6 +341,15 @@ __device__ __forceinline__ void lat_exec(const LatCtx& cx, uint32_t pk_s, const 
   } else if (op == OP_MUL || op == OP_SQR) {
     const fe A = operand(ins.x & F_A_CONST, ins.y);
     R = (op == OP_SQR) ? fe_sqr(A) : fe_mul(A, operand(ins.x & F_B_CONST, ins.z));
+  } else if (op == OP_POW5) {
+    // Poseidon S-box in one instruction: one fetch, x^2 and x^4 go straight to their witness positions (isa.h)
+    const fe A = slot_load(ins.y & 0xFFFFu);
+    const uint32_t d4 = ins.y >> 16;
+    const fe x2 = fe_sqr(A);
+    if (ins.z != NO_POS) { cx.out[2 * (size_t)ins.z] = fe_lo(x2); cx.out[2 * (size_t)ins.z + 1] = fe_hi(x2); }
+    const fe x4 = fe_sqr(x2);
+    if (d4 != 0xFFFFu) { cx.out[2 * (size_t)(ins.z + d4)] = fe_lo(x4); cx.out[2 * (size_t)(ins.z + d4) + 1] = fe_hi(x4); }
+    R = fe_mul(x4, A);
   } else if (op == OP_ADD || op == OP_SUB) {
     const fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
     R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);

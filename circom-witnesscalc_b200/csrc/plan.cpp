@@ -545,6 +545,44 @@ void build_macro_program(const Graph& g0, const PlanOptions& opt, PlanStats& sta
 
 }
 
+// Poseidon S-box: Sqr(x) -> Sqr(.) -> Mul(., x) with single-reader intermediates becomes ONE OP_POW5: x stays in
+// registers, x^2 and x^4 go straight to their witness positions and never enter the register file / slot file.
+// Returns the number of fused chains.
+uint64_t fuse_pow5(MacroProgram& mp) {
+  const size_t N = mp.g.nodes.size();
+  const std::vector<uint32_t>& out_start = mp.out_start; const std::vector<uint32_t>& out_list = mp.out_list;
+  auto n_out = [&](uint32_t i) { return out_start[i + 1] - out_start[i]; };
+  uint64_t n_fused = 0;
+  std::vector<uint32_t> readers(N, 0);
+  for (const MOp& m : mp.mops) {
+    if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) readers[t.node]++; }
+    else for (int k = 0; k < m.n_in; k++) if (!mp.is_const[m.in[k]] && (k == 0 || m.in[k] != m.in[0]) && (k < 2 || m.in[k] != m.in[1])) readers[m.in[k]]++;   // distinct operands
+  }
+  std::vector<MOp> fused; fused.reserve(mp.mops.size());
+  for (size_t q = 0; q < mp.mops.size(); q++) {
+    const MOp& a = mp.mops[q];
+    if (q + 2 < mp.mops.size() && a.opc == OP_SQR && !a.narrow && !mp.is_const[a.in[0]]) {
+      const MOp& b = mp.mops[q + 1]; const MOp& c = mp.mops[q + 2];
+      const bool chain = b.opc == OP_SQR && !b.narrow && b.in[0] == a.node && c.opc == OP_MUL && !c.narrow &&
+                         ((c.in[0] == b.node && c.in[1] == a.in[0]) || (c.in[1] == b.node && c.in[0] == a.in[0])) &&
+                         readers[a.node] == 1 && readers[b.node] == 1 && n_out(a.node) <= 1 && n_out(b.node) <= 1;
+      const uint32_t p2 = chain && n_out(a.node) ? out_list[out_start[a.node]] : NO_POS, p4 = chain && n_out(b.node) ? out_list[out_start[b.node]] : NO_POS;
+      // the position of a^4 is encoded relative to that of a^2 (circom numbers in2, in4 consecutively)
+      if (chain && (p4 == NO_POS || (p2 != NO_POS && p4 >= p2 && p4 - p2 < 0xFFFFu))) {
+        MOp f = c; f.opc = OP_POW5; f.n_in = 1; f.in[0] = a.in[0];
+        f.pos2 = p2; f.pos4 = p4;
+        fused.push_back(f);
+        n_fused++;
+        q += 2;
+        continue;
+      }
+    }
+    fused.push_back(a);
+  }
+  mp.mops.swap(fused);
+  return n_fused;
+}
+
 }  // namespace
 
 Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
@@ -564,37 +602,7 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
   const std::vector<uint32_t>& out_start = mp.out_start;
   const std::vector<uint32_t>& out_list = mp.out_list;
   auto n_out = [&](uint32_t i) { return out_start[i + 1] - out_start[i]; };
-  // Poseidon S-box: Sqr(x) -> Sqr(.) -> Mul(., x) with single-reader intermediates becomes ONE OP_POW5: x stays in
-  // registers, x^2 and x^4 go straight to their witness positions and never enter the register file
-  if (opt.fuse_pow5) {
-    std::vector<uint32_t> readers(N, 0);
-    for (const MOp& m : mp.mops) {
-      if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) readers[t.node]++; }
-      else for (int k = 0; k < m.n_in; k++) if (!mp.is_const[m.in[k]] && (k == 0 || m.in[k] != m.in[0]) && (k < 2 || m.in[k] != m.in[1])) readers[m.in[k]]++;   // distinct operands
-    }
-    std::vector<MOp> fused; fused.reserve(mp.mops.size());
-    for (size_t q = 0; q < mp.mops.size(); q++) {
-      const MOp& a = mp.mops[q];
-      if (q + 2 < mp.mops.size() && a.opc == OP_SQR && !a.narrow && !mp.is_const[a.in[0]]) {
-        const MOp& b = mp.mops[q + 1]; const MOp& c = mp.mops[q + 2];
-        const bool chain = b.opc == OP_SQR && !b.narrow && b.in[0] == a.node && c.opc == OP_MUL && !c.narrow &&
-                           ((c.in[0] == b.node && c.in[1] == a.in[0]) || (c.in[1] == b.node && c.in[0] == a.in[0])) &&
-                           readers[a.node] == 1 && readers[b.node] == 1 && n_out(a.node) <= 1 && n_out(b.node) <= 1;
-        const uint32_t p2 = chain && n_out(a.node) ? out_list[out_start[a.node]] : NO_POS, p4 = chain && n_out(b.node) ? out_list[out_start[b.node]] : NO_POS;
-        // the position of a^4 is encoded relative to that of a^2 (circom numbers in2, in4 consecutively)
-        if (chain && (p4 == NO_POS || (p2 != NO_POS && p4 >= p2 && p4 - p2 < 0xFFFFu))) {
-          MOp f = c; f.opc = OP_POW5; f.n_in = 1; f.in[0] = a.in[0];
-          f.pos2 = p2; f.pos4 = p4;
-          fused.push_back(f);
-          plan.stats.pow5++;
-          q += 2;
-          continue;
-        }
-      }
-      fused.push_back(a);
-    }
-    mp.mops.swap(fused);
-  }
+  if (opt.fuse_pow5) plan.stats.pow5 = fuse_pow5(mp);
   const std::vector<MOp>& mops = mp.mops;
   auto nconst_of = [&](const U256& c, bool neg) {       // int64 table form of a small signed constant
     int64_t v = 0;
@@ -790,6 +798,7 @@ struct LOp {
   bool has_out = false; uint32_t out_pos = 0;  // inline witness store (F_OUT), or the position of an OP_OUT
   bool slow = false;
   int32_t chain_prev = -1, chain_next = -1;    // a chain runs in ONE lane, back to back, inside one level
+  uint32_t pos2 = NO_POS, pos4 = NO_POS;       // OP_POW5
 };
 
 inline bool lat_is_slow(uint32_t opc) { return opc == OP_DIV || opc == OP_INV || opc == OP_POW || opc == OP_IDIV || opc == OP_MOD; }
@@ -802,6 +811,7 @@ uint32_t lat_cost(const LOp& o) {
   switch (o.opc) {
     case OP_MUL: return 1100 + around;
     case OP_SQR: return 950 + around;
+    case OP_POW5: return 950 + 950 + 1100 + around + 100;
     case OP_DOT: {
       uint32_t c = 1500;
       for (const PTerm& t : o.terms) c += t.kind == 0 ? 800u : 100u;
@@ -838,6 +848,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
   PlanStats pst;
   MacroProgram mp;
   build_macro_program(g0, po, pst, mp);
+  if (lo.fuse) fuse_pow5(mp);
   const Graph& g = mp.g;
   const size_t N = g.nodes.size();
   const std::vector<uint8_t>& is_const = mp.is_const;
@@ -889,20 +900,21 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
     std::vector<int32_t> def_op(N, -1);
     for (const MOp& m : mp.mops) {
       LOp o; o.opc = m.opc; o.val = m.node; o.n_in = m.n_in; o.shift = m.shift; o.mask = m.mask; o.ncs = m.ncs;
+      o.pos2 = m.pos2; o.pos4 = m.pos4;
       for (int k = 0; k < m.n_in; k++) o.in[k] = m.in[k];
       if (m.opc == OP_INPUT) o.input = g.nodes[m.node].a;
       uint32_t lv = 0;
       // chain candidate: the single newest operand, produced one level earlier by an ordinary instruction that nobody else reads
       int32_t chain_to = -1;
       // (only multiplication-class instructions: a chain of cheap ones would serialise what the lanes of a warp run in parallel)
-      if (use_chain && (m.opc == OP_MUL || m.opc == OP_SQR || m.opc == OP_DOT)) {
+      if (use_chain && (m.opc == OP_MUL || m.opc == OP_SQR || m.opc == OP_DOT || m.opc == OP_POW5)) {
         uint32_t newest = 0xFFFFFFFFu, amax = 0, n_at_max = 0;
         auto look = [&](uint32_t v) { if (avail[v] > amax) { amax = avail[v]; newest = v; n_at_max = 1; } else if (avail[v] == amax && v != newest) n_at_max++; };
         if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) look(t.node); }
         else for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]]) look(m.in[k]);
         if (amax > 0 && n_at_max == 1 && newest < N && def_op[newest] >= 0 && n_readers[newest] == 1) {
           const LOp& pr = ops[(size_t)def_op[newest]];
-          bool ok = (pr.opc == OP_MUL || pr.opc == OP_SQR || pr.opc == OP_DOT) && pr.level + 1 == amax && chain_len[chain_head[(size_t)def_op[newest]]] < lo.max_chain &&
+          bool ok = (pr.opc == OP_MUL || pr.opc == OP_SQR || pr.opc == OP_DOT || pr.opc == OP_POW5) && pr.level + 1 == amax && chain_len[chain_head[(size_t)def_op[newest]]] < lo.max_chain &&
                     1 + chain_slots[chain_head[(size_t)def_op[newest]]] + mop_slots(m) <= lo.packet_slots;     // a chain lives in one packet
           auto older = [&](uint32_t v) { if (v != newest && avail[v] > pr.level) ok = false; };
           if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) older(t.node); }
@@ -1018,6 +1030,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
         return make_instr(OP_OUT, 0, NO_DST, slot(o.in[0]), 0, o.out_pos);
       }
       if (o.opc == OP_SHRAND) return make_instr(OP_SHRAND, flags, dst, slot(o.in[0]), o.shift | (inline_const(o.mask) << 8), o.out_pos);
+      if (o.opc == OP_POW5) return make_instr(OP_POW5, flags, dst, slot(o.in[0]) | ((o.pos4 == NO_POS ? 0xFFFFu : o.pos4 - o.pos2) << 16), o.pos2, o.out_pos);
       if (o.opc == OP_DOT) {
         // terms ordered by kind so that the lanes of a warp walk the same code path
         std::vector<PTerm> ts = o.terms;
@@ -1057,7 +1070,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       const uint32_t op = h.x & 0xFFu;
       if (op == OP_DOT) { h.z += rb; return h; }
       if (op == OP_SHRAND) { h.z = (h.z & 0xFFu) | (((h.z >> 8) + rb) << 8); return h; }
-      if (op == OP_INPUT) return h;
+      if (op == OP_INPUT || op == OP_POW5) return h;
       if (h.x & F_A_CONST) h.y += rb;
       if ((h.x & F_B_CONST) && op_has_b_host(op)) h.z += rb;
       if ((h.x & F_C_CONST) && op == OP_TERN) h.w += rb;

@@ -226,6 +226,13 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
         dot_term(P, kind, rslot(reg), c);
       }
       R = fe_mont_reduce(P, (int)ncs);
+    } else if (op == OP_POW5) {
+      const uint32_t reg = ins.y & 0xFFFF, d4 = ins.y >> 16;
+      if (reg >= lp.n_slots) return false;
+      const fe x = rslot(reg), x2 = fe_sqr(x), x4 = fe_sqr(x2);
+      if (ins.z != NO_POS) { if (ins.z >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.z, x2.l, 32); }
+      if (d4 != 0xFFFF) { if (ins.z == NO_POS || ins.z + d4 >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)(ins.z + d4), x4.l, 32); }
+      R = fe_mul(x4, x);
     } else if (op == OP_SHRAND) {
       fe c;
       if (ins.y >= lp.n_slots || !pconst(pk, ins.z >> 8, &c)) return false;
