@@ -130,6 +130,24 @@ def test_latency_mode_random_graphs_and_golden(cwc, monkeypatch, env):
         print(f"latency mode {name} {env}: {ms:.2f} ms kernel")
 
 
+def test_poseidon_like_graphs_batch_and_latency(cwc):
+    """random graphs with Poseidon's shapes (OP_POW5, straight-line OP_DOT shapes, chains, divisions) on the device:
+    a small batch through the throughput kernel and single witnesses through the latency kernel"""
+    for seed in range(24):
+        rnd = random.Random(5000 + seed)
+        nodes, wit, imap = util.poseidon_like_graph(rnd, rnd.choice([2, 3, 5]), rnd.choice([3, 8, 20]))
+        g = cwc.Graph(po.serialize_graph(nodes, wit, imap))
+        rows = [[1] + [util.random_value(rnd) if rnd.random() < 0.8 else rnd.randrange(1 << 256) for _ in range(6)] for _ in range(5)]
+        inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(len(rows), 7, 32)
+        out = g.calc_witness_batch(inp)
+        for b, row in enumerate(rows):
+            want = po.evaluate(nodes, row, wit, "circom")
+            assert util.unpack_u256(out[b].tobytes()) == want, (seed, b)
+            if b < 2:
+                lat, _ = g.calc_witness_latency(inp[b])
+                assert util.unpack_u256(lat.tobytes()) == want, (seed, b, "latency")
+
+
 def test_single_witness_through_batch_kernel(cwc, monkeypatch):
     monkeypatch.setenv("GW_SINGLE_MODE", "batch")
     for name in ("circuit2", "circuit5_poseidon", "circuit9_authV2"):

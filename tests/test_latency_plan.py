@@ -97,3 +97,16 @@ def test_golden_circuits(name):
         assert 2 * info["n_levels"] < g.eval_latency(buf, fuse=False, chain=False)[1]["n_levels"]
     if name == "circuit8_sha256_512":
         assert info["n_chained"] == 0                             # the cost model keeps lane parallelism for bit-level graphs
+
+
+def test_poseidon_like_graphs():
+    """random graphs with Poseidon's shapes (tests/util.py: poseidon_like_graph): OP_POW5, the straight-line OP_DOT shapes,
+    Mul(const, x + c) folding, chains, split linear combinations, divisions on the slow warps"""
+    for seed in range(120):
+        rnd = random.Random(3000 + seed)
+        nodes, wit, imap = util.poseidon_like_graph(rnd, rnd.choice([2, 3, 5]), rnd.choice([3, 8, 20]))
+        g = util.SimGraph(po.serialize_graph(nodes, wit, imap), 12)
+        row = _rows(rnd, 6, 1)[0]
+        want = po.evaluate(nodes, row, wit, "circom")
+        for mode in (0, 1):
+            assert g.eval_latency(row, mode=mode, **VARIANTS[seed % len(VARIANTS)])[0] == want, (seed, mode)

@@ -286,3 +286,14 @@ def test_pow5_sbox_fusion():
     for name, n in (("circuit5_poseidon", 71), ("poseidon2", None)):
         g = util.SimGraph(util.golden_graph(name), 12)
         assert g.info["pow5"] == n if n is not None else g.info["pow5"] > 0
+
+
+def test_poseidon_like_graphs():
+    """random graphs with Poseidon's shapes through the throughput plan: S-box fusion in every operand / witness order"""
+    fused = 0
+    for seed in range(150):
+        rnd = random.Random(4000 + seed)
+        nodes, wit, imap = util.poseidon_like_graph(rnd, rnd.choice([2, 3, 5]), rnd.choice([3, 8, 20]))
+        g = _check(nodes, wit, imap, rnd.choice([6, 8, 12, 24]), rnd, n_rows=2)
+        fused += g.info["pow5"]
+    assert fused > 100

@@ -119,6 +119,63 @@ def random_graph(rnd: random.Random, n_inputs=6, n_ops=200, ops=None, n_consts=1
     return nodes, wit, {"x": (1, n_inputs)}
 
 
+def poseidon_like_graph(rnd: random.Random, t=3, rounds=8, n_inputs=6):
+    """Random graph with the shapes of circomlib's Poseidon (poseidon.circom: Ark, Sigma, Mix, MixS) and an occasional
+    division: S-box chains x^2, x^4, x^5 (operand order and witness order varied), `lc += c * in[j]` sums,
+    `in[i] + in[0] * c` updates, constants added before the S-box.  Exercises OP_POW5, the OP_DOT shapes, the
+    Mul(const, x + c) folding, lane chains and split linear combinations.  Returns (nodes, witness_signals, input_map)."""
+    nodes = [(po.K_INPUT, i) for i in range(n_inputs + 1)]
+
+    def const(v):
+        nodes.append((po.K_CONST, v))
+        return len(nodes) - 1
+
+    def duo(op, a, b):
+        nodes.append((po.K_DUO, po.DUO[op], a, b))
+        return len(nodes) - 1
+
+    st = [1 + rnd.randrange(n_inputs) for _ in range(t)]
+    wit = [0]
+    for _ in range(rounds):
+        full = rnd.random() < 0.3
+        st = [duo("Add", s, const(rnd.randrange(M))) if rnd.random() < 0.8 else s for s in st]
+        for j in range(t if full else 1):
+            x = st[j]
+            x2 = duo("Mul", x, x)
+            x4 = duo("Mul", x2, x2)
+            x5 = duo("Mul", x4, x) if rnd.random() < 0.8 else duo("Mul", x, x4)
+            outs = [x2, x4, x5]
+            if rnd.random() < 0.3:
+                rnd.shuffle(outs)
+            wit += [o for o in outs if rnd.random() < 0.9]
+            st[j] = x5
+        new = []
+        if full or rnd.random() < 0.3:
+            for _i in range(t):
+                lc = None
+                for j in range(t):
+                    c = const(rnd.randrange(M))
+                    term = duo("Mul", c, st[j]) if rnd.random() < 0.5 else duo("Mul", st[j], c)
+                    lc = term if lc is None else duo("Add", lc, term)
+                new.append(lc)
+        else:
+            lc = None
+            for j in range(t):
+                term = duo("Mul", const(rnd.randrange(M)), st[j])
+                lc = term if lc is None else duo("Add", lc, term)
+            new.append(lc)
+            for i in range(1, t):
+                new.append(duo("Add" if rnd.random() < 0.8 else "Sub", st[i], duo("Mul", st[0], const(rnd.randrange(M)))))
+        st = new
+        wit += [s for s in st if rnd.random() < 0.8]
+        if rnd.random() < 0.15:
+            d = duo("Div", st[0], st[-1])
+            wit.append(d)
+            st[0] = d
+    wit += st
+    return nodes, wit, {"x": (1, n_inputs)}
+
+
 # ---- test-only host libraries -------------------------------------------------------------------------
 def _build(name, sources, extra=()):
     os.makedirs(BUILD, exist_ok=True)
