@@ -261,6 +261,7 @@ struct LParams {
 
 static const int LAT_MAX_THREADS = 384;     // main + control + slow warps <= 12: 170 registers per thread
 static const uint32_t LAT_RING_SLOTS = 128; // packet ring: 3 stages x 2 KB per main warp (plan.hpp: LatencyOptions::packet_slots)
+static const uint32_t LAT_CTRL_BYTES = 320; // 32 B control words (levels, job counters) + 3 mbarriers x up to 11 main warps, 16 B aligned
 
 // Shared memory is addressed with 32-bit shared-window addresses and explicit ld/st.shared: a generic pointer costs a
 // window lookup (S2R) per access in this kernel's dependent chains.
@@ -379,55 +380,74 @@ __device__ __forceinline__ void lat_exec_slow(const LatCtx& cx, const uint4* pk,
   if ((ins.x & F_OUT) && op != OP_TERN) { cx.out[2 * (size_t)ins.w] = fe_lo(R); cx.out[2 * (size_t)ins.w + 1] = fe_hi(R); }
 }
 
-// Dynamic shared memory: [2 uint4 control words][n_slots][2] value file | [n_warps][3][LAT_RING_SLOTS] packet rings
+// Dynamic shared memory: [LAT_CTRL_BYTES: control words + mbarriers][n_slots][2] value file | [n_warps][3][LAT_RING_SLOTS] packet rings
 __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LParams p) {
   extern __shared__ uint4 lat_smem[];
   volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(lat_smem);   // [0] = completed levels, [1 + w] = jobs done by slow warp w
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(lat_smem);
   if (tid < 8) ctrl[tid] = 0;
+  if (tid < 3u * p.n_warps) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_s + 32u + 8u * tid) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   uint32_t st = 0;
-  const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(lat_smem);
   LatCtx cx;
-  cx.inputs = p.inputs; cx.out = p.out; cx.slots_s = smem_s + 32u; cx.dbg = p.dbg;
+  cx.inputs = p.inputs; cx.out = p.out; cx.slots_s = smem_s + LAT_CTRL_BYTES; cx.dbg = p.dbg;
 
+  // Packets reach the rings by TMA: ONE bulk copy (cp.async.bulk) per packet, issued by the CONTROL warp (lane w serves
+  // main warp w), completing on the mbarrier of the ring stage; the main warps only wait for their barrier, so neither
+  // the descriptor walk nor the copy issue is on the path of the warp that holds a level up.
+  const uint32_t bar0_s = smem_s + 32u;                          // mbarriers: [main warp][stage], 8 bytes each
+  const uint32_t ring0_s = cx.slots_s + 32u * p.n_slots;         // rings: [main warp][stage][LAT_RING_SLOTS]
+  auto wait_stage = [&](uint32_t w, uint32_t stage, uint32_t parity) {
+    const uint32_t bar = bar0_s + 8u * (3u * w + stage);
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  };
   if (warp < p.n_warps) {
     const uint32_t nl = p.n_levels;
     const uint32_t bar_threads = (p.n_warps + 1u) * 32u;        // the control warp joins every level barrier
-    const uint32_t ring_s = cx.slots_s + 32u * p.n_slots + warp * (3u * LAT_RING_SLOTS * 16u);
-    // a packet {offset, slots, headers, lanes} -> ring stage: asynchronous 16-byte copies, lane-strided
-    auto fetch = [&](const uint4 info, uint32_t stage) {
-      uint32_t d = ring_s + (stage * LAT_RING_SLOTS + lane) * 16u;
-      const uint4* g = p.code + info.x + lane;
-      for (uint32_t k = lane; k < info.y; k += 32, d += 512u, g += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
+    const uint32_t ring_s = ring0_s + warp * (3u * LAT_RING_SLOTS * 16u);
     uint4 cur = __ldg(p.first + 2 * warp), nxt = __ldg(p.first + 2 * warp + 1);
-    fetch(cur, 0);
-    fetch(nxt, 1);
-    uint32_t stage = 0;
+    uint32_t stage = 0, parity = 0;                  // parity of the stage's current use: flips every third level
     for (uint32_t L = 0; L < nl; L++) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");        // this level's packet has landed (the next one may be in flight)
-      __syncwarp();
+      wait_stage(warp, stage, parity);                             // this level's packet has landed
       const uint32_t pk_s = ring_s + stage * (LAT_RING_SLOTS * 16u);
-      const uint4 desc = lds128(pk_s);                             // names the packet two levels ahead
-      fetch(desc, stage == 0 ? 2u : stage - 1u);                   // stage + 2 mod 3
+      const uint4 desc = lds128(pk_s);                             // {offset, slots, headers, lanes} of the packet two levels ahead
       // header k belongs to lane k mod cur.w; a lane runs its headers in order (a chain: program order, no barrier)
       if (!(p.dbg & 16u) && lane < cur.w) for (uint32_t i = lane; i < cur.z; i += cur.w) lat_exec(cx, pk_s, lds128(pk_s + 16u * (1u + i)), &st);
       __syncwarp();
       asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
       cur = nxt; nxt = desc;
-      stage = stage == 2 ? 0u : stage + 1u;
+      if (stage == 2) { stage = 0; parity ^= 1u; } else stage++;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == p.n_warps) {
-    // control warp: before the barrier that ends level L it waits for the slow-warp jobs whose readers start at level
-    // L + 1; after the barrier it publishes that L + 1 levels are complete (slow-warp jobs issued at <= L + 1 may start)
+    // control warp.  Per level L: (1) lane w reads the descriptor of main warp w's packet L and starts the copy of its
+    // packet L + 2 into the stage that level L - 1 used; (2) it waits for the slow-warp jobs whose readers start at
+    // level L + 1; (3) it joins the barrier that ends the level and publishes that L + 1 levels are complete.
     const uint32_t nl = p.n_levels, bar_threads = (p.n_warps + 1u) * 32u;
+    const bool serve = lane < p.n_warps;
+    const uint32_t ring_s = ring0_s + lane * (3u * LAT_RING_SLOTS * 16u);
+    auto fetch = [&](const uint4 info, uint32_t stage) {
+      const uint32_t bytes = info.y * 16u, bar = bar0_s + 8u * (3u * lane + stage), d = ring_s + stage * (LAT_RING_SLOTS * 16u);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // earlier generic reads of the stage vs the async write
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      if (bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d), "l"(p.code + info.x), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (serve) { fetch(__ldg(p.first + 2 * lane), 0); fetch(__ldg(p.first + 2 * lane + 1), 1); }
+    uint32_t stage = 0, parity = 0;
     uint32_t wi = 0;
     uint4 nw = p.n_waits ? __ldg(p.waits) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
     for (uint32_t L = 0; L < nl; L++) {
+      if (serve) {
+        wait_stage(lane, stage, parity);
+        const uint4 desc = lds128(ring_s + stage * (LAT_RING_SLOTS * 16u));
+        fetch(desc, stage == 0 ? 2u : stage - 1u);               // stage + 2 mod 3: free since the barrier that ended level L - 1
+      }
+      __syncwarp();
       while (nw.x == L) {
         while (ctrl[1 + nw.y] < nw.z) __nanosleep(40);
         wi++;
@@ -437,6 +457,7 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
       asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
       __threadfence_block();
       if (lane == 0) { ctrl[0] = L + 1; if (p.level_clock) p.level_clock[L] = clock64(); }
+      if (stage == 2) { stage = 0; parity ^= 1u; } else stage++;
     }
   } else if (warp - p.n_warps - 1u < p.n_slow) {
     const uint32_t ws = warp - p.n_warps - 1u;
@@ -750,7 +771,7 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
       LatencyOptions lo;
       lo.n_warps = (uint32_t)env_int("GW_LAT_WARPS", (int)lo.n_warps);
       lo.packet_slots = LAT_RING_SLOTS;
-      lo.max_slots = (uint32_t)std::min<size_t>((prop.sharedMemPerBlockOptin / 16 - 2 - (size_t)lo.n_warps * 3 * LAT_RING_SLOTS) / 2, 0xFFFF);
+      lo.max_slots = (uint32_t)std::min<size_t>((prop.sharedMemPerBlockOptin / 16 - LAT_CTRL_BYTES / 16 - (size_t)lo.n_warps * 3 * LAT_RING_SLOTS) / 2, 0xFFFF);
       lo.n_slow_warps = (uint32_t)env_int("GW_LAT_SLOW_WARPS", (int)lo.n_slow_warps);
       lo.slow_levels = (uint32_t)env_int("GW_LAT_D", 0);
       lo.split_dot = env_int("GW_LAT_SPLIT", 1) != 0;
@@ -763,7 +784,7 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
   }
   const LatencyPlan& lp = lat_plan;
   const size_t in_b = (size_t)lp.n_inputs * 32, out_b = std::max<size_t>((size_t)lp.n_witness * 32, 32);
-  const size_t smem = ((size_t)lp.n_slots * 2 + 2 + (size_t)lp.n_warps * 3 * LAT_RING_SLOTS) * 16;
+  const size_t smem = ((size_t)lp.n_slots * 2 + LAT_CTRL_BYTES / 16 + (size_t)lp.n_warps * 3 * LAT_RING_SLOTS) * 16;
   const bool clocks = env_int("GW_LAT_CLOCKS", 0) != 0;
   if (!d->lat_code) {
     CUDA_CHECK(cudaMalloc(&d->lat_code, std::max<size_t>(lp.code.size(), 1) * sizeof(Instr)));
