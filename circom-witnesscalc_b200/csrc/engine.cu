@@ -241,12 +241,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
 
 // ---- single-witness latency mode ------------------------------------------------------------------------
 // One CTA evaluates ONE witness (plan.hpp: LatencyPlan).  MAIN warps run the plan level by level: every lane takes
-// one instruction of the level (instructions of one class share a warp, different classes sit in different warps and
-// therefore on different SM sub-partitions), values live in one shared-memory slot file, a named barrier over the
-// main warps separates levels.  SLOW warps run the long operations (Div/Inv/Pow/Idiv/Mod) asynchronously: a job
-// starts when the main warps have published the level that produces its operands, and its readers sit behind an
-// OP_WAIT on the job counter of that slow warp.  Headers of level L+2, tails/constants of level L+1 are in flight
-// while level L executes.
+// one instruction (or one chain of instructions) of the level -- instructions of one class share a warp, different
+// classes sit in different warps and therefore on different SM sub-partitions -- values live in one shared-memory slot
+// file, a named barrier over the main warps and the control warp separates levels.  SLOW warps run the long operations
+// (Div/Inv/Pow/Idiv/Mod) asynchronously: a job starts when the level that produces its operands has been published,
+// and the CONTROL warp waits for the job counter of that slow warp before it joins the barrier in front of the job's
+// readers.  The control warp also feeds the main warps: the packet (headers, OP_DOT tails, constants) of level L+2
+// lands in a 3-stage shared-memory ring per main warp by TMA while level L executes.
 struct LParams {
   const uint4* code; const uint4* first; uint32_t n_levels, n_warps;
   const uint4* jobs; const uint32_t* n_jobs; uint32_t max_jobs, n_slow;

@@ -981,7 +981,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
     }
     const size_t NV = avail.size();
 
-    // ---- 2. last level that reads each value (a long op may read its operands until its OP_WAIT level) -----
+    // ---- 2. last level that reads each value (a long op may read its operands until the level at which it is waited for) -----
     std::vector<int64_t> last_use(NV, -1);
     auto for_operands = [&](const LOp& o, auto&& fn) {
       if (o.opc == OP_DOT) { for (const PTerm& t : o.terms) if (t.kind != 2) fn(t.node); }

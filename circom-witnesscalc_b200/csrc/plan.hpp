@@ -66,7 +66,7 @@ Plan compile_plan(const Graph& g, const PlanOptions& opt);
 // later, behind a wait on the job's completion counter that a CONTROL warp performs before it joins the barrier of
 // the level in front of them (the control warp also publishes the completed levels: it has no asynchronous copies
 // in flight, so its fences are cheap).  Operands name slots of one shared-memory value file;
-// a slot is recycled only at a level boundary after its last reader (for a slow reader: after its OP_WAIT level).
+// a slot is recycled only at a level boundary after its last reader (for a slow reader: after the level at which the control warp waits for it).
 //
 //   code   : packets.  A packet is what ONE warp needs for ONE level (or one slow-warp job), contiguous: slot 0 =
 //            descriptor {offset, slots, headers, lanes of the same warp's packet two levels later}, then the headers
