@@ -767,6 +767,7 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
   std::lock_guard<std::mutex> lk(d->mu);
   {
     std::lock_guard<std::mutex> lk2(mu);
+    if (!lat_error.empty()) throw Error(lat_error);
     if (!lat_ready) {
       cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
       LatencyOptions lo;
@@ -779,7 +780,8 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
       lo.fuse = env_int("GW_LAT_FUSE", 1) != 0;
       lo.chain = env_int("GW_LAT_CHAIN", 1) != 0;
       if ((lo.n_warps + 1 + lo.n_slow_warps) * 32 > (uint32_t)LAT_MAX_THREADS) throw Error("GW_LAT_WARPS + GW_LAT_SLOW_WARPS must not exceed 11");
-      lat_plan = compile_latency_plan(graph, lo);
+      try { lat_plan = compile_latency_plan(graph, lo); }
+      catch (const Error& e) { lat_error = e.what(); throw; }
       lat_ready = true;
     }
   }

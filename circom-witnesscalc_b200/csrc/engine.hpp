@@ -4,6 +4,7 @@
 #pragma once
 #include <map>
 #include <mutex>
+#include <string>
 
 #include "graph.hpp"
 #include "plan.hpp"
@@ -34,6 +35,7 @@ class Engine {
   void run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms);
   LatencyPlan lat_plan;
   bool lat_ready = false;
+  std::string lat_error;      // why the latency plan could not be built (remembered: the compile is not repeated per call)
 
  private:
   struct Dev;
