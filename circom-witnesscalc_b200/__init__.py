@@ -17,6 +17,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcircom_witnesscalc.so")
 CLI_PATH = os.path.join(_HERE, "bin", "calc-witness")
+CLI_BATCH_PATH = os.path.join(_HERE, "bin", "calc-witness-batch")
+REF_EXAMPLE_PATH = os.path.join(_HERE, "bin", "ref-example-calc-witness")   # reference examples/calc_witness.c, built unchanged
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -62,6 +64,9 @@ _L.gw_wtns_file_size.restype = _sz
 _L.gw_wtns_file_size.argtypes = [_vp]
 _L.gw_calc_witness_batch_wtns.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, ctypes.c_int, ctypes.POINTER(gw_status_t)]
 _L.gw_graph_select.argtypes = [_vp, _vp, _sz, ctypes.POINTER(_vp), ctypes.POINTER(gw_status_t)]
+CHUNK_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, ctypes.c_int, _sz, _sz, _vp, _sz, _vp)
+_L.gw_calc_witness_batch_stream.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _sz, _sz, CHUNK_FN, _vp, ctypes.POINTER(gw_status_t)]
+_L.gw_set_device.argtypes = [ctypes.c_int]
 _L.gw_device_count.restype = ctypes.c_int
 _L.gw_microbench_imad.restype = ctypes.c_double
 _L.gw_microbench_imad.argtypes = [ctypes.c_int, ctypes.c_int]
@@ -69,7 +74,7 @@ _L.gw_microbench_imad.argtypes = [ctypes.c_int, ctypes.c_int]
 EXPORTS = ["gw_calc_witness", "gw_graph_load", "gw_graph_free", "gw_graph_info", "gw_graph_input_signal",
            "gw_graph_calc_witness", "gw_calc_witness_batch", "gw_calc_witness_batch_on", "gw_calc_witness_batch_device", "gw_calc_witness_latency", "gw_wtns_header",
            "gw_device_count", "gw_microbench_imad", "gw_inputs_parse_batch", "gw_wtns_file_size", "gw_calc_witness_batch_wtns",
-           "gw_graph_select"]
+           "gw_graph_select", "gw_calc_witness_batch_stream", "gw_set_device"]
 
 
 class WitnessCalcError(RuntimeError):
@@ -113,6 +118,12 @@ def wtns_from_witness(witness) -> bytes:
     hdr = ctypes.create_string_buffer(76)
     _L.gw_wtns_header(len(witness), hdr)
     return hdr.raw + b"".join(int(v).to_bytes(32, "little") for v in witness)
+
+
+def set_device(device: int):
+    """gw_set_device: CUDA device of the single-witness entry points"""
+    if _L.gw_set_device(device) != 0:
+        raise WitnessCalcError(f"CUDA device {device} does not exist")
 
 
 def device_count() -> int:
@@ -224,23 +235,45 @@ class Graph:
         _check(rc, st)
         return Graph(_handle=h)
 
-    def calc_witness_latency(self, inputs_row: np.ndarray, device=0):
-        """ONE input set uint8 [I, 32] -> (witness uint8 [W, 32], kernel milliseconds): gw_calc_witness_latency."""
+    def calc_witness_latency(self, inputs_row: np.ndarray, device=0, want_flags=False):
+        """ONE input set uint8 [I, 32] -> (witness uint8 [W, 32], kernel milliseconds): gw_calc_witness_latency.
+        want_flags=True returns (witness, flags) instead, flags = the set's reference-undefined bits."""
         inputs_row = np.ascontiguousarray(inputs_row, dtype=np.uint8)
         assert inputs_row.shape == (self.n_inputs, 32), inputs_row.shape
         out = np.empty((self.n_witness, 32), dtype=np.uint8)
         ms = ctypes.c_float(0)
+        fl = ctypes.c_uint32(0)
         st = gw_status_t()
-        rc = _L.gw_calc_witness_latency(self._h, device, inputs_row.ctypes.data, out.ctypes.data, None, ctypes.byref(ms),
-                                        ctypes.byref(st))
+        rc = _L.gw_calc_witness_latency(self._h, device, inputs_row.ctypes.data, out.ctypes.data,
+                                        ctypes.addressof(fl) if want_flags else None, ctypes.byref(ms), ctypes.byref(st))
         _check(rc, st)
-        return out, float(ms.value)
+        return (out, int(fl.value)) if want_flags else (out, float(ms.value))
 
     def calc_witness_batch_ptr(self, inputs_ptr, n_sets, witness_ptr, flags_ptr=None, n_gpus=1, first_device=0):
         """HOST pointers (e.g. pinned torch tensors): no allocation, no copies besides the DMA.  The sets are sharded
         over devices first_device .. first_device + n_gpus - 1 (gw_calc_witness_batch_on)."""
         st = gw_status_t()
         rc = _L.gw_calc_witness_batch_on(self._h, first_device, inputs_ptr, n_sets, witness_ptr, flags_ptr, n_gpus, ctypes.byref(st))
+        _check(rc, st)
+
+    def calc_witness_batch_stream(self, inputs_ptr, n_sets, consumer, n_gpus=1, first_device=0, chunk_sets=0):
+        """gw_calc_witness_batch_stream: HOST input pointer; `consumer(device, first_set, rows, flags)` is called per chunk with
+        rows = uint8 [n, W, 32] and flags = uint32 [n] VIEWS of the library's pinned ring (valid during the call only);
+        a truthy return value stops the stream."""
+        W = self.n_witness
+
+        def tramp(_user, device, first, n, rows, row_bytes, flags):
+            r = np.ctypeslib.as_array(ctypes.cast(rows, ctypes.POINTER(ctypes.c_uint8)), shape=(n, W, 32)) if W else np.empty((n, 0, 32), np.uint8)
+            f = np.ctypeslib.as_array(ctypes.cast(flags, ctypes.POINTER(ctypes.c_uint32)), shape=(n,))
+            try:
+                return 1 if consumer(device, first, r, f) else 0
+            except Exception:          # nothing may unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = CHUNK_FN(tramp)
+        st = gw_status_t()
+        rc = _L.gw_calc_witness_batch_stream(self._h, first_device, n_gpus, inputs_ptr, n_sets, chunk_sets, cb, None, ctypes.byref(st))
         _check(rc, st)
 
     def calc_witness_batch_device(self, device, d_inputs_ptr, n_sets, d_witness_ptr, d_flags_ptr=None, stream=None):

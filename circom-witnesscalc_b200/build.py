@@ -16,6 +16,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libcircom_witnesscalc.so")
 BIN = os.path.join(HERE, "bin", "calc-witness")
 BIN_BATCH = os.path.join(HERE, "bin", "calc-witness-batch")
+# the reference's own C embedding example (examples/calc_witness.c), compiled UNCHANGED from where it lies against this
+# library's header: the acceptance test of the drop-in C ABI.  Only built where /root/reference exists (here, not on the
+# GPU box, which uses the prebuilt binary); no reference source is copied into the repo.
+REF_EXAMPLE_SRC = "/root/reference/examples/calc_witness.c"
+BIN_REF_EXAMPLE = os.path.join(HERE, "bin", "ref-example-calc-witness")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["engine.cu", "graph.cpp", "plan.cpp", "inputs.cpp", "wtns.cpp", "capi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -46,6 +51,16 @@ def build(force=False, verbose=False):
         cmd = ["g++", "-O2", "-std=c++17", "-o", BIN_BATCH, os.path.join(CSRC, "calc_witness_batch_main.cpp"),
                "-L" + os.path.dirname(LIB), "-lcircom_witnesscalc", "-Wl,-rpath,$ORIGIN/../lib"]
         subprocess.check_call(cmd)
+    header = os.path.join(HERE, "..", "include", "graph_witness.h")
+    if os.path.exists(REF_EXAMPLE_SRC) and (force or _newer(BIN_REF_EXAMPLE, [LIB, REF_EXAMPLE_SRC, header])):
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            # the example includes "../include/graph_witness.h": give it OUR header at that relative path
+            os.makedirs(os.path.join(tmp, "examples")); os.makedirs(os.path.join(tmp, "include"))
+            os.symlink(REF_EXAMPLE_SRC, os.path.join(tmp, "examples", "calc_witness.c"))
+            os.symlink(os.path.abspath(header), os.path.join(tmp, "include", "graph_witness.h"))
+            subprocess.check_call(["gcc", "-w", "-o", BIN_REF_EXAMPLE, os.path.join(tmp, "examples", "calc_witness.c"),
+                                   "-L" + os.path.dirname(LIB), "-lcircom_witnesscalc", "-Wl,-rpath,$ORIGIN/../lib"])
     return LIB
 
 

@@ -5,6 +5,7 @@
 
 #include <string.h>
 
+#include <atomic>
 #include <list>
 #include <memory>
 #include <mutex>
@@ -38,10 +39,12 @@ template <typename F> static int guarded(const gw_status_t* status, F&& f) {
   catch (...) { set_status(status, ERROR, "unknown error"); return 1; }
 }
 
+static int single_device();
 static void calc_one(Engine& eng, const char* json, void** wtns_data, size_t* wtns_len) {
   InputList in = deserialize_inputs(json, strlen(json));
   std::vector<U256> buf = build_inputs_buffer(eng.graph, in);
   const uint32_t W = eng.plan.n_witness;
+  const int dev = single_device();
   size_t n = wtns_size(W);
   uint8_t* out = (uint8_t*)malloc(n);
   if (!out) throw Error("Failed to allocate memory for wtns_data");
@@ -50,33 +53,52 @@ static void calc_one(Engine& eng, const char* json, void** wtns_data, size_t* wt
     // a single witness goes through the latency-mode kernel (intra-level node parallelism) unless
     // GW_SINGLE_MODE=batch asks for the throughput kernel with a batch of one
     const char* mode = getenv("GW_SINGLE_MODE");
-    if (mode && !strcmp(mode, "batch")) eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, 0);
+    if (mode && !strcmp(mode, "batch")) eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, dev);
     else {
       // a graph whose live values do not fit the latency kernel's shared-memory value file still gets its witness from
       // the GPU: the throughput kernel with a batch of one
-      try { eng.run_latency(0, (const uint8_t*)buf.data(), out + WTNS_HEADER_BYTES, nullptr, nullptr); }
+      try { eng.run_latency(dev, (const uint8_t*)buf.data(), out + WTNS_HEADER_BYTES, nullptr, nullptr); }
       catch (const Error& e) {
         if (strncmp(e.what(), "latency plan:", 13) != 0) throw;
-        eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, 0);
+        eng.run_host((const uint8_t*)buf.data(), 1, out + WTNS_HEADER_BYTES, nullptr, 1, dev);
       }
     }
   } catch (...) { free(out); throw; }
   *wtns_data = out; *wtns_len = n;
 }
 
-// gw_calc_witness is stateless for the caller; parsed graphs are kept in a small cache keyed by content
+// gw_calc_witness is stateless for the caller; parsed graphs are kept in a small cache keyed by content.  A hit is
+// confirmed by comparing the bytes (the hash only narrows the search), and engines are built outside the lock.
+struct CacheEntry { uint64_t hash; std::vector<uint8_t> bytes; std::shared_ptr<Engine> engine; };
 static std::mutex g_cache_mu;
-static std::list<std::pair<std::pair<uint64_t, size_t>, std::shared_ptr<Engine>>> g_cache;
+static std::list<CacheEntry> g_cache;
 static std::shared_ptr<Engine> cached_engine(const uint8_t* data, size_t len) {
   uint64_t h = 1469598103934665603ull;
   for (size_t i = 0; i < len; i++) { h ^= data[i]; h *= 1099511628211ull; }
+  auto lookup = [&]() -> std::shared_ptr<Engine> {
+    for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+      if (it->hash == h && it->bytes.size() == len && memcmp(it->bytes.data(), data, len) == 0) { g_cache.splice(g_cache.begin(), g_cache, it); return g_cache.front().engine; }
+    return nullptr;
+  };
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (std::shared_ptr<Engine> e = lookup()) return e;
+  }
+  std::shared_ptr<Engine> e(new Engine(data, len));         // parse + plan compilation: other callers are not held up
   std::lock_guard<std::mutex> lk(g_cache_mu);
-  for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
-    if (it->first.first == h && it->first.second == len) { g_cache.splice(g_cache.begin(), g_cache, it); return g_cache.front().second; }
-  std::shared_ptr<Engine> e(new Engine(data, len));
-  g_cache.emplace_front(std::make_pair(h, len), e);
+  if (std::shared_ptr<Engine> other = lookup()) return other;   // somebody else built the same graph meanwhile
+  g_cache.push_front(CacheEntry{h, std::vector<uint8_t>(data, data + len), e});
   if (g_cache.size() > 4) g_cache.pop_back();
   return e;
+}
+
+// device of the single-witness entry points (gw_calc_witness, gw_graph_calc_witness): gw_set_device, else GW_DEVICE, else 0
+static std::atomic<int> g_device{-1};
+static int single_device() {
+  int d = g_device.load();
+  if (d >= 0) return d;
+  const char* s = getenv("GW_DEVICE");
+  return (s && *s) ? atoi(s) : 0;
 }
 
 extern "C" {
@@ -214,6 +236,27 @@ int gw_graph_select(const gw_graph_t* graph, const uint32_t* positions, size_t n
     g->input_names = graph->input_names;
     *selected = g.release();
   });
+}
+
+int gw_calc_witness_batch_stream(gw_graph_t* graph, int first_device, int n_gpus, const uint8_t* inputs, size_t n_sets,
+                                 size_t chunk_sets, gw_witness_chunk_fn fn, void* user, gw_status_t* status) {
+  if (!graph || !fn || (n_sets && !inputs)) { set_status(status, ERROR, "null argument"); return 1; }
+  return guarded(status, [&]() {
+    int ndev = cuda_device_count();
+    if (ndev == 0) throw Error("no CUDA device available: this library has no CPU fallback");
+    if (n_gpus < 1) n_gpus = 1;
+    if (first_device < 0 || first_device + n_gpus > ndev) throw Error("device range exceeds the visible CUDA devices");
+    graph->engine->run_stream(inputs, n_sets, n_gpus, first_device, chunk_sets,
+                              [&](int device, size_t first, size_t n, const uint8_t* rows, size_t row_bytes, const uint32_t* flags) {
+                                return fn(user, device, first, n, rows, row_bytes, flags);
+                              });
+  });
+}
+
+int gw_set_device(int device) {
+  if (device < 0 || device >= cuda_device_count()) return 1;
+  g_device.store(device);
+  return 0;
 }
 
 void gw_wtns_header(uint32_t n_witness, uint8_t* dst76) { wtns_write_header(dst76, n_witness); }

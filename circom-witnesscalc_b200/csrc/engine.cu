@@ -14,9 +14,13 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <thread>
+#include <vector>
 
 #include "engine.hpp"
 #include "alu.cuh"
@@ -36,7 +40,9 @@ struct KParams {
   uint32_t I, W;
   uint32_t n_tiles;
   unsigned long long spill_threads;
-  unsigned long long out_wrap;   // profiling aid (GW_DEBUG_OUT_WRAP): witness rows wrap modulo this many rows; 0 = off
+#ifdef GW_PROFILING
+  unsigned long long out_wrap;   // profiling aid (GW_DEBUG_OUT_WRAP, -DGW_PROFILING builds only): witness rows wrap modulo this many rows; 0 = off
+#endif
 };
 
 __device__ __forceinline__ fe fe_from(uint4 lo, uint4 hi) {
@@ -86,7 +92,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
     const bool active = w < p.B;
     const unsigned long long wl = active ? w : p.B - 1;
     const uint4* in = p.inputs + wl * p.I * 2;
+#ifdef GW_PROFILING
     uint4* out = p.out + (p.out_wrap ? wl % p.out_wrap : wl) * p.W * 2;
+#else
+    uint4* out = p.out + wl * p.W * 2;
+#endif
     uint32_t st = 0;
     auto out_store = [&](uint32_t j, const fe& x) { if (active) { out[2 * (size_t)j] = fe_lo(x); out[2 * (size_t)j + 1] = fe_hi(x); } };
 
@@ -560,11 +570,17 @@ struct Engine::Dev {
   size_t smem_max = 0;
   uint4* code = nullptr; uint4* consts = nullptr;
   uint4* spill = nullptr; size_t spill_threads = 0;
-  // staging for the host-buffer API
+  // every launch of eval_batch_kernel on this device waits for the previous one: they all share the spill area,
+  // whatever stream the caller enqueues them on
+  cudaEvent_t last_kernel = nullptr;
+  // staging for the host-buffer APIs
   cudaStream_t stream[2] = {nullptr, nullptr};
   uint4* d_in[2] = {nullptr, nullptr}; uint4* d_out[2] = {nullptr, nullptr};
   uint32_t* d_status[2] = {nullptr, nullptr};
   size_t chunk = 0;
+  // pinned host ring of the streaming API (three chunks: one in the consumer's hands, one landing, one enqueued)
+  uint8_t* h_ring[3] = {nullptr, nullptr, nullptr}; uint32_t* h_flags[3] = {nullptr, nullptr, nullptr};
+  size_t h_ring_bytes = 0, h_flags_n = 0;
   // single-witness latency mode
   uint4* lat_code = nullptr; uint4* lat_first = nullptr; uint4* lat_jobs = nullptr; uint32_t* lat_njobs = nullptr; uint4* lat_waits = nullptr;
   unsigned long long* lat_clock = nullptr;
@@ -573,6 +589,43 @@ struct Engine::Dev {
 };
 
 static int env_int(const char* name, int dflt) { const char* s = getenv(name); return (s && *s) ? atoi(s) : dflt; }
+
+// Pins the CALLING thread to the CPUs of the NUMA node the GPU hangs off (sysfs: numa_node of its PCI function,
+// cpulist of that node), so that the thread's pinned allocations are node-local and its copies do not cross the
+// socket interconnect.  Only ever called on threads this library created.  GW_NUMA=0 turns it off.
+static void bind_thread_near_device(int device) {
+  if (env_int("GW_NUMA", 1) == 0) return;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) return;
+  for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+  char path[160];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  if (node < 0) return;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return;
+  char list[4096] = {0};
+  const bool got = fgets(list, (int)sizeof list, f) != nullptr;
+  fclose(f);
+  if (!got) return;
+  cpu_set_t allowed, want;
+  CPU_ZERO(&allowed); CPU_ZERO(&want);
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
+  int n_want = 0;
+  for (const char* c = list; *c;) {
+    while (*c == ',' || *c == ' ' || *c == '\n') c++;
+    if (*c < '0' || *c > '9') break;
+    long lo = strtol(c, const_cast<char**>(&c), 10), hi = lo;
+    if (*c == '-') hi = strtol(c + 1, const_cast<char**>(&c), 10);
+    for (long k = lo; k <= hi && k < CPU_SETSIZE; k++) if (CPU_ISSET((int)k, &allowed)) { CPU_SET((int)k, &want); n_want++; }
+  }
+  if (n_want > 0) sched_setaffinity(0, sizeof want, &want);
+}
 
 Engine::Engine(const uint8_t* graph_data, size_t len) {
   graph = deserialize_witnesscalc_graph(graph_data, len);
@@ -612,6 +665,8 @@ Engine::~Engine() {
     cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
     cudaFree(d->lat_code); cudaFree(d->lat_first); cudaFree(d->lat_jobs); cudaFree(d->lat_njobs); cudaFree(d->lat_waits); cudaFree(d->lat_clock); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
     for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
+    for (int i = 0; i < 3; i++) { cudaFreeHost(d->h_ring[i]); cudaFreeHost(d->h_flags[i]); }
+    if (d->last_kernel) cudaEventDestroy(d->last_kernel);
     delete d;
   }
 }
@@ -625,7 +680,7 @@ Engine::Dev* Engine::dev(int device) {
   if (e != cudaSuccess || ndev == 0) throw Error("no CUDA device available: this library has no CPU fallback");
   if (device < 0 || device >= ndev) throw Error("CUDA device index out of range");
   CUDA_CHECK(cudaSetDevice(device));
-  Dev* d = new Dev();
+  std::unique_ptr<Dev> d(new Dev());
   d->device = device;
   cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   d->sms = prop.multiProcessorCount;
@@ -637,16 +692,19 @@ Engine::Dev* Engine::dev(int device) {
   d->max_threads = t_max;
   CUDA_CHECK(cudaFuncSetAttribute(eval_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
   CUDA_CHECK(cudaFuncSetAttribute(eval_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));   // per device, not per graph
+  CUDA_CHECK(cudaEventCreateWithFlags(&d->last_kernel, cudaEventDisableTiming));
   CUDA_CHECK(cudaMalloc(&d->code, plan.code.size() * sizeof(Instr)));
   CUDA_CHECK(cudaMemcpy(d->code, plan.code.data(), plan.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMalloc(&d->consts, plan.consts.size() * 32));
   CUDA_CHECK(cudaMemcpy(d->consts, plan.consts.data(), plan.consts.size() * 32, cudaMemcpyHostToDevice));
   d->spill_threads = (size_t)d->sms * t_max;
   if (plan.n_spill || plan.n_spill_narrow) CUDA_CHECK(cudaMalloc(&d->spill, ((size_t)plan.n_spill * 32 + (size_t)plan.n_spill_narrow * 8) * d->spill_threads));
-  devs[device] = d;
-  return d;
+  devs[device] = d.get();
+  return d.release();
 }
 
+// Enqueues one eval_batch_kernel on `stream`, behind every earlier launch of this engine on the device (the spill
+// area is indexed by resident thread and shared by all launches).  Callers hold d->mu.
 void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
   if (B == 0 || plan.code.empty()) return;
   KParams p;
@@ -659,14 +717,18 @@ void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uin
   if (n_tiles > 0xFFFFFFFFull) throw Error("batch too large");
   p.n_tiles = (uint32_t)n_tiles;
   p.spill_threads = d->spill_threads;
+#ifdef GW_PROFILING
   p.out_wrap = (unsigned long long)env_int("GW_DEBUG_OUT_WRAP", 0);
+#endif
   // whatever shared memory the rings and the register file leave goes to the most used constants
   const size_t base = smem_base(plan, T);
   p.n_hot = (uint32_t)std::min<size_t>(plan.consts.size(), (d->smem_max - base) / 32);
   if (env_int("GW_HOT_CONSTS", -1) >= 0) p.n_hot = std::min<uint32_t>(p.n_hot, (uint32_t)env_int("GW_HOT_CONSTS", 0));
   const int grid = (int)std::min<size_t>(n_tiles, (size_t)d->sms);
+  CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, d->last_kernel, 0));
   eval_batch_kernel<<<grid, T, base + (size_t)p.n_hot * 32, (cudaStream_t)stream>>>(p);
   CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(d->last_kernel, (cudaStream_t)stream));
 }
 
 int Engine::device_max_threads(int device) { return dev(device)->max_threads; }
@@ -674,9 +736,50 @@ int Engine::device_max_threads(int device) { return dev(device)->max_threads; }
 void Engine::run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
   Dev* d = dev(device);
   CUDA_CHECK(cudaSetDevice(device));
-  std::lock_guard<std::mutex> lk(d->mu);     // the spill area is shared by all launches on this device
+  std::lock_guard<std::mutex> lk(d->mu);     // enqueue order = execution order of the kernels (launch() chains them)
   launch(d, d_inputs, B, d_witness, d_status, stream);
 }
+
+// device staging buffers of the host-buffer APIs, two of each, for chunks of `chunk` input sets
+void Engine::ensure_staging(Dev* d, size_t chunk) {
+  if (chunk <= d->chunk) return;
+  const size_t in_b = (size_t)plan.n_inputs * 32, out_b = (size_t)plan.n_witness * 32;
+  // the old buffers go first (they can be most of HBM); the bookkeeping is cleared before anything can throw
+  d->chunk = 0;
+  for (int i = 0; i < 2; i++) {
+    cudaFree(d->d_in[i]); d->d_in[i] = nullptr;
+    cudaFree(d->d_out[i]); d->d_out[i] = nullptr;
+    cudaFree(d->d_status[i]); d->d_status[i] = nullptr;
+  }
+  for (int i = 0; i < 2; i++) {
+    CUDA_CHECK(cudaMalloc(&d->d_in[i], std::max<size_t>(chunk * in_b, 32)));
+    CUDA_CHECK(cudaMalloc(&d->d_out[i], std::max<size_t>(chunk * out_b, 32)));
+    CUDA_CHECK(cudaMalloc(&d->d_status[i], chunk * 4));
+    if (!d->stream[i]) CUDA_CHECK(cudaStreamCreateWithFlags(&d->stream[i], cudaStreamNonBlocking));
+  }
+  d->chunk = chunk;
+}
+
+namespace {
+// GW_TRACE_HOST=1: device-side timeline of a host-buffer call (per chunk: start, inputs landed, kernel done, witness landed)
+struct HostTrace {
+  bool on; std::vector<cudaEvent_t> ev;
+  HostTrace() : on(env_int("GW_TRACE_HOST", 0) != 0) {}
+  void mark(cudaStream_t st) { if (on) { cudaEvent_t e; if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); ev.push_back(e); } } }
+  void print(int device, size_t B, size_t chunk) {
+    if (!on) return;
+    fprintf(stderr, "[gw trace] device %d: %zu sets, chunk %zu:", device, B, chunk);
+    for (size_t i = 0; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[i]); fprintf(stderr, "%s%.1f", i % 4 == 0 ? " | " : " ", ms); }
+    fprintf(stderr, " ms\n");
+  }
+  ~HostTrace() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+// no copy may still target the caller's (or the ring's) memory when a host-buffer call returns, also on errors
+struct StreamDrain {
+  cudaStream_t a, b;
+  ~StreamDrain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); }
+};
+}  // namespace
 
 // host buffers: chunked, double-buffered H2D -> kernel -> D2H on two streams
 void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, size_t out_pitch) {
@@ -696,55 +799,35 @@ void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* w
   size_t chunk = std::min<size_t>(budget / std::max<size_t>(out_b + in_b, 1), 2 * d->spill_threads);
   if (B >= 4 * 2048) chunk = std::min(chunk, (B + 3) / 4);
   chunk = std::max<size_t>(std::min(chunk, B), 1);
-  if (chunk > d->chunk) {
-    for (int i = 0; i < 2; i++) {
-      cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]);
-      CUDA_CHECK(cudaMalloc(&d->d_in[i], chunk * in_b));
-      CUDA_CHECK(cudaMalloc(&d->d_out[i], std::max<size_t>(chunk * out_b, 32)));
-      CUDA_CHECK(cudaMalloc(&d->d_status[i], chunk * 4));
-      if (!d->stream[i]) CUDA_CHECK(cudaStreamCreateWithFlags(&d->stream[i], cudaStreamNonBlocking));
-    }
-    d->chunk = chunk;
-  }
-  // Both streams share the spill area, so kernels of consecutive chunks must not overlap: an event
-  // chains kernel k+1 behind kernel k while the copies of the two streams overlap with it.
-  cudaEvent_t kdone[2]; CUDA_CHECK(cudaEventCreateWithFlags(&kdone[0], cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&kdone[1], cudaEventDisableTiming));
-  // GW_TRACE_HOST=1: device-side timeline of the call (per chunk: start, inputs landed, kernel done, witness landed)
-  const bool trace = env_int("GW_TRACE_HOST", 0) != 0;
-  std::vector<cudaEvent_t> tev;
-  auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  ensure_staging(d, chunk);
+  // The kernels of consecutive chunks run back to back (launch() chains them: one spill area) while the copies
+  // of the two streams overlap with them.
+  HostTrace tr;
+  StreamDrain drain{d->stream[0], d->stream[1]};
   int k = 0;
   for (size_t off = 0; off < B; off += chunk, k ^= 1) {
     size_t nb = std::min(chunk, B - off);
     cudaStream_t s = d->stream[k];
-    mark(s);
+    tr.mark(s);
     CUDA_CHECK(cudaMemcpyAsync(d->d_in[k], inputs + off * in_b, nb * in_b, cudaMemcpyHostToDevice, s));
-    mark(s);
-    if (off) CUDA_CHECK(cudaStreamWaitEvent(s, kdone[k ^ 1], 0));
+    tr.mark(s);
     launch(d, d->d_in[k], nb, d->d_out[k], status ? d->d_status[k] : nullptr, s);
-    CUDA_CHECK(cudaEventRecord(kdone[k], s));
-    mark(s);
+    tr.mark(s);
     if (out_pitch == out_b) CUDA_CHECK(cudaMemcpyAsync(witness + off * out_b, d->d_out[k], nb * out_b, cudaMemcpyDeviceToHost, s));
     else if (out_b) CUDA_CHECK(cudaMemcpy2DAsync(witness + off * out_pitch, out_pitch, d->d_out[k], out_b, out_b, nb, cudaMemcpyDeviceToHost, s));
     if (status) CUDA_CHECK(cudaMemcpyAsync(status + off, d->d_status[k], nb * 4, cudaMemcpyDeviceToHost, s));
-    mark(s);
+    tr.mark(s);
   }
   CUDA_CHECK(cudaStreamSynchronize(d->stream[0]));
   CUDA_CHECK(cudaStreamSynchronize(d->stream[1]));
-  if (trace) {
-    fprintf(stderr, "[gw trace] device %d: %zu sets, chunk %zu:", device, B, chunk);
-    for (size_t i = 0; i < tev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, "%s%.1f", i % 4 == 0 ? " | " : " ", ms); }
-    fprintf(stderr, " ms\n");
-    for (cudaEvent_t e : tev) cudaEventDestroy(e);
-  }
-  cudaEventDestroy(kdone[0]); cudaEventDestroy(kdone[1]);
+  tr.print(device, B, chunk);
 }
 
 void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device, size_t out_pitch) {
   if (B == 0) return;
   if (out_pitch == 0) out_pitch = (size_t)plan.n_witness * 32;
   if (n_gpus <= 1) { run_host_on(first_device, inputs, B, witness, status, out_pitch); return; }
-  // independent input sets: contiguous shards, one host thread per GPU, no collective
+  // independent input sets: contiguous shards, one host thread per GPU (pinned to the GPU's NUMA node), no collective
   const size_t in_b = (size_t)plan.n_inputs * 32;
   std::vector<std::thread> th;
   std::vector<std::string> errs(n_gpus);
@@ -752,8 +835,93 @@ void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_
     size_t lo = B * g / n_gpus, hi = B * (g + 1) / n_gpus;
     if (hi == lo) continue;
     th.emplace_back([=, &errs]() {
-      try { run_host_on(first_device + g, inputs + lo * in_b, hi - lo, witness + lo * out_pitch, status ? status + lo : nullptr, out_pitch); }
-      catch (const std::exception& e) { errs[g] = e.what(); }
+      try {
+        bind_thread_near_device(first_device + g);
+        run_host_on(first_device + g, inputs + lo * in_b, hi - lo, witness + lo * out_pitch, status ? status + lo : nullptr, out_pitch);
+      } catch (const std::exception& e) { errs[g] = e.what(); }
+    });
+  }
+  for (auto& t : th) t.join();
+  for (auto& e : errs) if (!e.empty()) throw Error(e);
+}
+
+// Streaming output path: the witnesses of the batch never exist in host memory all at once.  Per GPU, chunk k's rows
+// go kernel -> device staging buffer (k mod 2) -> pinned ring slot (k mod 3); the consumer sees chunk k - 1 while
+// chunk k lands and chunk k + 1 is enqueued, so the device-to-host engine never waits for the host.
+void Engine::stream_on(int device, const uint8_t* inputs, size_t B, size_t first_set, size_t chunk_req, const ChunkFn& fn) {
+  Dev* d = dev(device);
+  CUDA_CHECK(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(d->mu);
+  const size_t in_b = (size_t)plan.n_inputs * 32, out_b = std::max<size_t>((size_t)plan.n_witness * 32, 32);
+  // chunk: a ring slot of GW_STREAM_CHUNK_MB (default 8 GiB; three slots are pinned per GPU), a device staging budget
+  // like run_host_on's, at most one full wave of resident threads; whole warps
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t dev_budget = (free_b + 2 * d->chunk * (in_b + out_b)) / 5;
+  size_t chunk = chunk_req;
+  if (chunk == 0) {
+    const size_t slot = (size_t)env_int("GW_STREAM_CHUNK_MB", 8192) << 20;
+    chunk = std::min<size_t>(std::min(slot, dev_budget) / out_b, d->spill_threads);
+    if (chunk >= 64) chunk = chunk / 32 * 32;
+  }
+  chunk = std::max<size_t>(std::min(std::min(chunk, dev_budget / (in_b + out_b)), B), 1);
+  ensure_staging(d, chunk);
+  if (chunk * out_b > d->h_ring_bytes || chunk > d->h_flags_n) {
+    d->h_ring_bytes = 0; d->h_flags_n = 0;
+    for (int i = 0; i < 3; i++) { cudaFreeHost(d->h_ring[i]); d->h_ring[i] = nullptr; cudaFreeHost(d->h_flags[i]); d->h_flags[i] = nullptr; }
+    for (int i = 0; i < 3; i++) {
+      CUDA_CHECK(cudaHostAlloc(&d->h_ring[i], chunk * out_b, cudaHostAllocDefault));
+      CUDA_CHECK(cudaHostAlloc(&d->h_flags[i], chunk * 4, cudaHostAllocDefault));
+    }
+    d->h_ring_bytes = chunk * out_b; d->h_flags_n = chunk;
+  }
+  struct Events {
+    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+    ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } landed;
+  for (int i = 0; i < 3; i++) CUDA_CHECK(cudaEventCreateWithFlags(&landed.e[i], cudaEventDisableTiming));
+  HostTrace tr;
+  StreamDrain drain{d->stream[0], d->stream[1]};
+  auto deliver = [&](size_t k) {
+    const size_t off = k * chunk, nb = std::min(chunk, B - off);
+    CUDA_CHECK(cudaEventSynchronize(landed.e[k % 3]));
+    if (fn(device, first_set + off, nb, d->h_ring[k % 3], (size_t)plan.n_witness * 32, d->h_flags[k % 3]) != 0) throw Error("witness stream stopped by the consumer");
+  };
+  size_t k = 0;
+  for (size_t off = 0; off < B; off += chunk, k++) {
+    const size_t nb = std::min(chunk, B - off);
+    const int sb = (int)(k & 1), slot = (int)(k % 3);
+    cudaStream_t s = d->stream[sb];
+    tr.mark(s);
+    CUDA_CHECK(cudaMemcpyAsync(d->d_in[sb], inputs + off * in_b, nb * in_b, cudaMemcpyHostToDevice, s));
+    tr.mark(s);
+    launch(d, d->d_in[sb], nb, d->d_out[sb], d->d_status[sb], s);
+    tr.mark(s);
+    if (plan.n_witness) CUDA_CHECK(cudaMemcpyAsync(d->h_ring[slot], d->d_out[sb], nb * (size_t)plan.n_witness * 32, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(d->h_flags[slot], d->d_status[sb], nb * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaEventRecord(landed.e[slot], s));
+    tr.mark(s);
+    if (k >= 1) deliver(k - 1);
+  }
+  if (k >= 1) deliver(k - 1);
+  tr.print(device, B, chunk);
+}
+
+void Engine::run_stream(const uint8_t* inputs, size_t B, int n_gpus, int first_device, size_t chunk_sets, const ChunkFn& fn) {
+  if (B == 0) return;
+  if (n_gpus < 1) n_gpus = 1;
+  // always on worker threads: they are pinned near their GPU before the ring is allocated, the caller's affinity is left alone
+  const size_t in_b = (size_t)plan.n_inputs * 32;
+  std::vector<std::thread> th;
+  std::vector<std::string> errs(n_gpus);
+  for (int g = 0; g < n_gpus; g++) {
+    size_t lo = B * g / n_gpus, hi = B * (g + 1) / n_gpus;
+    if (hi == lo) continue;
+    th.emplace_back([=, &errs, &fn]() {
+      try {
+        bind_thread_near_device(first_device + g);
+        stream_on(first_device + g, inputs + lo * in_b, hi - lo, lo, chunk_sets, fn);
+      } catch (const std::exception& e) { errs[g] = e.what(); }
     });
   }
   for (auto& t : th) t.join();
@@ -788,7 +956,11 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
   const LatencyPlan& lp = lat_plan;
   const size_t in_b = (size_t)lp.n_inputs * 32, out_b = std::max<size_t>((size_t)lp.n_witness * 32, 32);
   const size_t smem = ((size_t)lp.n_slots * 2 + LAT_CTRL_BYTES / 16 + (size_t)lp.n_warps * 3 * LAT_RING_SLOTS) * 16;
+#ifdef GW_PROFILING
   const bool clocks = env_int("GW_LAT_CLOCKS", 0) != 0;
+#else
+  const bool clocks = false;
+#endif
   if (!d->lat_code) {
     CUDA_CHECK(cudaMalloc(&d->lat_code, std::max<size_t>(lp.code.size(), 1) * sizeof(Instr)));
     CUDA_CHECK(cudaMemcpy(d->lat_code, lp.code.data(), lp.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
@@ -812,7 +984,10 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
   p.waits = d->lat_waits; p.n_waits = (uint32_t)(lp.waits.size() / 4);
   p.inputs = d->lat_in; p.out = d->lat_out; p.status = status ? d->lat_status : nullptr;
   p.level_clock = d->lat_clock;
-  p.dbg = (uint32_t)env_int("GW_LAT_DBG", 0);
+  p.dbg = 0;
+#ifdef GW_PROFILING
+  p.dbg = (uint32_t)env_int("GW_LAT_DBG", 0);      // timing experiments: -DGW_PROFILING builds only
+#endif
   CUDA_CHECK(cudaMemcpyAsync(d->lat_in, inputs, in_b, cudaMemcpyHostToDevice, 0));
   if (status) CUDA_CHECK(cudaMemsetAsync(d->lat_status, 0, 4, 0));
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -2,6 +2,7 @@
 // This is the persistent state the reference does not have (it re-parses the graph on every
 // calc_witness call, /root/reference/src/lib.rs:129-130).
 #pragma once
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -31,6 +32,11 @@ class Engine {
   // wtns_size(W) rounded up and witness pointing WTNS_HEADER_BYTES into the first row, every row becomes a complete
   // .wtns file image once the caller has written the 76-byte headers (the DMA engine does the framing).
   void run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, int n_gpus, int first_device, size_t out_pitch = 0);
+  // Streaming output path: chunks of witness rows are handed to `fn` from a pinned ring as they land (one worker
+  // thread per GPU; fn(device, first_set, n_sets, rows, row_bytes, flags) returns nonzero to stop).  The memory
+  // is only valid during the call.  chunk_sets = 0 picks the chunk size.
+  typedef std::function<int(int, size_t, size_t, const uint8_t*, size_t, const uint32_t*)> ChunkFn;
+  void run_stream(const uint8_t* inputs, size_t B, int n_gpus, int first_device, size_t chunk_sets, const ChunkFn& fn);
   // single witness, latency mode (one CTA, intra-level node parallelism); host buffers
   void run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms);
   LatencyPlan lat_plan;
@@ -41,6 +47,8 @@ class Engine {
   struct Dev;
   Dev* dev(int device);
   void launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
+  void ensure_staging(Dev* d, size_t chunk);
+  void stream_on(int device, const uint8_t* inputs, size_t B, size_t first_set, size_t chunk_req, const ChunkFn& fn);
   void run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, size_t out_pitch);
   void init_plan();
   std::map<int, Dev*> devs;

@@ -118,6 +118,9 @@ void put_ld(std::vector<uint8_t>& b, uint32_t fno, const std::vector<uint8_t>& p
 }
 }  // namespace
 
+// upper bound of the input buffer length (slots of 32 bytes): 2^28 slots = 8 GiB per input set is beyond any circuit
+static const uint64_t kMaxInputs = 1ull << 28;
+
 Graph deserialize_witnesscalc_graph(const uint8_t* data, size_t len) {
   if (len < kMagicLen + 8) throw Error("graph: file too short");
   if (memcmp(data, kMagic, kMagicLen) != 0) throw Error("graph: Invalid magic");
@@ -197,10 +200,12 @@ Graph deserialize_witnesscalc_graph(const uint8_t* data, size_t len) {
   for (uint32_t s : g.witness_signals) if (s >= g.nodes.size()) throw Error("graph: witness signal out of range");
   // get_inputs_size, lib.rs:138-152: (max Input idx in the first contiguous run of Input nodes) + 1.
   // Deviation: also cover every Input node and every mapped slot so nothing can index out of range.
-  uint32_t mx = 0;
-  for (const Node& nd : g.nodes) if (nd.kind == N_INPUT) mx = std::max(mx, nd.a);
-  for (auto& kv : g.inputs) if (kv.second.second) mx = std::max(mx, kv.second.first + kv.second.second - 1);
-  g.inputs_size = mx + 1;
+  // Computed in 64 bits and bounded: an Input index or a mapped extent near 2^32 must not wrap the buffer size.
+  uint64_t mx = 0;
+  for (const Node& nd : g.nodes) if (nd.kind == N_INPUT) mx = std::max<uint64_t>(mx, nd.a);
+  for (auto& kv : g.inputs) if (kv.second.second) mx = std::max<uint64_t>(mx, (uint64_t)kv.second.first + kv.second.second - 1);
+  if (mx + 1 > kMaxInputs) throw Error("graph: input index or input signal extent out of range");
+  g.inputs_size = (uint32_t)(mx + 1);
   return g;
 }
 

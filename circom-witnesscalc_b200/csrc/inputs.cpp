@@ -138,6 +138,7 @@ InputList deserialize_inputs(const char* json, size_t len) {
 }
 
 std::vector<U256> build_inputs_buffer(const Graph& g, const InputList& inputs) {
+  if (g.inputs_size == 0) throw Error("Failed to calculate witness: graph without an input buffer");
   std::vector<U256> buf(g.inputs_size, u256_from_u64(0));
   buf[0] = u256_from_u64(1);
   for (auto& kv : inputs) {

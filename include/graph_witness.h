@@ -109,6 +109,9 @@ int gw_calc_witness_batch_on(gw_graph_t *graph, int first_device, const uint8_t 
 int gw_calc_witness_batch_device(gw_graph_t *graph, int device, const void *d_inputs, size_t n_sets,
                                  void *d_witness, uint32_t *d_flags, void *cuda_stream, gw_status_t *status);
 
+/* Calls on one graph and device may come from any thread and any stream: the library runs the kernels of one graph
+ * on one device one after the other (they share a per-device scratch area), in the order the calls were made. */
+
 /* single-witness latency mode (BASELINE config 5): ONE input set (n_inputs x 32 B, host) is evaluated by one
  * CTA: the graph is scheduled into dependency levels, the independent instructions of a level are spread over
  * the lanes of the main warps, the long operations (Div, Pow, Idiv, Mod) run asynchronously on dedicated warps;
@@ -141,6 +144,25 @@ int gw_calc_witness_batch_wtns(gw_graph_t *graph, const uint8_t *inputs, size_t 
  * free it with gw_graph_free. */
 int gw_graph_select(const gw_graph_t *graph, const uint32_t *positions, size_t n_positions, gw_graph_t **selected,
                     gw_status_t *status);
+
+/* Streaming (SURVEY 8f-2 "streaming D2H"): like gw_calc_witness_batch_on, but the witnesses are handed to `fn` chunk by
+ * chunk as they land in a ring of three pinned host buffers per GPU that the library owns, so a batch whose witnesses
+ * do not fit host memory (262 144 authV2 input sets = 806 GB) runs end to end at its real size.  `fn` is called with
+ *   rows  : n_sets x row_bytes bytes (row_bytes = n_witness x 32), the witnesses of input sets first_set .. first_set + n_sets - 1,
+ *   flags : n_sets x uint32 (the per-set bits of gw_calc_witness_batch),
+ * valid only until it returns; returning nonzero stops the stream (the call then fails with an error).  One worker
+ * thread per GPU calls it: chunks of one GPU arrive in order, chunks of different GPUs may arrive concurrently.
+ * While `fn` looks at chunk k, chunk k + 1 is being copied and chunk k + 2 computed.  chunk_sets = 0 lets the library
+ * choose (GW_STREAM_CHUNK_MB of pinned memory per ring slot, default 8192).  The worker threads are pinned to the CPUs of
+ * their GPU's NUMA node before the ring is allocated (GW_NUMA=0 turns that off). */
+typedef int (*gw_witness_chunk_fn)(void *user, int device, size_t first_set, size_t n_sets, const uint8_t *rows,
+                                   size_t row_bytes, const uint32_t *flags);
+int gw_calc_witness_batch_stream(gw_graph_t *graph, int first_device, int n_gpus, const uint8_t *inputs, size_t n_sets,
+                                 size_t chunk_sets, gw_witness_chunk_fn fn, void *user, gw_status_t *status);
+
+/* CUDA device used by the single-witness entry points gw_calc_witness / gw_graph_calc_witness (default: the GW_DEVICE
+ * environment variable, else device 0 of CUDA_VISIBLE_DEVICES).  Returns 1 if the device does not exist. */
+int gw_set_device(int device);
 
 /* writes the 76-byte .wtns header for n_witness values (src/lib.rs:114-123) */
 void gw_wtns_header(uint32_t n_witness, uint8_t *dst76);

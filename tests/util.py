@@ -36,6 +36,31 @@ def golden_wtns(name) -> bytes:
     return lzma.decompress(open(os.path.join(GOLDEN, "wtns", name + ".wtns.xz"), "rb").read())
 
 
+def kat():
+    """reference-held known answers per golden graph (tests/golden/kat.json, written by tools/gen_graphs.py):
+    [{inputs: {name: value | [values]}, expOut: {main signal: value}, source}]"""
+    return json.load(open(os.path.join(GOLDEN, "kat.json")))
+
+
+def kat_cases():
+    return [(g, i) for g, v in sorted(kat().items()) for i in range(len(v))]
+
+
+def kat_check(witness, input_map, n_inputs_row, case, out_names):
+    """expOut of a circom_tester assertOut: main OUTPUT signals sit at witness positions 1.. in declaration order
+    (out_names), main INPUT signals after them in input-buffer order."""
+    n_out = len(out_names)
+    for k, v in case["expOut"].items():
+        if k in out_names:
+            assert witness[1 + out_names.index(k)] == int(v), (k, case.get("desc"))
+        else:
+            off, ln = input_map[k]
+            assert ln == 1 and witness[n_out + off] == int(v), (k, case.get("desc"))
+
+
+KAT_OUTPUTS = {"authV2_32_32": ["userID"], "poseidon2": ["out"], "poseidon3": ["out"], "poseidon5": ["out"]}
+
+
 # ---- packing ----------------------------------------------------------------------------------------
 def pack_u256(vals) -> bytes:
     return b"".join(int(v).to_bytes(32, "little") for v in vals)
@@ -88,7 +113,7 @@ def random_value(rnd: random.Random):
     return rnd.randrange(M)
 
 
-def random_graph(rnd: random.Random, n_inputs=6, n_ops=200, ops=None, n_consts=12):
+def random_graph(rnd: random.Random, n_inputs=6, n_ops=200, ops=None, n_consts=12, uno_ext=True):
     """A graph in the layout build-circuit produces: Input run first, then constants and ops.
     Returns (nodes, witness_signals, input_map)."""
     duo = ops if ops is not None else list(range(20))
@@ -103,7 +128,9 @@ def random_graph(rnd: random.Random, n_inputs=6, n_ops=200, ops=None, n_consts=1
         pick = lambda: rnd.randrange(n) if rnd.random() < 0.7 else rnd.randrange(max(0, n - 8), n)
         r = rnd.random()
         if r < 0.08:
-            nodes.append((po.K_UNO, 0, pick()))
+            # Neg mostly; Id / Lnot / Bnot (north_star's unary ops; the reference snapshot has Neg and Id only,
+            # graph.rs:175-178, and Id is unimplemented! at run time) are drawn too when `uno_ext`
+            nodes.append((po.K_UNO, rnd.choice((0, 0, 1, 2, 3)) if uno_ext else 0, pick()))
         elif r < 0.16:
             nodes.append((po.K_TRES, 0, pick(), pick(), pick()))
         else:

@@ -14,9 +14,16 @@ of graph::optimize (/root/reference/src/graph.rs:358-365: tree_shake, propagate,
 value_numbering, constants, tree_shake) are restated in `optimize()`.
 
 Known, documented differences from a real build-circuit run:
-  * witness_signals = every distinct signal value in [1, main outputs, main
-    inputs, remaining signals in execution order] (like circom --O1); the real
-    tool keeps only the signals surviving circom's constraint simplifier.
+  * witness_signals = [1, main outputs, main inputs, remaining signals in
+    execution order] minus, at the default opt_level 2, every non-main signal
+    that a `<==` defines by a LINEAR expression of other signals: circom's
+    constraint simplifier, which build-circuit runs at full strength
+    (build-circuit.rs:2189-2205), substitutes exactly such linear constraints
+    away, so what is left are the inputs/outputs of main, the signals defined
+    by quadratic constraints and the `<--` hints.  The real simplifier also
+    works on explicit `===` constraints and picks its own substitution order;
+    the selection here is an approximation of its result, not a replica.
+    opt_level 1 keeps every distinct declared signal (circom --O1-like).
   * node order is this executor's data-flow order; any topological order is
     valid for the evaluator.
 """
@@ -508,11 +515,18 @@ class Program:
 # --------------------------------------------------------------------------
 
 class Sym:
-    """A value that depends on input signals: reference to a graph node."""
-    __slots__ = ("id",)
+    """A value that depends on input signals: reference to a graph node.  `deg` is the degree of the EXPRESSION that
+    produced it in the signals it reads (circom's classification of `<==` right-hand sides): 1 = linear, 2 = quadratic,
+    3 = not quadratic (only legal under `<--`).  A signal read has degree 1 whatever defined the signal."""
+    __slots__ = ("id", "deg")
 
-    def __init__(self, i):
+    def __init__(self, i, deg=1):
         self.id = i
+        self.deg = deg
+
+
+def _deg(v):
+    return v.deg if isinstance(v, Sym) else 0
 
     def __repr__(self):
         return f"n{self.id}"
@@ -543,17 +557,26 @@ class Builder:
     def duo(self, op, a, b):
         if not isinstance(a, Sym) and not isinstance(b, Sym):
             return po.eval_duo(op, a, b, "circom")
-        return Sym(self._push((po.K_DUO, op, self.node_of(a), self.node_of(b))))
+        da, db = _deg(a), _deg(b)
+        if op in (2, 3):                       # Add, Sub
+            deg = max(da, db)
+        elif op == 0:                          # Mul
+            deg = min(da + db, 3)
+        elif op == 1 and db == 0:              # Div by a constant
+            deg = da
+        else:
+            deg = 3
+        return Sym(self._push((po.K_DUO, op, self.node_of(a), self.node_of(b))), deg)
 
     def uno(self, op, a):
         if not isinstance(a, Sym):
             return po.eval_uno(op, a, "circom")
-        return Sym(self._push((po.K_UNO, op, a.id)))
+        return Sym(self._push((po.K_UNO, op, a.id)), a.deg if op == 0 else 3)
 
     def tern(self, c, a, b):
         if not isinstance(c, Sym):
             return a if c != 0 else b
-        return Sym(self._push((po.K_TRES, 0, c.id, self.node_of(a), self.node_of(b))))
+        return Sym(self._push((po.K_TRES, 0, c.id, self.node_of(a), self.node_of(b))), 3)
 
 
 def _prod(dims):
@@ -564,13 +587,14 @@ def _prod(dims):
 
 
 class Signal:
-    __slots__ = ("name", "kind", "dims", "vals", "owner")
+    __slots__ = ("name", "kind", "dims", "vals", "owner", "lin")
 
     def __init__(self, name, kind, dims, owner):
         self.name = name
         self.kind = kind
         self.dims = dims
         self.vals = [None] * _prod(dims)
+        self.lin = [False] * len(self.vals)     # defined by `<==` with a linear (or constant) right-hand side
         self.owner = owner
 
 
@@ -635,8 +659,9 @@ class Env:
 
 
 class Executor:
-    def __init__(self, prog: Program):
+    def __init__(self, prog: Program, opt_level=2):
         self.prog = prog
+        self.opt_level = opt_level      # 1: every declared signal is a witness signal; 2: signals defined by a linear `<==` are not
         self.b = Builder()
         self.signal_order: List[Signal] = []
         self.constraints: List[Tuple[int, int, str]] = []   # (node_a, node_b, where)
@@ -680,20 +705,24 @@ class Executor:
         self.n_fixed = len(wit)
         n_all = 1 + sum(len(s.vals) for s in main_sigs)
         unassigned = 0
+        n_linear = 0
         for sig in self.signal_order:
             if sig.owner is comp and (sig.kind != "inter"):
                 continue
-            for v in sig.vals:
+            for k, v in enumerate(sig.vals):
                 n_all += 1
                 if v is None:
                     unassigned += 1
+                    continue
+                if self.opt_level >= 2 and sig.lin[k]:
+                    n_linear += 1              # circom --O2: the linear constraint defining it is substituted away
                     continue
                 nid = self.b.node_of(v)
                 if nid not in seen:
                     seen.add(nid)
                     wit.append(nid)
-        self.stats = {"signals_declared": n_all, "signals_unassigned": unassigned,
-                      "components": self.n_components}
+        self.stats = {"signals_declared": n_all, "signals_unassigned": unassigned, "signals_linear_eliminated": n_linear,
+                      "opt_level": self.opt_level, "components": self.n_components}
         return self.b.nodes, wit, input_map
 
     # ---- components ------------------------------------------------------
@@ -867,21 +896,22 @@ class Executor:
                 raise CircomError("initialised multi-signal declaration")
             sig = comp.signals[names[0][0]]
             val = self.eval(init[1], env)
-            self.assign_signal(sig, 0, sig.dims, val, f"{comp.path}:{line}")
+            self.assign_signal(sig, 0, sig.dims, val, f"{comp.path}:{line}", init[0])
 
-    def assign_signal(self, sig: Signal, off, dims, val, where):
+    def assign_signal(self, sig: Signal, off, dims, val, where, op="<--"):
         if dims:
             if not isinstance(val, list) or len(val) != dims[0]:
                 raise CircomError(f"{where}: array shape mismatch assigning {sig.name}")
             stride = _prod(dims[1:])
             for i, v in enumerate(val):
-                self.assign_signal(sig, off + i * stride, dims[1:], v, where)
+                self.assign_signal(sig, off + i * stride, dims[1:], v, where, op)
             return
         if isinstance(val, (list, tuple)) or val is None:
             raise CircomError(f"{where}: scalar signal {sig.name} assigned a non-scalar")
         if sig.vals[off] is not None:
             raise CircomError(f"{where}: signal {sig.name}[{off}] assigned twice")
         sig.vals[off] = val
+        sig.lin[off] = op in ("<==", "==>") and _deg(val) <= 1
         if sig.kind == "input":
             owner = sig.owner
             if owner.pending > 0:
@@ -954,7 +984,7 @@ class Executor:
             return                     # tag assignment: ignored
         if op == "=":
             raise CircomError(f"{where}: '=' on signal {name}")
-        self.assign_signal(sig, off, dims, val, where)
+        self.assign_signal(sig, off, dims, val, where, op)
 
     def resolve_signal(self, name, acc, env: Env, where, allow_tag=False):
         """name + accessors -> (Signal, flat offset, remaining dims)."""
@@ -1018,7 +1048,7 @@ class Executor:
         v = sig.vals[off]
         if v is None:
             raise CircomError(f"{where}: signal {sig.owner.path}.{sig.name}[{off}] read before assignment")
-        return v
+        return Sym(v.id, 1) if isinstance(v, Sym) else v
 
     def binop(self, op, a, b):
         if isinstance(a, list) or isinstance(b, list):
@@ -1266,14 +1296,14 @@ def dedupe_outputs(outputs, n_fixed):
     return res
 
 
-def compile_circuit(path: str, lib_dirs: List[str], check_inputs: Optional[dict] = None, seed=0x5EED):
+def compile_circuit(path: str, lib_dirs: List[str], check_inputs: Optional[dict] = None, seed=0x5EED, opt_level=2):
     """Returns dict(nodes, witness, input_map, stats).  If check_inputs is given
     ({name: [ints]}), every `===` of the sources is verified on the unoptimised graph."""
     prog = Program(lib_dirs)
     prog.load(path)
     if prog.main is None:
         raise CircomError("no main component")
-    ex = Executor(prog)
+    ex = Executor(prog, opt_level)
     nodes, wit, input_map = ex.run_main()
     stats = dict(ex.stats)
     stats["nodes_unoptimized"] = len(nodes)
@@ -1293,8 +1323,8 @@ def compile_circuit(path: str, lib_dirs: List[str], check_inputs: Optional[dict]
             "n_fixed": ex.n_fixed, "executor": ex}
 
 
-def build_graph(path: str, lib_dirs: List[str], check_inputs=None, seed=0x5EED):
-    res = compile_circuit(path, lib_dirs, check_inputs, seed)
+def build_graph(path: str, lib_dirs: List[str], check_inputs=None, seed=0x5EED, opt_level=2):
+    res = compile_circuit(path, lib_dirs, check_inputs, seed, opt_level)
     nodes, wit = res["nodes"], res["witness"]
     n_fixed = res["n_fixed"]          # 1 + main outputs + main inputs: never deduplicated
     onodes, owit = optimize(nodes, wit, seed)
@@ -1331,12 +1361,14 @@ if __name__ == "__main__":
     ap.add_argument("out")
     ap.add_argument("-l", action="append", default=[], dest="libs")
     ap.add_argument("--inputs", help="inputs.json used to verify every === of the sources")
+    ap.add_argument("--O1", action="store_const", const=1, default=2, dest="opt_level",
+                    help="keep every declared signal in the witness (default --O2-like: signals defined by a linear <== are dropped)")
     a = ap.parse_args()
     chk = None
     if a.inputs:
         chk = po.deserialize_inputs(open(a.inputs).read())
     t0 = time.time()
-    data, _, _, _, st = build_graph(a.circuit, a.libs, chk)
+    data, _, _, _, st = build_graph(a.circuit, a.libs, chk, opt_level=a.opt_level)
     with open(a.out, "wb") as f:
         f.write(data)
     st["seconds"] = round(time.time() - t0, 2)
