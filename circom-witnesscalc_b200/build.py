@@ -22,7 +22,7 @@ BIN_BATCH = os.path.join(HERE, "bin", "calc-witness-batch")
 REF_EXAMPLE_SRC = "/root/reference/examples/calc_witness.c"
 BIN_REF_EXAMPLE = os.path.join(HERE, "bin", "ref-example-calc-witness")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["engine.cu", "graph.cpp", "plan.cpp", "inputs.cpp", "wtns.cpp", "capi.cpp"]
+SOURCES = ["engine.cu", "graph.cpp", "plan.cpp", "bitplan.cpp", "inputs.cpp", "wtns.cpp", "capi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

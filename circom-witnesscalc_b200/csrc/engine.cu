@@ -40,6 +40,8 @@ struct KParams {
   uint32_t I, W;
   uint32_t n_tiles;
   unsigned long long spill_threads;
+  // optional indirection (the bit-sliced path's fallback): evaluate the input sets row_map[0 .. *n_dev) instead of 0 .. B
+  const uint32_t* row_map; const uint32_t* n_dev;
 #ifdef GW_PROFILING
   unsigned long long out_wrap;   // profiling aid (GW_DEBUG_OUT_WRAP, -DGW_PROFILING builds only): witness rows wrap modulo this many rows; 0 = off
 #endif
@@ -68,6 +70,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
   uint4* rf = hot + 2 * (size_t)p.n_hot + tid;       // this thread's column of the register file
   const unsigned long long gthread = (unsigned long long)blockIdx.x * T + tid;
   const uint32_t n = p.n_slots;
+  const unsigned long long B = p.n_dev ? (unsigned long long)*p.n_dev : p.B;       // uniform over the grid
+  const uint32_t n_tiles = p.n_dev ? (uint32_t)((B + T - 1) / T) : p.n_tiles;
+  if (blockIdx.x >= n_tiles) return;
 
   for (uint32_t k = tid; k < 2 * p.n_hot; k += T) hot[k] = __ldg(p.consts + k);
   __syncthreads();
@@ -87,10 +92,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
     return (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32));
   };
 
-  for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const unsigned long long w = (unsigned long long)tile * T + tid;
-    const bool active = w < p.B;
-    const unsigned long long wl = active ? w : p.B - 1;
+    const bool active = w < B;
+    const unsigned long long wi = active ? w : B - 1;
+    const unsigned long long wl = p.row_map ? (unsigned long long)p.row_map[wi] : wi;     // row of the input / witness arrays
     const uint4* in = p.inputs + wl * p.I * 2;
 #ifdef GW_PROFILING
     uint4* out = p.out + (p.out_wrap ? wl % p.out_wrap : wl) * p.W * 2;
@@ -245,7 +251,113 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
       }
       pc = npc;
     }
-    if (p.status != nullptr && active) p.status[w] = st;
+    if (p.status != nullptr && active) p.status[wl] = st;
+  }
+}
+
+// ---- bit-sliced path for Boolean graphs (bitplan.hpp) ---------------------------------------------------------------
+// One warp = one GROUP of 32 input sets.  A plane is one 32-bit word of the warp's plane file in shared memory: bit k =
+// the value for input set 32 g + k.  The plan is a sequence of steps of 32 independent 3-input look-up tables; in a step
+// every LANE executes its own LUT (lane = instruction, word = 32 input sets), so a step costs one coalesced 512-byte
+// header load, three shared-memory reads, ~25 logic instructions and one write per lane, and warps never synchronise
+// with each other.  The prologue packs the inputs into planes and CHECKS the contract the plan was typed under (every
+// input is 0 or 1); input sets that break it are handed to eval_batch_kernel through bad_list.
+struct BParams {
+  const uint4* code; uint32_t n_steps, n_slots;
+  const uint2* in_list; uint32_t n_in;      // (input index, plane slot or BIT_NO_SLOT) of every input the typing looked at
+  const uint4* inputs;                      // [B][I][2]
+  uint32_t I, W;
+  unsigned long long B;
+  uint32_t n_groups;
+  uint32_t* planes;                         // [n_groups][W]: plane word of every witness position
+  uint32_t* ok_words;                       // [n_groups]: bit k = input set 32 g + k satisfies the contract
+  uint32_t* bad_list; uint32_t* n_bad;      // the other input sets, for the fallback launch
+  uint32_t* status;                         // [B] or null (per-set flags: 0 for every set evaluated here)
+};
+
+__device__ __forceinline__ uint32_t lut3_eval(uint32_t lut, uint32_t a, uint32_t b, uint32_t c) {
+  // branch-free (the 32 lanes hold 32 different tables): a multiplexer tree over the 8 table bits spread to masks
+#define GW_LM(k) ((uint32_t)((int32_t)(lut << (31 - (k))) >> 31))
+  const uint32_t t0 = (a & GW_LM(1)) | (~a & GW_LM(0));
+  const uint32_t t1 = (a & GW_LM(3)) | (~a & GW_LM(2));
+  const uint32_t t2 = (a & GW_LM(5)) | (~a & GW_LM(4));
+  const uint32_t t3 = (a & GW_LM(7)) | (~a & GW_LM(6));
+#undef GW_LM
+  const uint32_t u0 = (b & t1) | (~b & t0), u1 = (b & t3) | (~b & t2);
+  return (c & u1) | (~c & u0);
+}
+
+__global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
+  extern __shared__ uint32_t bit_smem[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t g = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= p.n_groups) return;
+  uint32_t* S = bit_smem + (size_t)warp * p.n_slots;
+  const unsigned long long row = (unsigned long long)g * 32u + lane;
+  const bool in_range = row < p.B;
+  if (lane == 0) { S[BIT_SLOT_ZERO] = 0u; S[BIT_SLOT_ONES] = 0xFFFFFFFFu; }
+  // pack + contract check: lane = input set
+  const uint4* in = p.inputs + (in_range ? row : 0ull) * p.I * 2;
+  bool ok = in_range;
+#pragma unroll 4
+  for (uint32_t k = 0; k < p.n_in; k++) {
+    const uint2 e = __ldg(p.in_list + k);
+    const uint4 lo = __ldg(in + 2 * (size_t)e.x), hi = __ldg(in + 2 * (size_t)e.x + 1);
+    const bool is_bit = (lo.x <= 1u) && ((lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) == 0u);
+    ok = ok && is_bit;
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, in_range && (lo.x & 1u));
+    if (lane == 0 && e.y != BIT_NO_SLOT) S[e.y] = word;
+  }
+  const uint32_t okw = __ballot_sync(0xFFFFFFFFu, ok);
+  if (lane == 0) p.ok_words[g] = okw;
+  if (in_range && !ok) p.bad_list[atomicAdd(p.n_bad, 1u)] = (uint32_t)row;
+  if (p.status != nullptr && ok) p.status[row] = 0u;
+  if (okw == 0u) return;                                   // nobody in this group honours the contract
+  __syncwarp();
+  uint32_t* planes = p.planes + (size_t)g * p.W;
+  uint4 ins = __ldg(p.code + 32u + lane);                  // step 0 is the prologue above
+  for (uint32_t st = 1; st < p.n_steps; st++) {
+    const uint4 nxt = __ldg(p.code + (size_t)min(st + 1u, p.n_steps - 1u) * 32u + lane);
+    const uint32_t a = S[ins.y & 0xFFFFu], b = S[ins.y >> 16], c = S[ins.z & 0xFFFFu];
+    const uint32_t r = lut3_eval(ins.x, a, b, c);
+    const uint32_t dst = ins.z >> 16;
+    if (dst != BIT_NO_SLOT) S[dst] = r;                      // never a slot another lane reads in this step (bitplan.cpp)
+    if (ins.w != BIT_NO_POS) planes[ins.w] = r;
+    __syncwarp();
+    ins = nxt;
+  }
+}
+
+// Plane words -> canonical 32-byte witness values.  A warp takes one group and 32 consecutive witness positions (one
+// plane word per lane) and writes, for each of the group's input sets, the 32 x 32 bytes of that stretch of the set's
+// witness row with two 512-byte coalesced streaming stores: the HBM-bound part of the bit-sliced path.
+__global__ void __launch_bounds__(256) bit_expand_kernel(const uint32_t* __restrict__ planes, const uint32_t* __restrict__ ok_words,
+                                                         const int32_t* __restrict__ const_of_pos, const uint4* __restrict__ consts,
+                                                         uint4* __restrict__ out, uint32_t W, uint32_t n_groups, uint32_t tiles_per_group) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const unsigned long long t = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t g = (uint32_t)(t / tiles_per_group);
+  if (g >= n_groups) return;
+  const uint32_t j0 = (uint32_t)(t % tiles_per_group) * 32u, j = j0 + lane;
+  const uint32_t okw = __ldg(ok_words + g);
+  if (okw == 0u) return;
+  const uint32_t word = j < W ? __ldg(planes + (size_t)g * W + j) : 0u;
+  const int32_t cidx = j < W ? __ldg(const_of_pos + j) : -1;
+  const uint32_t half = lane & 1u;
+  for (uint32_t w = 0; w < 32u; w++) {
+    if (!((okw >> w) & 1u)) continue;
+    uint4* row = out + ((size_t)g * 32u + w) * W * 2;
+#pragma unroll
+    for (uint32_t h = 0; h < 2u; h++) {
+      const uint32_t pz = h * 16u + (lane >> 1);
+      const uint32_t wv = __shfl_sync(0xFFFFFFFFu, word, pz);
+      const int32_t ci = __shfl_sync(0xFFFFFFFFu, cidx, pz);
+      if (j0 + pz < W) {
+        uint4 v = make_uint4(half ? 0u : ((wv >> w) & 1u), 0u, 0u, 0u);
+        if (ci >= 0) v = __ldg(consts + 2 * (size_t)ci + half);
+        __stcs(row + 2 * (size_t)(j0 + pz) + half, v);
+      }
+    }
   }
 }
 
@@ -285,6 +397,26 @@ __device__ __forceinline__ void sts128(uint32_t a, const uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ fe lds_fe(uint32_t a) { return fe_from(lds128(a), lds128(a + 16)); }
+// Progress flags between warps that do not share a barrier (completed levels, jobs done per slow warp): written and
+// polled with shared-memory atomics by ONE lane (an atomic is never a data race, and 32 lanes hammering one word would
+// serialise); the block-level fences around them order the value-file accesses they publish.
+__device__ __forceinline__ void flag_publish(uint32_t a, uint32_t v) {
+  __threadfence_block();
+  uint32_t old;
+  asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  (void)old;
+}
+__device__ __forceinline__ uint32_t flag_read(uint32_t a) {
+  uint32_t v;
+  asm volatile("atom.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+// the whole warp waits until the flag at shared address a reaches v
+__device__ __forceinline__ void flag_wait(uint32_t a, uint32_t v, uint32_t lane, uint32_t sleep_ns) {
+  if (lane == 0) while (flag_read(a) < v) __nanosleep(sleep_ns);
+  __syncwarp();
+  __threadfence_block();
+}
 
 // The rare operations live in one out-of-line function so that the code a main warp walks every level (Mul, Sqr,
 // OP_DOT, Add/Sub, stores) stays small; the slow warps call nothing else.
@@ -460,14 +592,14 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
       }
       __syncwarp();
       while (nw.x == L) {
-        while (ctrl[1 + nw.y] < nw.z) __nanosleep(40);
+        flag_wait(smem_s + 4u * (1u + nw.y), nw.z, lane, 40);
         wi++;
         nw = wi < p.n_waits ? __ldg(p.waits + wi) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
       }
       __threadfence_block();
+      __syncwarp();                                                // the whole warp arrives at the barrier together
       asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
-      __threadfence_block();
-      if (lane == 0) { ctrl[0] = L + 1; if (p.level_clock) p.level_clock[L] = clock64(); }
+      if (lane == 0) { flag_publish(smem_s, L + 1); if (p.level_clock) p.level_clock[L] = clock64(); }
       if (stage == 2) { stage = 0; parity ^= 1u; } else stage++;
     }
   } else if (warp - p.n_warps - 1u < p.n_slow) {
@@ -478,12 +610,10 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
       const uint4 job = __ldg(jq + j);                             // {issue level, packet offset, headers, 0}
       const uint4* pk = p.code + job.y;
       const uint4 ins = lane < job.z ? __ldg(pk + 1 + lane) : make_uint4(OP_NOP, 0, 0, 0);
-      while (ctrl[0] < job.x) __nanosleep(100);
-      __threadfence_block();
+      flag_wait(smem_s, job.x, lane, 100);
       lat_exec_slow(cx, pk, ins, &st);
-      __threadfence_block();
       __syncwarp();
-      if (lane == 0) ctrl[1 + ws] = j + 1;
+      if (lane == 0) flag_publish(smem_s + 4u * (1u + ws), j + 1);
     }
   }
   if (p.status != nullptr && st) atomicOr(p.status, st);
@@ -581,6 +711,10 @@ struct Engine::Dev {
   // pinned host ring of the streaming API (three chunks: one in the consumer's hands, one landing, one enqueued)
   uint8_t* h_ring[3] = {nullptr, nullptr, nullptr}; uint32_t* h_flags[3] = {nullptr, nullptr, nullptr};
   size_t h_ring_bytes = 0, h_flags_n = 0;
+  // bit-sliced path (bitplan.hpp): program tables, and per-launch scratch that grows with the largest batch seen
+  uint4* bit_code = nullptr; uint2* bit_inputs = nullptr; int32_t* bit_constpos = nullptr; uint4* bit_consts = nullptr;
+  uint32_t* bit_planes = nullptr; uint32_t* bit_ok = nullptr; uint32_t* bit_bad = nullptr; uint32_t* bit_nbad = nullptr;
+  size_t bit_groups = 0;
   // single-witness latency mode
   uint4* lat_code = nullptr; uint4* lat_first = nullptr; uint4* lat_jobs = nullptr; uint32_t* lat_njobs = nullptr; uint4* lat_waits = nullptr;
   unsigned long long* lat_clock = nullptr;
@@ -643,6 +777,13 @@ void Engine::init_plan() {
   opt.fuse_pow5 = env_int("GW_FUSE_POW5", 1) != 0;
   opt.max_terms = (uint32_t)env_int("GW_MAX_TERMS", (int)opt.max_terms);
   plan = compile_plan(graph, opt);
+  // Boolean graphs get a bit-sliced plan as well (exact for every input: input sets that are not bits fall back to `plan`)
+  if (env_int("GW_BITSLICE", 1) != 0) {
+    BitPlanOptions bo;
+    bo.max_slots = (uint32_t)env_int("GW_BIT_MAX_SLOTS", (int)bo.max_slots);
+    bo.merge_luts = env_int("GW_BIT_MERGE", 1) != 0;
+    bit_plan = compile_bit_plan(graph, bo);
+  }
 }
 
 // shared memory of a CTA of T threads without the hot-constant area: instruction rings + register file
@@ -663,6 +804,8 @@ Engine::~Engine() {
     Dev* d = kv.second;
     cudaSetDevice(d->device);
     cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
+    cudaFree(d->bit_code); cudaFree(d->bit_inputs); cudaFree(d->bit_constpos); cudaFree(d->bit_consts);
+    cudaFree(d->bit_planes); cudaFree(d->bit_ok); cudaFree(d->bit_bad); cudaFree(d->bit_nbad);
     cudaFree(d->lat_code); cudaFree(d->lat_first); cudaFree(d->lat_jobs); cudaFree(d->lat_njobs); cudaFree(d->lat_waits); cudaFree(d->lat_clock); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
     for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
     for (int i = 0; i < 3; i++) { cudaFreeHost(d->h_ring[i]); cudaFreeHost(d->h_flags[i]); }
@@ -699,15 +842,71 @@ Engine::Dev* Engine::dev(int device) {
   CUDA_CHECK(cudaMemcpy(d->consts, plan.consts.data(), plan.consts.size() * 32, cudaMemcpyHostToDevice));
   d->spill_threads = (size_t)d->sms * t_max;
   if (plan.n_spill || plan.n_spill_narrow) CUDA_CHECK(cudaMalloc(&d->spill, ((size_t)plan.n_spill * 32 + (size_t)plan.n_spill_narrow * 8) * d->spill_threads));
+  if (use_bit_path()) {
+    const BitPlan& bp = bit_plan;
+    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+    CUDA_CHECK(cudaMalloc(&d->bit_code, bp.code.size() * sizeof(BitOp)));
+    CUDA_CHECK(cudaMemcpy(d->bit_code, bp.code.data(), bp.code.size() * sizeof(BitOp), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->bit_inputs, std::max<size_t>(bp.inputs.size(), 2) * 4));
+    CUDA_CHECK(cudaMemcpy(d->bit_inputs, bp.inputs.data(), bp.inputs.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->bit_constpos, std::max<size_t>(bp.const_of_pos.size(), 1) * 4));
+    CUDA_CHECK(cudaMemcpy(d->bit_constpos, bp.const_of_pos.data(), bp.const_of_pos.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->bit_consts, std::max<size_t>(bp.const_vals.size(), 1) * 32));
+    CUDA_CHECK(cudaMemcpy(d->bit_consts, bp.const_vals.data(), bp.const_vals.size() * 32, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->bit_nbad, 4));
+  }
   devs[device] = d.get();
   return d.release();
 }
 
 // Enqueues one eval_batch_kernel on `stream`, behind every earlier launch of this engine on the device (the spill
 // area is indexed by resident thread and shared by all launches).  Callers hold d->mu.
+// Bit-sliced path: pack + contract check + LUT steps (bit_eval_kernel), expansion of the plane words to witness rows
+// (bit_expand_kernel), then the generic kernel for the input sets that are not bits (usually none: an empty launch).
+void Engine::launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
+  const BitPlan& bp = bit_plan;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n_groups = (B + 31) / 32;
+  if (n_groups > 0x7FFFFFFFull) throw Error("batch too large");
+  CUDA_CHECK(cudaStreamWaitEvent(s, d->last_kernel, 0));
+  if (n_groups > d->bit_groups) {
+    // scratch of the largest batch seen; cudaFree waits for the kernels that still use the old one
+    cudaFree(d->bit_planes); d->bit_planes = nullptr; cudaFree(d->bit_ok); d->bit_ok = nullptr; cudaFree(d->bit_bad); d->bit_bad = nullptr;
+    d->bit_groups = 0;
+    CUDA_CHECK(cudaMalloc(&d->bit_planes, n_groups * (size_t)std::max<uint32_t>(bp.n_witness, 1) * 4));
+    CUDA_CHECK(cudaMalloc(&d->bit_ok, n_groups * 4));
+    CUDA_CHECK(cudaMalloc(&d->bit_bad, n_groups * 32 * 4));
+    d->bit_groups = n_groups;
+  }
+  CUDA_CHECK(cudaMemsetAsync(d->bit_nbad, 0, 4, s));
+  BParams q;
+  q.code = d->bit_code; q.n_steps = bp.n_steps; q.n_slots = bp.n_slots;
+  q.in_list = d->bit_inputs; q.n_in = (uint32_t)(bp.inputs.size() / 2);
+  q.inputs = (const uint4*)d_inputs; q.I = bp.n_inputs; q.W = bp.n_witness; q.B = B; q.n_groups = (uint32_t)n_groups;
+  q.planes = d->bit_planes; q.ok_words = d->bit_ok; q.bad_list = d->bit_bad; q.n_bad = d->bit_nbad; q.status = d_status;
+  // warps per CTA: as many as the plane files allow, but enough CTAs to cover the SMs twice
+  int wpb = (int)std::min<size_t>(8, d->smem_max / ((size_t)bp.n_slots * 4));
+  while (wpb > 1 && n_groups < (size_t)wpb * 2 * (size_t)d->sms) wpb--;
+  if (wpb < 1) throw Error("bit-sliced plan: plane file does not fit shared memory");
+  const int env_wpb = env_int("GW_BIT_WARPS", 0);
+  if (env_wpb >= 1 && env_wpb <= wpb) wpb = env_wpb;
+  bit_eval_kernel<<<(unsigned)((n_groups + wpb - 1) / wpb), wpb * 32, (size_t)wpb * bp.n_slots * 4, s>>>(q);
+  CUDA_CHECK(cudaGetLastError());
+  const uint32_t tiles = (bp.n_witness + 31) / 32;
+  const unsigned long long n_warp_tiles = (unsigned long long)n_groups * tiles;
+  if (n_warp_tiles) {
+    bit_expand_kernel<<<(unsigned)((n_warp_tiles + 7) / 8), 256, 0, s>>>(d->bit_planes, d->bit_ok, d->bit_constpos, d->bit_consts, (uint4*)d_witness,
+                                                                        bp.n_witness, (uint32_t)n_groups, tiles);
+    CUDA_CHECK(cudaGetLastError());
+  }
+}
+
 void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
   if (B == 0 || plan.code.empty()) return;
+  const bool bit = use_bit_path() && B >= (size_t)env_int("GW_BIT_MIN_SETS", 1);
+  if (bit) launch_bit(d, d_inputs, B, d_witness, d_status, stream);
   KParams p;
+  p.row_map = bit ? d->bit_bad : nullptr; p.n_dev = bit ? d->bit_nbad : nullptr;
   p.code = d->code; p.n_slots = (uint32_t)plan.code.size(); p.consts = d->consts;
   p.inputs = (const uint4*)d_inputs; p.out = (uint4*)d_witness; p.spill = d->spill; p.status = d_status;
   p.nspill = reinterpret_cast<uint2*>(d->spill + (size_t)plan.n_spill * 2 * d->spill_threads);

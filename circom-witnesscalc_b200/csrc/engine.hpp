@@ -7,6 +7,7 @@
 #include <mutex>
 #include <string>
 
+#include "bitplan.hpp"
 #include "graph.hpp"
 #include "plan.hpp"
 
@@ -21,6 +22,7 @@ class Engine {
 
   Graph graph;
   Plan plan;
+  BitPlan bit_plan;           // bit-sliced plan (bitplan.hpp); used by every batch launch when eligible (GW_BITSLICE=0: never)
   int max_threads = 512;      // upper bound of threads per CTA (GW_THREADS); one persistent CTA per SM
   int threads_for(size_t B, int sms, int t_max) const;
   int device_max_threads(int device);   // threads per CTA (= input sets per SM and wave) the device allows for this plan
@@ -47,6 +49,8 @@ class Engine {
   struct Dev;
   Dev* dev(int device);
   void launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
+  bool use_bit_path() const { return bit_plan.eligible && bit_plan.n_luts > 0; }
+  void launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
   void ensure_staging(Dev* d, size_t chunk);
   void stream_on(int device, const uint8_t* inputs, size_t B, size_t first_set, size_t chunk_req, const ChunkFn& fn);
   void run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, size_t out_pitch);

@@ -308,3 +308,77 @@ int64_t sim_eval_latency(SimGraph* s, const uint8_t* inputs, uint8_t* witness, u
   return rc;
 }
 }
+
+// ---- bit-sliced plan (bitplan.hpp) on the host: one group of up to 32 input sets, exactly what bit_eval_kernel and
+// bit_expand_kernel do (contract check + pack, steps of 32 LUTs on one word per plane, expansion of the plane words) ----
+#include "../../circom-witnesscalc_b200/csrc/bitplan.hpp"
+
+struct BitSim { Graph g; BitPlan bp; };
+
+extern "C" {
+
+BitSim* sim_bit_load(const uint8_t* data, size_t len, uint32_t max_support, int merge, char* err, size_t errlen) {
+  try {
+    std::unique_ptr<BitSim> s(new BitSim());
+    s->g = deserialize_witnesscalc_graph(data, len);
+    BitPlanOptions o; if (max_support) o.max_support = max_support; o.merge_luts = merge != 0;
+    s->bp = compile_bit_plan(s->g, o);
+    if (!s->bp.eligible && err && errlen) { strncpy(err, s->bp.reason.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return s.release();
+  } catch (const std::exception& e) { if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; } return nullptr; }
+}
+void sim_bit_free(BitSim* s) { delete s; }
+void sim_bit_info(BitSim* s, uint64_t* out) {
+  const BitPlan& b = s->bp;
+  out[0] = b.eligible; out[1] = b.n_steps; out[2] = b.n_slots; out[3] = b.n_luts; out[4] = b.n_levels; out[5] = b.n_nodes_bit;
+  out[6] = b.n_nodes_tt; out[7] = b.n_nodes_bv; out[8] = b.n_full_adders; out[9] = b.n_merged; out[10] = b.inputs.size() / 2; out[11] = b.const_vals.size();
+}
+// inputs: n x I x 32 B (n <= 32), witness: n x W x 32 B; returns the mask of input sets that satisfy the bit contract
+// (only their rows are written), or -1 on a malformed plan
+int64_t sim_bit_eval(BitSim* s, const uint8_t* inputs, uint32_t n, uint8_t* witness) {
+  const BitPlan& b = s->bp;
+  if (!b.eligible || n > 32) return -1;
+  std::vector<uint32_t> S(b.n_slots, 0);
+  S[BIT_SLOT_ONES] = 0xFFFFFFFFu;
+  uint32_t ok = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
+  for (size_t k = 0; k < b.inputs.size(); k += 2) {
+    const uint32_t idx = b.inputs[k], slot = b.inputs[k + 1];
+    if (idx >= b.n_inputs) return -1;
+    uint32_t word = 0;
+    for (uint32_t w = 0; w < n; w++) {
+      const uint8_t* v = inputs + ((size_t)w * b.n_inputs + idx) * 32;
+      bool is_bit = v[0] <= 1;
+      for (int q = 1; q < 32; q++) is_bit &= v[q] == 0;
+      if (!is_bit) ok &= ~(1u << w);
+      word |= (uint32_t)(v[0] & 1) << w;
+    }
+    if (slot != BIT_NO_SLOT) { if (slot >= b.n_slots) return -1; S[slot] = word; }
+  }
+  std::vector<uint32_t> planes(b.n_witness, 0);
+  for (uint32_t st = 0; st < b.n_steps; st++) {
+    uint32_t res[32]; 
+    for (uint32_t lane = 0; lane < 32; lane++) {                 // all lanes read ...
+      const BitOp& op = b.code[(size_t)st * 32 + lane];
+      const uint32_t sa = op.y & 0xFFFF, sb = op.y >> 16, sc = op.z & 0xFFFF;
+      if (sa >= b.n_slots || sb >= b.n_slots || sc >= b.n_slots) return -1;
+      res[lane] = bit_lut3(op.x & 0xFF, S[sa], S[sb], S[sc]);
+    }
+    for (uint32_t lane = 0; lane < 32; lane++) {                 // ... before any lane writes
+      const BitOp& op = b.code[(size_t)st * 32 + lane];
+      const uint32_t dst = op.z >> 16;
+      if (dst != BIT_NO_SLOT) { if (dst >= b.n_slots || dst < 2) return -1; S[dst] = res[lane]; }
+      if (op.w != BIT_NO_POS) { if (op.w >= b.n_witness) return -1; planes[op.w] = res[lane]; }
+    }
+  }
+  for (uint32_t w = 0; w < n; w++) {
+    if (!((ok >> w) & 1)) continue;
+    for (uint32_t j = 0; j < b.n_witness; j++) {
+      uint8_t* dst = witness + ((size_t)w * b.n_witness + j) * 32;
+      if (b.const_of_pos[j] >= 0) memcpy(dst, b.const_vals[(size_t)b.const_of_pos[j]].l, 32);
+      else { memset(dst, 0, 32); dst[0] = (planes[j] >> w) & 1; }
+    }
+  }
+  return (int64_t)ok;
+}
+
+}  // extern "C"

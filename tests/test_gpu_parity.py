@@ -394,3 +394,59 @@ def test_set_device_and_graph_cache(cwc):
     for _ in range(2):
         assert cwc.calc_witness('{"a": "5"}', ga) == [1, 12]
         assert cwc.calc_witness('{"a": "5"}', gb) == [1, 14]
+
+
+def test_bitsliced_path_boolean_graphs_and_fallback(cwc, monkeypatch):
+    """Boolean graphs run bit-sliced (csrc/bitplan.cpp: 32 input sets per word, lane = LUT instruction); the plan is typed
+    under the contract "inputs are bits", which the kernel checks per input set: the sets that break it are evaluated by
+    the generic kernel in the same call.  Every row must equal the oracle whichever path produced it, flags included."""
+    from tests.test_bitplan import boolean_graph
+    rnd = random.Random(99)
+    for t in range(6):
+        n_in = rnd.choice([5, 24, 70])
+        nodes, wit, imap = boolean_graph(rnd, n_inputs=n_in, n_gates=rnd.choice([60, 300]))
+        data = po.serialize_graph(nodes, wit, imap)
+        g = cwc.Graph(data)
+        B = rnd.choice([1, 31, 32, 33, 200, 1029])
+        rows = [[1] + [rnd.randrange(2) for _ in range(n_in)] for _ in range(B)]
+        bad = set(rnd.sample(range(B), min(B, rnd.choice([0, 1, 9])))) if t else set()
+        for b in bad:
+            rows[b][1 + rnd.randrange(n_in)] = rnd.choice([2, po.M - 1, rnd.randrange(po.M), 1 << 255])
+        inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(B, n_in + 1, 32)
+        out, flags = g.calc_witness_batch(inp, want_flags=True)
+        for b in sorted(set(range(0, B, max(1, B // 24))) | bad | {B - 1}):
+            assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, rows[b], wit, "circom"), (t, b, b in bad)
+        assert (flags[[b for b in range(B) if b not in bad]] == 0).all()
+        # the generic kernel alone gives the same bytes
+        monkeypatch.setenv("GW_BITSLICE", "0")
+        g0 = cwc.Graph(data)
+        monkeypatch.delenv("GW_BITSLICE")
+        assert (g0.calc_witness_batch(inp) == out).all(), t
+
+
+def test_bitsliced_sha256_bits_and_field_inputs(cwc):
+    """SHA-256(512) through the bit-sliced path: digests against hashlib, rows with non-bit inputs (the generic kernel
+    takes them) against the C oracle, all in one batch with a ragged last group."""
+    import hashlib
+    from oracle import cref
+    name = "circuit8_sha256_512"
+    data = util.golden_graph(name)
+    g = cwc.Graph(data)
+    rng = np.random.default_rng(88)
+    B = 32 * 9 + 5
+    inp = np.zeros((B, g.n_inputs, 32), dtype=np.uint8)
+    inp[:, :, 0] = rng.integers(0, 2, size=(B, g.n_inputs), dtype=np.uint8)
+    inp[:, 0, 0] = 1
+    field_rows = [7, 64, 65, B - 1]
+    vals = util.random_field_batch(rng, (len(field_rows), g.n_inputs)).view(np.uint8).reshape(len(field_rows), g.n_inputs, 32)
+    for k, b in enumerate(field_rows):
+        inp[b, 1:] = vals[k, 1:]
+    out = g.calc_witness_batch(inp)
+    for b in (0, 1, 31, 32, 100, B - 2):
+        bits = inp[b, 1:513, 0]
+        msg = bytes(int("".join(str(int(x)) for x in bits[8 * i:8 * i + 8]), 2) for i in range(64))
+        dg = out[b, 1:257, 0]
+        assert bytes(int("".join(str(int(x)) for x in dg[8 * i:8 * i + 8]), 2) for i in range(32)) == hashlib.sha256(msg).digest(), b
+    rows = field_rows + [0, 8, 63, 66]
+    want = cref.CGraph(data).evaluate_batch(inp[rows], 4)
+    assert (out[rows] == want).all()

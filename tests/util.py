@@ -231,7 +231,7 @@ def field_host_lib(emulate_ptx=False):
 def sim_lib():
     if "sim" not in _libs:
         src = [os.path.join(ROOT, "tests/csrc/plan_host_sim.cpp")] + [os.path.join(CSRC, f) for f in
-                                                                      ("graph.cpp", "plan.cpp", "inputs.cpp", "wtns.cpp")]
+                                                                      ("graph.cpp", "plan.cpp", "bitplan.cpp", "inputs.cpp", "wtns.cpp")]
         L = ctypes.CDLL(_build("libgwsim.so", src))
         L.sim_load.restype = ctypes.c_void_p
         L.sim_load.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t]
@@ -250,8 +250,47 @@ def sim_lib():
         L.sim_inputs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
         L.sim_reserialize.restype = ctypes.c_size_t
         L.sim_reserialize.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.sim_bit_load.restype = ctypes.c_void_p
+        L.sim_bit_load.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+        L.sim_bit_free.argtypes = [ctypes.c_void_p]
+        L.sim_bit_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        L.sim_bit_eval.restype = ctypes.c_int64
+        L.sim_bit_eval.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p]
         _libs["sim"] = L
     return _libs["sim"]
+
+
+class BitSimGraph:
+    """bit-sliced plan (csrc/bitplan.cpp) on the host simulator: groups of up to 32 input sets"""
+
+    def __init__(self, data: bytes, max_support=0, merge=True):
+        self.L = sim_lib()
+        err = ctypes.create_string_buffer(512)
+        self.h = self.L.sim_bit_load(data, len(data), max_support, int(merge), err, 512)
+        if not self.h:
+            raise ValueError(err.value.decode())
+        info = (ctypes.c_uint64 * 12)()
+        self.L.sim_bit_info(self.h, info)
+        keys = ["eligible", "n_steps", "n_slots", "n_luts", "n_levels", "n_bit", "n_tt", "n_bv", "n_full_adders", "n_merged", "n_inputs_checked", "n_consts"]
+        self.info = dict(zip(keys, [int(x) for x in info]))
+        self.reason = err.value.decode()
+        nodes, wit, _ = po.deserialize_graph(data)
+        self.I = 1 + max([n[1] for n in nodes if n[0] == po.K_INPUT] + [0])
+        self.W = len(wit)
+
+    def eval(self, rows):
+        """rows: list (<= 32) of input lists -> (list of witness lists or None where the bit contract fails, ok mask)"""
+        n = len(rows)
+        out = ctypes.create_string_buffer(32 * self.W * n)
+        ok = self.L.sim_bit_eval(self.h, b"".join(pack_u256(r) for r in rows), n, out)
+        assert ok >= 0, "malformed bit plan"
+        res = [unpack_u256(out.raw[32 * self.W * b:32 * self.W * (b + 1)]) if (ok >> b) & 1 else None for b in range(n)]
+        return res, int(ok)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.sim_bit_free(self.h)
+            self.h = None
 
 
 class SimGraph:
