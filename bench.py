@@ -49,13 +49,13 @@ def shard_range(n_units: int, rank: int, world: int):
 
 
 def launch_plan(n_sets: int, max_chunk: int, sms: int):
-    """[lo, hi) per launch: the fewest launches that fit `max_chunk` sets each, balanced, whole warps on every SM"""
+    """[lo, hi) per launch.  The kernel runs one persistent CTA per SM and its time steps with ceil(warps per CTA / 4)
+    (four schedulers per SM), so a launch should fill whole quads of warps on every SM: chunks are multiples of
+    sms x 128 input sets (sms x 32 when less fits), as large as `max_chunk` allows; the last launch takes the rest."""
     if n_sets <= 0:
         return []
-    wave = sms * 32
-    n_launch = max(1, -(-n_sets // max(max_chunk, wave)))
-    chunk = -(-n_sets // n_launch)
-    chunk = min(-(-chunk // wave) * wave, max(max_chunk // wave * wave, wave))
+    quad, wave = sms * 128, sms * 32
+    chunk = max_chunk // quad * quad if max_chunk >= quad else max(max_chunk // wave * wave, wave)
     return [(lo, min(lo + chunk, n_sets)) for lo in range(0, n_sets, chunk)]
 
 

@@ -55,7 +55,10 @@ __device__ __forceinline__ uint4 fe_hi(const fe& a) { return make_uint4(a.l[4], 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 static const int RING = 64;          // instruction slots staged per warp in shared memory (two blocks of 32)
-static const int MAX_THREADS = 512;  // one persistent CTA per SM; 512 threads x 128 registers = the whole register file
+#ifndef GW_MAX_THREADS
+#define GW_MAX_THREADS 512           // one persistent CTA per SM; 512 threads x 128 registers = the whole register file
+#endif
+static const int MAX_THREADS = GW_MAX_THREADS;
 
 // One thread = one input set; blockDim.x = T threads (a multiple of 32, chosen per launch so that one CTA per SM covers
 // the batch).  Dynamic shared memory: [T/32 warps][RING] instruction slots | [n_hot][2] hot constants | register file
@@ -165,9 +168,35 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
         have_result = false;
       } else if (op == OP_DOT) {
         // fused linear combination: 512-bit accumulator, ONE Montgomery reduction
-        const uint32_t nt = ins.y & 0xFFu;
+        const uint32_t nt = ins.y & 0xFFu, shape = ins.y >> 16;
         dot_acc P;
         dot_init(P);
+        if (shape & 1u) {
+          // straight-line path for the shapes Poseidon's mix layers produce (plan.cpp: shape hint; terms ordered
+          // products, added value, constant): no term loop, so the accumulator needs no loop-carried register shuffling
+          const uint32_t n_mac = (shape >> 1) & 3u;
+          const uint4 t01 = ring[(pc + 1) & (RING - 1)], t23 = ring[(pc + 2) & (RING - 1)], t45 = ring[(pc + 3) & (RING - 1)];
+          auto term_lo = [&](uint32_t k) { return k == 0 ? t01.x : k == 1 ? t01.z : k == 2 ? t23.x : k == 3 ? t23.z : t45.x; };
+          auto term_ci = [&](uint32_t k) { return k == 0 ? t01.y : k == 1 ? t01.w : k == 2 ? t23.y : k == 3 ? t23.w : t45.y; };
+          {
+            const fe c = const_load(t01.y);
+            const fe x = rf_load(t01.x >> 16);
+            dot_mac(P, x.l, c.l);
+          }
+          if (n_mac >= 2) {
+            const fe c = const_load(t01.w);
+            const fe x = rf_load(t01.z >> 16);
+            dot_mac(P, x.l, c.l);
+          }
+          if (n_mac >= 3) {
+            const fe c = const_load(t23.y);
+            const fe x = rf_load(t23.x >> 16);
+            dot_mac(P, x.l, c.l);
+          }
+          uint32_t k = n_mac;
+          if (shape & 8u) { const fe y = rf_load(term_lo(k) >> 16); dot_add256(P, y.l, 8); k++; }
+          if (shape & 16u) { const fe c = const_load(term_ci(k)); dot_add256(P, c.l, 0); }
+        } else
 #pragma unroll 1
         for (uint32_t t = 0; t < nt; t++) {
           const uint4 sl = ring[(pc + 1 + (t >> 1)) & (RING - 1)];
@@ -275,6 +304,8 @@ struct BParams {
   uint32_t* status;                         // [B] or null (per-set flags: 0 for every set evaluated here)
 };
 
+static const uint32_t BIT_PREFETCH = 4;
+
 __device__ __forceinline__ uint32_t lut3_eval(uint32_t lut, uint32_t a, uint32_t b, uint32_t c) {
   // branch-free (the 32 lanes hold 32 different tables): a multiplexer tree over the 8 table bits spread to masks
 #define GW_LM(k) ((uint32_t)((int32_t)(lut << (31 - (k))) >> 31))
@@ -315,16 +346,26 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   if (okw == 0u) return;                                   // nobody in this group honours the contract
   __syncwarp();
   uint32_t* planes = p.planes + (size_t)g * p.W;
-  uint4 ins = __ldg(p.code + 32u + lane);                  // step 0 is the prologue above
-  for (uint32_t st = 1; st < p.n_steps; st++) {
-    const uint4 nxt = __ldg(p.code + (size_t)min(st + 1u, p.n_steps - 1u) * 32u + lane);
-    const uint32_t a = S[ins.y & 0xFFFFu], b = S[ins.y >> 16], c = S[ins.z & 0xFFFFu];
-    const uint32_t r = lut3_eval(ins.x, a, b, c);
-    const uint32_t dst = ins.z >> 16;
-    if (dst != BIT_NO_SLOT) S[dst] = r;                      // never a slot another lane reads in this step (bitplan.cpp)
-    if (ins.w != BIT_NO_POS) planes[ins.w] = r;
-    __syncwarp();
-    ins = nxt;
+  // the headers of the next BIT_PREFETCH steps are in flight while a step executes: one L2 round trip per step would
+  // otherwise be the whole cost of a step (a handful of warps per SM cannot hide it)
+  const uint32_t last = p.n_steps - 1u;
+  uint4 q[BIT_PREFETCH];
+#pragma unroll
+  for (uint32_t k = 0; k < BIT_PREFETCH; k++) q[k] = __ldg(p.code + (size_t)min(1u + k, last) * 32u + lane);   // step 0 is the prologue above
+  for (uint32_t st = 1; st < p.n_steps; st += BIT_PREFETCH) {
+#pragma unroll
+    for (uint32_t k = 0; k < BIT_PREFETCH; k++) {
+      const uint4 ins = q[k];
+      q[k] = __ldg(p.code + (size_t)min(st + k + BIT_PREFETCH, last) * 32u + lane);
+      if (st + k < p.n_steps) {                              // uniform
+        const uint32_t a = S[ins.y & 0xFFFFu], b = S[ins.y >> 16], c = S[ins.z & 0xFFFFu];
+        const uint32_t r = lut3_eval(ins.x, a, b, c);
+        const uint32_t dst = ins.z >> 16;
+        if (dst != BIT_NO_SLOT) S[dst] = r;                  // never a slot another lane reads in this step (bitplan.cpp)
+        if (ins.w != BIT_NO_POS) planes[ins.w] = r;
+        __syncwarp();
+      }
+    }
   }
 }
 
@@ -411,6 +452,9 @@ __device__ __forceinline__ uint32_t flag_read(uint32_t a) {
   asm volatile("atom.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+// The barrier that ends a level: main warps and the control warp arrive at ONE barrier instruction (a function of its
+// own, so that every participant executes the same bar.sync: what compute-sanitizer's synccheck expects of an aligned barrier).
+__device__ __noinline__ void lat_level_barrier(uint32_t n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
 // the whole warp waits until the flag at shared address a reaches v
 __device__ __forceinline__ void flag_wait(uint32_t a, uint32_t v, uint32_t lane, uint32_t sleep_ns) {
   if (lane == 0) while (flag_read(a) < v) __nanosleep(sleep_ns);
@@ -561,7 +605,7 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
       // header k belongs to lane k mod cur.w; a lane runs its headers in order (a chain: program order, no barrier)
       if (!(p.dbg & 16u) && lane < cur.w) for (uint32_t i = lane; i < cur.z; i += cur.w) lat_exec(cx, pk_s, lds128(pk_s + 16u * (1u + i)), &st);
       __syncwarp();
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      lat_level_barrier(bar_threads);
       cur = nxt; nxt = desc;
       if (stage == 2) { stage = 0; parity ^= 1u; } else stage++;
     }
@@ -598,7 +642,7 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
       }
       __threadfence_block();
       __syncwarp();                                                // the whole warp arrives at the barrier together
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      lat_level_barrier(bar_threads);
       if (lane == 0) { flag_publish(smem_s, L + 1); if (p.level_clock) p.level_clock[L] = clock64(); }
       if (stage == 2) { stage = 0; parity ^= 1u; } else stage++;
     }
@@ -769,13 +813,14 @@ Engine::Engine(Graph g) : graph(std::move(g)) { init_plan(); }
 
 void Engine::init_plan() {
   max_threads = env_int("GW_THREADS", MAX_THREADS);
-  if (max_threads < 32 || max_threads > MAX_THREADS || (max_threads & 31)) throw Error("GW_THREADS must be a multiple of 32 in [32, 512]");
+  if (max_threads < 32 || max_threads > MAX_THREADS || (max_threads & 31)) throw Error("GW_THREADS must be a multiple of 32 in [32, " + std::to_string(MAX_THREADS) + "]");
   PlanOptions opt; opt.n_regs = (uint32_t)env_int("GW_REGS", (int)opt.n_regs);
   opt.div_batch = (uint32_t)env_int("GW_DIV_BATCH", (int)opt.div_batch);
   opt.fuse_dot = env_int("GW_FUSE_DOT", 1) != 0;
   opt.narrow = env_int("GW_NARROW", 1) != 0;
   opt.fuse_pow5 = env_int("GW_FUSE_POW5", 1) != 0;
   opt.max_terms = (uint32_t)env_int("GW_MAX_TERMS", (int)opt.max_terms);
+  opt.dot_shapes = env_int("GW_DOT_SHAPES", 1) != 0;
   plan = compile_plan(graph, opt);
   // Boolean graphs get a bit-sliced plan as well (exact for every input: input sets that are not bits fall back to `plan`)
   if (env_int("GW_BITSLICE", 1) != 0) {

@@ -61,6 +61,7 @@ def test_rows_do_not_depend_on_the_slice_and_launch_plans_cover_the_shard():
         assert sum(hi - lo for lo, hi in plan) == n and all(0 < hi - lo <= max(mx, 148 * 32) for lo, hi in plan)
         assert all(plan[k][1] == plan[k + 1][0] for k in range(len(plan) - 1))
         assert all((hi - lo) % (148 * 32) == 0 for lo, hi in plan[:-1])
+    assert bench.launch_plan(262144, 80000, 148) == [(0, 75776), (75776, 151552), (151552, 227328), (227328, 262144)]
 
 
 def test_shard_range_properties():

@@ -30,9 +30,9 @@ if not a.no_imad:
 for name in a.circuits.split(","):
     g = cwc.Graph(util.golden_graph(name))
     I, W = g.n_inputs, g.n_witness
-    B = a.batch or max(1024, min(148 * 256 * 2, int(110e9 // (32 * W))))
+    B = int(os.environ.get("GW_BATCH", "0")) or a.batch or max(1024, min(148 * 256 * 2, int(110e9 // (32 * W))))
     if a.batch and not os.environ.get("GW_DEBUG_OUT_WRAP"):
-        B = min(B, int(150e9 // (32 * W)))
+        B = min(B, int(160e9 // (32 * W)))
     rng = np.random.default_rng(9)
     vals = util.random_field_batch(rng, (min(B, 4096), I))
     if "sha256" in name:
