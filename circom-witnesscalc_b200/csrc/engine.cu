@@ -168,35 +168,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
         have_result = false;
       } else if (op == OP_DOT) {
         // fused linear combination: 512-bit accumulator, ONE Montgomery reduction
-        const uint32_t nt = ins.y & 0xFFu, shape = ins.y >> 16;
+        const uint32_t nt = ins.y & 0xFFu;
         dot_acc P;
         dot_init(P);
-        if (shape & 1u) {
-          // straight-line path for the shapes Poseidon's mix layers produce (plan.cpp: shape hint; terms ordered
-          // products, added value, constant): no term loop, so the accumulator needs no loop-carried register shuffling
-          const uint32_t n_mac = (shape >> 1) & 3u;
-          const uint4 t01 = ring[(pc + 1) & (RING - 1)], t23 = ring[(pc + 2) & (RING - 1)], t45 = ring[(pc + 3) & (RING - 1)];
-          auto term_lo = [&](uint32_t k) { return k == 0 ? t01.x : k == 1 ? t01.z : k == 2 ? t23.x : k == 3 ? t23.z : t45.x; };
-          auto term_ci = [&](uint32_t k) { return k == 0 ? t01.y : k == 1 ? t01.w : k == 2 ? t23.y : k == 3 ? t23.w : t45.y; };
-          {
-            const fe c = const_load(t01.y);
-            const fe x = rf_load(t01.x >> 16);
-            dot_mac(P, x.l, c.l);
-          }
-          if (n_mac >= 2) {
-            const fe c = const_load(t01.w);
-            const fe x = rf_load(t01.z >> 16);
-            dot_mac(P, x.l, c.l);
-          }
-          if (n_mac >= 3) {
-            const fe c = const_load(t23.y);
-            const fe x = rf_load(t23.x >> 16);
-            dot_mac(P, x.l, c.l);
-          }
-          uint32_t k = n_mac;
-          if (shape & 8u) { const fe y = rf_load(term_lo(k) >> 16); dot_add256(P, y.l, 8); k++; }
-          if (shape & 16u) { const fe c = const_load(term_ci(k)); dot_add256(P, c.l, 0); }
-        } else
 #pragma unroll 1
         for (uint32_t t = 0; t < nt; t++) {
           const uint4 sl = ring[(pc + 1 + (t >> 1)) & (RING - 1)];
@@ -707,10 +681,23 @@ __global__ void imad_bench_kernel(uint32_t* out, int iters, uint32_t y) {
   if (acc == 0x12345678u) out[0] = acc;
 }
 
+// The library works on the device it is told to, and leaves the calling thread's current device as it found it
+// (a caller that mixes this library with its own CUDA code must not find itself on another GPU after a call).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaSetDevice");
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+};
+
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x); } while (0)
 
 double imad_microbench(int device, int which) {
-  CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard on(device);
   cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   uint32_t* d; CUDA_CHECK(cudaMalloc(&d, 4));
   const int iters = 4000, threads = 256, blocks = prop.multiProcessorCount * 8;
@@ -768,6 +755,7 @@ struct Engine::Dev {
 
 static int env_int(const char* name, int dflt) { const char* s = getenv(name); return (s && *s) ? atoi(s) : dflt; }
 
+
 // Pins the CALLING thread to the CPUs of the NUMA node the GPU hangs off (sysfs: numa_node of its PCI function,
 // cpulist of that node), so that the thread's pinned allocations are node-local and its copies do not cross the
 // socket interconnect.  Only ever called on threads this library created.  GW_NUMA=0 turns it off.
@@ -820,7 +808,6 @@ void Engine::init_plan() {
   opt.narrow = env_int("GW_NARROW", 1) != 0;
   opt.fuse_pow5 = env_int("GW_FUSE_POW5", 1) != 0;
   opt.max_terms = (uint32_t)env_int("GW_MAX_TERMS", (int)opt.max_terms);
-  opt.dot_shapes = env_int("GW_DOT_SHAPES", 1) != 0;
   plan = compile_plan(graph, opt);
   // Boolean graphs get a bit-sliced plan as well (exact for every input: input sets that are not bits fall back to `plan`)
   if (env_int("GW_BITSLICE", 1) != 0) {
@@ -847,6 +834,8 @@ int Engine::threads_for(size_t B, int sms, int t_max) const {
 Engine::~Engine() {
   for (auto& kv : devs) {
     Dev* d = kv.second;
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(d->device);
     cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
     cudaFree(d->bit_code); cudaFree(d->bit_inputs); cudaFree(d->bit_constpos); cudaFree(d->bit_consts);
@@ -856,6 +845,7 @@ Engine::~Engine() {
     for (int i = 0; i < 3; i++) { cudaFreeHost(d->h_ring[i]); cudaFreeHost(d->h_flags[i]); }
     if (d->last_kernel) cudaEventDestroy(d->last_kernel);
     delete d;
+    if (prev >= 0) cudaSetDevice(prev);
   }
 }
 
@@ -867,7 +857,7 @@ Engine::Dev* Engine::dev(int device) {
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) throw Error("no CUDA device available: this library has no CPU fallback");
   if (device < 0 || device >= ndev) throw Error("CUDA device index out of range");
-  CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard on(device);
   std::unique_ptr<Dev> d(new Dev());
   d->device = device;
   cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -979,7 +969,7 @@ int Engine::device_max_threads(int device) { return dev(device)->max_threads; }
 
 void Engine::run_device(int device, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
   Dev* d = dev(device);
-  CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard on(device);
   std::lock_guard<std::mutex> lk(d->mu);     // enqueue order = execution order of the kernels (launch() chains them)
   launch(d, d_inputs, B, d_witness, d_status, stream);
 }
@@ -1028,7 +1018,7 @@ struct StreamDrain {
 // host buffers: chunked, double-buffered H2D -> kernel -> D2H on two streams
 void Engine::run_host_on(int device, const uint8_t* inputs, size_t B, uint8_t* witness, uint32_t* status, size_t out_pitch) {
   Dev* d = dev(device);
-  CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard on(device);
   std::lock_guard<std::mutex> lk(d->mu);
   const size_t in_b = (size_t)plan.n_inputs * 32, out_b = (size_t)plan.n_witness * 32;
   if (out_pitch == 0) out_pitch = out_b;
@@ -1094,7 +1084,7 @@ void Engine::run_host(const uint8_t* inputs, size_t B, uint8_t* witness, uint32_
 // chunk k lands and chunk k + 1 is enqueued, so the device-to-host engine never waits for the host.
 void Engine::stream_on(int device, const uint8_t* inputs, size_t B, size_t first_set, size_t chunk_req, const ChunkFn& fn) {
   Dev* d = dev(device);
-  CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard on(device);
   std::lock_guard<std::mutex> lk(d->mu);
   const size_t in_b = (size_t)plan.n_inputs * 32, out_b = std::max<size_t>((size_t)plan.n_witness * 32, 32);
   // chunk: a ring slot of GW_STREAM_CHUNK_MB (default 8 GiB; three slots are pinned per GPU), a device staging budget
@@ -1175,7 +1165,7 @@ void Engine::run_stream(const uint8_t* inputs, size_t B, int n_gpus, int first_d
 // one witness, host buffers: inputs I x 32 B, witness W x 32 B; returns the kernel time in ms if asked
 void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms) {
   Dev* d = dev(device);
-  CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard on(device);
   std::lock_guard<std::mutex> lk(d->mu);
   {
     std::lock_guard<std::mutex> lk2(mu);

@@ -671,19 +671,12 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       if (m.narrow) plan.stats.narrow_instrs++;
       if (m.opc == OP_DOT) {
         std::vector<uint32_t> words;
-        // terms ordered products, +value, -value, constant: the kernel's straight-line path (shape hint below) relies on it
+        // terms ordered products, +value, -value, constant (lanes of a warp then walk the same term kinds together)
         std::vector<PTerm> ts = m.terms;
         std::stable_sort(ts.begin(), ts.end(), [](const PTerm& a, const PTerm& b) {
           auto key = [](const PTerm& t) { return t.kind == 0 ? 0 : t.kind == 1 ? (t.neg ? 2 : 1) : 3; };
           return key(a) < key(b);
         });
-        uint32_t n_k[4] = {0, 0, 0, 0};
-        for (const PTerm& t : ts) n_k[t.kind == 0 ? 0 : t.kind == 2 ? 3 : (t.neg ? 2 : 1)]++;
-        // .y bits 16..: bit 0 = straight-line shape (1-3 products, at most one added value, no subtracted value, at most
-        // one constant), bits 1-2 = products, bit 3 = has an added value, bit 4 = has a constant
-        e.enc[0] = 0;
-        if (opt.dot_shapes && !m.narrow && n_k[0] >= 1 && n_k[0] <= 3 && n_k[1] <= 1 && n_k[2] == 0 && n_k[3] <= 1)
-          e.enc[0] = 1u | (n_k[0] << 1) | (n_k[1] << 3) | (n_k[3] << 4);
         for (const PTerm& t : ts) {
           uint32_t kind = t.kind == 0 ? (uint32_t)T_MAC : t.kind == 2 ? (uint32_t)T_CONST : (t.neg ? (uint32_t)T_SUBHI : (uint32_t)T_ADDHI);
           uint32_t reg = t.kind == 2 ? 0u : (uint32_t)al.reg_of[t.node];
@@ -731,7 +724,7 @@ Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
       const uint32_t* outs = &out_list[out_start[m.node]];
       if (out_inline[u]) { e.flags |= F_OUT; plan.stats.outs++; }
       if (m.opc == OP_DOT) {
-        al.emit(make_instr(OP_DOT, e.flags, dsts[u], (uint32_t)m.terms.size() | (m.ncs << 8) | (e.enc[0] << 16), 0, out_inline[u] ? outs[0] : 0));
+        al.emit(make_instr(OP_DOT, e.flags, dsts[u], (uint32_t)m.terms.size() | (m.ncs << 8), 0, out_inline[u] ? outs[0] : 0));
         for (const Instr& sl : e.term_slots) plan.code.push_back(sl);
       } else if (m.opc == OP_POW5) {
         al.emit(make_instr(OP_POW5, e.flags, dsts[u], e.enc[0] | ((m.pos4 == NO_POS ? 0xFFFFu : m.pos4 - m.pos2) << 16), m.pos2, out_inline[u] ? outs[0] : 0));

@@ -27,7 +27,6 @@ struct PlanOptions {
   uint32_t max_terms = 8;    // max terms of one OP_DOT (<= DOT_MAX_TERMS, <= n_regs - 3)
   bool narrow = true;        // narrow typing: provably small values are computed on int64 (isa.h: F_NARROW)
   bool fuse_pow5 = true;     // Sqr -> Sqr -> Mul S-box chains become one OP_POW5 (throughput plan)
-  bool dot_shapes = true;    // shape hints for the kernel's straight-line OP_DOT path (1-3 products, <= 1 added value, <= 1 constant)
   bool fold_addc = false;    // Mul(constant, value +- constant) -> OP_DOT terms that do not wait for the Add (latency mode)
 };
 
