@@ -207,13 +207,16 @@ def config_batch(cwc, torch, tag, name, B, seed, peaks, imad_peak, reps=5, warmu
     timad = imad_per_witness(info) * B / (ms * 1e-3) / 1e12
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     t_hbm, t_imad = alg_bytes / (hbm_peak * 1e9), imad_per_witness(info) / imad_peak       # seconds per witness at each roof
-    bound = "hbm" if t_hbm >= t_imad else "imad"
+    # a graph that runs bit-sliced executes LUT instructions on 32 input sets per word, no field multiplications: what
+    # bounds it is reading the inputs and writing 32 bytes per witness value
+    bound = "hbm" if (t_hbm >= t_imad or info.get("bit_eligible")) else "imad"
     roof = ({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak} if bound == "hbm" else
             {"bound": "imad", "achieved": timad, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": timad * 1e12 / imad_peak})
     res = {"config": tag, "circuit": name, "batch": B, "launches_per_step": len(launches), "ms_per_step": ms, "witnesses_per_s": rate,
            "node_ops_per_s": rate * info["n_ops"], "roofline": roof, "hbm_algorithmic_GBps": gbs, "imad_algorithmic_T": timad,
            "parity_rows_bit_exact": bool((got == want).all()), "rows_checked": len(rows), "witness_len": W, "inputs_len": I,
            "n_instrs": info["n_instrs"], "n_spill": info["n_spill"],
+           "bit_sliced": bool(info.get("bit_eligible")), "bit_luts": info.get("bit_luts"), "bit_steps": info.get("bit_steps"),
            "l2": f"{chunk * W * 32 / 1e6:.0f} MB of witness written per launch (L2 is 126 MB)"}
     del d_in, d_out, g
     torch.cuda.empty_cache()

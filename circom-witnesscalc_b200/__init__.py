@@ -41,7 +41,9 @@ class gw_graph_info_t(ctypes.Structure):
                 ("n_div", ctypes.c_uint64), ("n_spill_ld", ctypes.c_uint64), ("n_spill_st", ctypes.c_uint64),
                 ("n_slots", ctypes.c_uint32), ("n_dot", ctypes.c_uint32), ("n_dot_mac", ctypes.c_uint32),
                 ("n_mul_instr", ctypes.c_uint32), ("n_inversions", ctypes.c_uint32), ("threads", ctypes.c_uint32),
-                ("sets_per_thread", ctypes.c_uint32), ("n_narrow_instr", ctypes.c_uint32)]
+                ("sets_per_thread", ctypes.c_uint32), ("n_narrow_instr", ctypes.c_uint32),
+                ("bit_eligible", ctypes.c_uint32), ("bit_luts", ctypes.c_uint32), ("bit_steps", ctypes.c_uint32),
+                ("bit_wide", ctypes.c_uint32)]
 
 
 _libc = ctypes.CDLL(None)

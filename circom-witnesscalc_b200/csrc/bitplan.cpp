@@ -12,21 +12,52 @@ namespace gw {
 
 namespace {
 
-typedef unsigned __int128 u128;
-const uint64_t BV_LIM = (uint64_t)1 << 62;
-
 inline int n_operands(const Node& nd) { return nd.kind == N_TRES ? 3 : nd.kind == N_DUO ? 2 : nd.kind == N_UNO ? 1 : 0; }
 inline uint32_t operand(const Node& nd, int k) { return k == 0 ? nd.a : k == 1 ? nd.b : nd.c; }
 inline fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 inline U256 to_u256(const fe& v) { U256 r; memcpy(r.l, v.l, 32); return r; }
-inline bool u256_small(const U256& v, uint64_t* out) {       // v < 2^62 ?
-  for (int k = 2; k < 8; k++) if (v.l[k]) return false;
-  const uint64_t x = (uint64_t)v.l[0] | ((uint64_t)v.l[1] << 32);
-  if (x >= BV_LIM) return false;
-  *out = x;
-  return true;
-}
-inline int bit_length(uint64_t v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
+
+// Exact upper bounds of bit-vector values: 256-bit unsigned integers.  A bit-vector value must stay below M, so that
+// the integer the planes hold IS the field element the reference computes (no reduction ever happens).
+struct Big {
+  U256 v;
+  Big() { memset(v.l, 0, 32); }
+  explicit Big(uint64_t x) { memset(v.l, 0, 32); v.l[0] = (uint32_t)x; v.l[1] = (uint32_t)(x >> 32); }
+  explicit Big(const U256& x) : v(x) {}
+  bool is_zero() const { for (int k = 0; k < 8; k++) if (v.l[k]) return false; return true; }
+  bool is_one() const { if (v.l[0] != 1) return false; for (int k = 1; k < 8; k++) if (v.l[k]) return false; return true; }
+  int bits() const { for (int k = 7; k >= 0; k--) if (v.l[k]) { int n = 0; uint32_t x = v.l[k]; while (x) { n++; x >>= 1; } return 32 * k + n; } return 0; }
+  bool bit(int p) const { return p < 256 && ((v.l[p >> 5] >> (p & 31)) & 1u); }
+  bool operator<(const Big& o) const { return v < o.v; }
+  bool below_modulus() const { return v < BN254_M; }
+  // false on overflow past 256 bits
+  static bool add(const Big& a, const Big& b, Big* r) {
+    uint64_t c = 0;
+    for (int k = 0; k < 8; k++) { c += (uint64_t)a.v.l[k] + b.v.l[k]; r->v.l[k] = (uint32_t)c; c >>= 32; }
+    return c == 0;
+  }
+  static bool shl(const Big& a, uint32_t k, Big* r) {
+    if (a.is_zero()) { *r = Big(); return true; }
+    if ((uint32_t)a.bits() + k > 256) return false;
+    *r = Big();
+    for (int p = 0; p < a.bits(); p++) if (a.bit(p)) r->v.l[(p + (int)k) >> 5] |= 1u << ((p + (int)k) & 31);
+    return true;
+  }
+  static Big shr(const Big& a, uint32_t k) {
+    Big r;
+    for (int p = (int)k; p < a.bits(); p++) if (a.bit(p)) r.v.l[(p - (int)k) >> 5] |= 1u << ((p - (int)k) & 31);
+    return r;
+  }
+  static bool mul(const Big& a, const Big& b, Big* r) {
+    if (a.bits() + b.bits() > 256) return false;            // conservative: the product certainly fits below
+    uint32_t P[16];
+    u256_mul_wide(P, a.v.l, b.v.l);
+    for (int k = 8; k < 16; k++) if (P[k]) return false;
+    memcpy(r->v.l, P, 32);
+    return true;
+  }
+  static Big ones(int n) { Big r; for (int p = 0; p < n && p < 256; p++) r.v.l[p >> 5] |= 1u << (p & 31); return r; }
+};
 
 // ---- truth tables over <= 6 variables held in 64 bits: bit idx = f(x_0 = idx & 1, x_1 = idx >> 1 & 1, ..) --------------
 inline uint64_t tt_cofactor(uint64_t t, int n, int k, int val) {     // fix variable k: table over the remaining n - 1 variables
@@ -57,16 +88,17 @@ struct BGraph {
   struct BN { uint8_t kind, n, lut; uint32_t in[3]; };       // K_INPUT: in[0] = input index; K_LUT: n inputs, table of 2^n bits
   std::vector<BN> nodes;
   std::map<std::array<uint32_t, 4>, uint32_t> cse;
-  std::map<uint32_t, uint32_t> input_ids;
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> input_ids;   // (input index, bit or BIT_CONTRACT) -> node
   BGraph() {
     nodes.push_back(BN{K_ZERO, 0, 0, {0, 0, 0}});
     nodes.push_back(BN{K_ONE, 0, 0, {0, 0, 0}});
   }
-  uint32_t input(uint32_t idx) {
-    auto it = input_ids.find(idx);
+  uint32_t input(uint32_t idx, uint32_t bit) {
+    auto key = std::make_pair(idx, bit);
+    auto it = input_ids.find(key);
     if (it != input_ids.end()) return it->second;
-    nodes.push_back(BN{K_INPUT, 0, 0, {idx, 0, 0}});
-    return input_ids[idx] = (uint32_t)nodes.size() - 1;
+    nodes.push_back(BN{K_INPUT, 0, 0, {idx, bit, 0}});
+    return input_ids[key] = (uint32_t)nodes.size() - 1;
   }
   // f(leaves) given by `table` (2^n bits, n <= 6): constants, repeated and irrelevant leaves are removed, what is
   // left becomes one LUT (n <= 3) or a Shannon tree of multiplexers over the last leaf
@@ -114,7 +146,7 @@ struct BGraph {
 };
 
 struct TT { std::vector<uint32_t> sup; std::vector<U256> tab; };
-struct BV { std::vector<std::vector<uint32_t>> cols; uint64_t hi = 0; bool compressed = true; };
+struct BV { std::vector<std::vector<uint32_t>> cols; Big hi; bool compressed = true; };
 enum { V_NONE = 0, V_CONST = 1, V_TT = 2, V_BV = 3 };
 struct Val { uint8_t k = V_NONE; int32_t plane = -1; int32_t tt = -1, bv = -1; U256 c; };
 
@@ -139,6 +171,25 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
   }
   bool any_input = false;
   for (size_t i = 0; i < N; i++) if (needed[i] && g.nodes[i].kind == N_INPUT && g.nodes[i].a != 0) any_input = true;
+  // An input whose every reader is Shr(input, constant) (Num2Bits: (in >> i) & 1) is a FIELD input: any value is fine, its
+  // planes are the bits of the value reduced mod M.  Every other input is under the bit contract.
+  std::vector<uint8_t> field_input(N, 0);
+  for (size_t i = 0; i < N; i++) field_input[i] = needed[i] && g.nodes[i].kind == N_INPUT && g.nodes[i].a != 0;
+  {
+    bool any_shift = false;
+    std::vector<uint8_t> shifted(N, 0);
+    for (size_t i = 0; i < N; i++) {
+      if (!needed[i]) continue;
+      const Node& nd = g.nodes[i];
+      for (int k = 0; k < n_operands(nd); k++) {
+        const uint32_t o = operand(nd, k);
+        if (!field_input[o]) continue;
+        if (nd.kind == N_DUO && nd.op == OP_SHR && k == 0 && g.nodes[nd.b].kind == N_CONST) { shifted[o] = 1; any_shift = true; }
+        else field_input[o] = 0;
+      }
+    }
+    (void)any_shift; (void)shifted;                          // an input nobody reads (a witness signal only) is a field input too
+  }
   if (!any_input || bp.n_witness == 0) { bp.reason = "no live inputs or empty witness"; return bp; }
 
   BGraph bg;
@@ -158,7 +209,7 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
   // compress a bit heap to one plane per column with full adders (carry-save: ~ one adder per surplus bit)
   auto compress = [&](BV& b) {
     if (b.compressed) return;
-    const size_t width = (size_t)bit_length(b.hi);
+    const size_t width = (size_t)b.hi.bits();
     if (b.cols.size() < width) b.cols.resize(width);
     for (size_t p = 0; p < b.cols.size(); p++) {
       std::vector<uint32_t> q;
@@ -192,23 +243,21 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
     if (v.bv >= 0) return v.bv;
     BV b;
     if (v.k == V_CONST) {
-      uint64_t c;
-      if (!u256_small(v.c, &c)) return -1;
-      b.hi = c;
-      for (int p = 0; p < bit_length(c); p++) { b.cols.emplace_back(); if ((c >> p) & 1) b.cols.back().push_back(1); }
+      b.hi = Big(v.c);
+      if (!b.hi.below_modulus()) return -1;
+      for (int p = 0; p < b.hi.bits(); p++) { b.cols.emplace_back(); if (b.hi.bit(p)) b.cols.back().push_back(1); }
     } else if (v.k == V_TT) {
-      if (v.plane >= 0) { b.hi = 1; b.cols = {{(uint32_t)v.plane}}; }
+      if (v.plane >= 0) { b.hi = Big(1); b.cols = {{(uint32_t)v.plane}}; }
       else {
         const TT& t = tts[(size_t)v.tt];
-        uint64_t mx = 0;
-        std::vector<uint64_t> sm(t.tab.size());
-        for (size_t a = 0; a < t.tab.size(); a++) { if (!u256_small(t.tab[a], &sm[a])) return -1; mx = std::max(mx, sm[a]); }
+        Big mx;
+        for (size_t a = 0; a < t.tab.size(); a++) { const Big x(t.tab[a]); if (!x.below_modulus()) return -1; if (mx < x) mx = x; }
         std::vector<uint32_t> leaves;
         for (uint32_t s : t.sup) leaves.push_back((uint32_t)val[s].plane);
         b.hi = mx;
-        for (int p = 0; p < bit_length(mx); p++) {
+        for (int p = 0; p < mx.bits(); p++) {
           uint64_t bits = 0;
-          for (size_t a = 0; a < sm.size(); a++) bits |= ((sm[a] >> p) & 1ull) << a;
+          for (size_t a = 0; a < t.tab.size(); a++) bits |= (uint64_t)Big(t.tab[a]).bit(p) << a;
           b.cols.push_back({bg.func(leaves, bits)});
         }
       }
@@ -225,7 +274,18 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
       if (nd.kind == N_INPUT) {
         if (nd.a == 0) { set_const(i, ONE); continue; }          // get_inputs_buffer forces slot 0 to 1 (lib.rs:177-181)
         if (nd.a >= g.inputs_size) throw Fail{"input index out of range"};
-        set_leaf(i, bg.input(nd.a));                             // CONTRACT: inputs are bits (checked per input set on the device)
+        if (field_input[i]) {
+          // the 254 bits of the input reduced mod M (Fr::new, graph.rs:376): a bit vector below M, no contract
+          BV b;
+          b.hi = Big(BN254_M);
+          b.hi.v.l[0] -= 1;                                      // M - 1 (M is odd)
+          for (uint32_t p = 0; p < 254; p++) b.cols.push_back({bg.input(nd.a, p)});
+          bvs.push_back(std::move(b));
+          val[i] = Val(); val[i].k = V_BV; val[i].bv = (int32_t)bvs.size() - 1;
+          bp.has_field_inputs = true;
+          continue;
+        }
+        set_leaf(i, bg.input(nd.a, BIT_CONTRACT));               // CONTRACT: the input is a bit (checked per input set on the device)
         continue;
       }
       const int no = n_operands(nd);
@@ -354,7 +414,11 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
           val[i] = Val(); val[i].k = V_TT; val[i].tt = (int32_t)tts.size() - 1; val[i].plane = plane;
         }
         if (val[i].k == V_NONE && have_virtual) {
-          bp.n_nodes_tt++;
+          // a table of small integers (a sum of a few bits) is integer logic; a table of field-sized entries is what gives
+          // field arithmetic away (see the eligibility test at the end)
+          int width = 0;
+          for (const U256& t : virt.tab) width = std::max(width, Big(t).bits());
+          if (width <= 64) bp.n_nodes_bv++; else bp.n_nodes_tt++;
           tts.push_back(std::move(virt));
           val[i] = Val(); val[i].k = V_TT; val[i].tt = (int32_t)tts.size() - 1; val[i].plane = -1;
         }
@@ -367,11 +431,10 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
       if (ia < 0 || ib < 0) throw Fail{std::string("node ") + std::to_string(i) + ": operand of op " + std::to_string(opc) + " is not a small non-negative integer under the bit contract"};
       BV r;
       // a constant shift amount; anything >= 2^62 reads as "at least 254" (the reference's cut-off)
-      auto shift_const = [&](const Val& v, uint64_t* k) { if (v.k != V_CONST) return false; if (!u256_small(v.c, k)) { *k = 1000; } return true; };
+      auto shift_const = [&](const Val& v, uint64_t* k) { if (v.k != V_CONST) return false; const Big c(v.c); *k = c.bits() > 16 ? 1000 : c.v.l[0]; return true; };
       switch (opc) {
         case OP_ADD: {
-          if ((u128)bvs[(size_t)ia].hi + bvs[(size_t)ib].hi >= BV_LIM) throw Fail{"sum does not fit 62 bits"};
-          r.hi = bvs[(size_t)ia].hi + bvs[(size_t)ib].hi;
+          if (!Big::add(bvs[(size_t)ia].hi, bvs[(size_t)ib].hi, &r.hi) || !r.hi.below_modulus()) throw Fail{"a sum of integers can reach the modulus"};
           r.compressed = false;
           for (int side = 0; side < 2; side++) {
             const uint32_t on = o[side];
@@ -387,14 +450,13 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
           const bool ca = val[o[0]].k == V_CONST, cb = val[o[1]].k == V_CONST;
           BV& x = bvs[(size_t)(ca ? ib : ia)];
           BV& y = bvs[(size_t)(ca ? ia : ib)];
-          if ((u128)x.hi * y.hi >= BV_LIM) throw Fail{"product does not fit 62 bits"};
-          r.hi = x.hi * y.hi;
+          if (!Big::mul(x.hi, y.hi, &r.hi) || !r.hi.below_modulus()) throw Fail{"a product of integers can reach the modulus"};
           r.compressed = false;
           compress(x);
           if (ca || cb) {
-            const uint64_t c = y.hi;                            // the constant's value
-            for (int s = 0; s < bit_length(c); s++) {
-              if (!((c >> s) & 1)) continue;
+            const Big c = y.hi;                                 // the constant's value
+            for (int s = 0; s < c.bits(); s++) {
+              if (!c.bit(s)) continue;
               if (r.cols.size() < x.cols.size() + (size_t)s) r.cols.resize(x.cols.size() + (size_t)s);
               for (size_t p = 0; p < x.cols.size(); p++) { const uint32_t pl = plane_of_col(x, p); if (pl) r.cols[p + (size_t)s].push_back(pl); }
             }
@@ -414,8 +476,8 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
           if (!shift_const(val[o[1]], &k)) throw Fail{"shift by a non-constant amount"};
           const BV& x = bvs[(size_t)ia];
           if (k >= 254) break;                                 // graph.rs:621-635: b >= 254 -> 0 (r.hi stays 0)
-          if (k >= 62 || ((u128)x.hi << k) >= BV_LIM) throw Fail{"left shift does not fit 62 bits"};
-          r.hi = x.hi << k; r.compressed = x.compressed;
+          if (!Big::shl(x.hi, (uint32_t)k, &r.hi) || !r.hi.below_modulus()) throw Fail{"a left shift can reach the modulus"};
+          r.compressed = x.compressed;
           r.cols.assign((size_t)k, {});
           r.cols.insert(r.cols.end(), x.cols.begin(), x.cols.end());
           break;
@@ -425,7 +487,7 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
           if (!shift_const(val[o[1]], &k)) throw Fail{"shift by a non-constant amount"};
           BV& x = bvs[(size_t)ia];
           compress(x);
-          r.hi = k >= 62 ? 0 : (x.hi >> k);                    // graph.rs:637-672 (b >= 254 -> 0; a < 2^62 anyway)
+          r.hi = k >= 254 ? Big() : Big::shr(x.hi, (uint32_t)k);   // graph.rs:637-672 (b >= 254 -> 0)
           for (size_t p = (size_t)std::min<uint64_t>(k, x.cols.size()); p < x.cols.size(); p++) r.cols.push_back(x.cols[p]);
           break;
         }
@@ -436,15 +498,18 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
           const size_t w = opc == OP_BAND ? std::min(x.cols.size(), y.cols.size()) : std::max(x.cols.size(), y.cols.size());
           const uint32_t t4 = opc == OP_BAND ? 0x8u : opc == OP_BOR ? 0xEu : 0x6u;
           for (size_t p = 0; p < w; p++) { const uint32_t pl = bg.lut2(t4, plane_of_col(x, p), plane_of_col(y, p)); r.cols.push_back(pl ? std::vector<uint32_t>{pl} : std::vector<uint32_t>{}); }
-          if (opc == OP_BAND) r.hi = std::min(x.hi, y.hi);
-          else { uint64_t m = std::max(x.hi, y.hi), f = 0; while (f < m) f = (f << 1) | 1u; r.hi = f; }   // d < 2^62 < M: bit_or/bit_xor never reduce
+          if (opc == OP_BAND) r.hi = x.hi < y.hi ? x.hi : y.hi;
+          else {
+            r.hi = Big::ones(std::max(x.hi.bits(), y.hi.bits()));
+            if (!r.hi.below_modulus()) throw Fail{"a bitwise or/xor can reach the modulus"};     // then bit_or/bit_xor never reduce (graph.rs:689-717)
+          }
           break;
         }
         default: throw Fail{std::string("op ") + std::to_string(opc) + " on integers that are not functions of a few bits"};
       }
       bp.n_nodes_bv++;
-      if (r.hi == 0) { set_const(i, ZERO); continue; }
-      if (r.hi == 1) {                                          // a bit again (Band(x >> k, 1)): from here on a table leaf
+      if (r.hi.is_zero()) { set_const(i, ZERO); continue; }
+      if (r.hi.is_one()) {                                          // a bit again (Band(x >> k, 1)): from here on a table leaf
         compress(r);
         set_leaf(i, plane_of_col(r, 0));
         continue;
@@ -456,6 +521,7 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
 
     // ---- witness positions: bits or constants ---------------------------------------------------------------------------
     std::vector<uint32_t> out_plane(bp.n_witness, 0);
+    std::vector<uint32_t> wide_planes;                       // LUT DAG node per wide plane, stored at plane index W + k
     bp.const_of_pos.assign(bp.n_witness, -1);
     std::map<U256, int32_t> cix;
     auto const_out = [&](uint32_t j, const U256& c) {
@@ -468,8 +534,18 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
       if (v.k == V_CONST) const_out(j, v.c);
       else if (v.plane >= 2) out_plane[j] = (uint32_t)v.plane;
       else if (v.plane >= 0) const_out(j, v.plane ? ONE : ZERO);
-      else throw Fail{"a witness signal is neither a bit nor a constant under the bit contract"};
+      else if (v.k == V_BV || to_bv(g.witness_signals[j]) >= 0) {
+        // an integer of several bits (a bit heap, or a table of integers below M): its planes go behind the position
+        // planes, the expansion assembles the value
+        BV& b = bvs[(size_t)val[g.witness_signals[j]].bv];
+        compress(b);
+        bp.const_of_pos[j] = -2;
+        bp.wide.push_back(j); bp.wide.push_back((uint32_t)wide_planes.size()); bp.wide.push_back((uint32_t)b.cols.size());
+        for (size_t p = 0; p < b.cols.size(); p++) wide_planes.push_back(plane_of_col(b, p));
+      }
+      else throw Fail{"a witness signal is neither a bit, an integer below M nor a constant under the bit contract"};
     }
+    bp.plane_stride = bp.n_witness + (uint32_t)wide_planes.size();
 
     // ---- dead LUT elimination, optional merging of single-use LUTs into their reader -----------------------------------
     const size_t NB = bg.nodes.size();
@@ -477,7 +553,8 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
     auto count_fanout = [&]() {
       std::fill(fan.begin(), fan.end(), 0);
       std::vector<uint8_t> live(NB, 0);
-      for (uint32_t j = 0; j < bp.n_witness; j++) if (bp.const_of_pos[j] < 0) { live[out_plane[j]] = 1; fan[out_plane[j]]++; }
+      for (uint32_t j = 0; j < bp.n_witness; j++) if (bp.const_of_pos[j] == -1) { live[out_plane[j]] = 1; fan[out_plane[j]]++; }
+      for (uint32_t pl : wide_planes) { live[pl] = 1; fan[pl]++; }
       for (size_t b = NB; b-- > 2;) {
         if (!live[b] || bg.nodes[b].kind != BGraph::K_LUT) continue;
         for (int q = 0; q < bg.nodes[b].n; q++) { live[bg.nodes[b].in[q]] = 1; fan[bg.nodes[b].in[q]]++; }
@@ -529,7 +606,8 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
     // extra copies: a plane that sits at several witness positions, or an input plane that is a witness signal itself
     struct Emit { uint32_t node; uint32_t pos; bool copy; };
     std::vector<std::vector<uint32_t>> pos_of(NB);
-    for (uint32_t j = 0; j < bp.n_witness; j++) if (bp.const_of_pos[j] < 0) pos_of[out_plane[j]].push_back(j);
+    for (uint32_t j = 0; j < bp.n_witness; j++) if (bp.const_of_pos[j] == -1) pos_of[out_plane[j]].push_back(j);
+    for (size_t k = 0; k < wide_planes.size(); k++) pos_of[wide_planes[k]].push_back(bp.n_witness + (uint32_t)k);
     std::vector<uint32_t> step_of(NB, 0);                      // step in which the plane is written; inputs: 0 (prologue), LUTs: >= 1
     std::vector<uint32_t> level(NB, 0);
     std::vector<uint32_t> fill(2, 0);                          // LUTs per step (index = step)
@@ -567,8 +645,8 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
       for (int q = 0; q < bg.nodes[b].n; q++) last_read[bg.nodes[b].in[q]] = std::max(last_read[bg.nodes[b].in[q]], step_of[b]);
       bp.n_luts++;
     }
-    for (size_t b = 2; b < NB; b++) {
-      if (!live[b]) continue;
+    for (size_t b = 0; b < NB; b++) {
+      if (!live[b] && b >= 2) continue;
       const std::vector<uint32_t>& ps = pos_of[b];
       const bool is_lut = bg.nodes[b].kind == BGraph::K_LUT;
       for (size_t k = is_lut ? 1 : 0; k < ps.size(); k++) {
@@ -590,9 +668,11 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
       dying[last_read[b]].push_back(b);
     };
     // every input the typing looked at is checked against the contract, also those whose plane ended up unread
-    for (auto& kv : bg.input_ids) {
-      if (live[kv.second] && last_read[kv.second] > 0) take(kv.second);
-      bp.inputs.push_back(kv.first); bp.inputs.push_back(slot[kv.second]);
+    for (auto& kv : bg.input_ids) {                          // ordered by (input index, bit)
+      const bool used = live[kv.second] && last_read[kv.second] > 0;
+      if (used) take(kv.second);
+      if (!used && kv.first.second != BIT_CONTRACT) continue; // an unread bit of a field input needs no plane (and no check)
+      bp.inputs.push_back(kv.first.first); bp.inputs.push_back(slot[kv.second]); bp.inputs.push_back(kv.first.second);
     }
     bp.code.assign((size_t)bp.n_steps * 32, BitOp{0, 0, BIT_NO_SLOT << 16, BIT_NO_POS});
     for (uint32_t s = 1; s < bp.n_steps; s++) {
@@ -613,6 +693,14 @@ BitPlan compile_bit_plan(const Graph& g, const BitPlanOptions& opt) {
       for (uint32_t b : dying[s]) free_slots.push_back(slot[b]);
     }
     bp.n_slots = n_slots;
+    // A graph of field arithmetic is "Boolean" too if one pretends that its inputs are bits -- every node is then a table
+    // of field values over a few bits -- but nobody feeds such a graph bits.  Its typing gives it away: (almost) no node
+    // is a bit or an integer, everything is a table (Poseidon(1): 600 tables, no bit), or 254-bit table entries get
+    // synthesised into thousands of LUTs per operation.  Not worth a speculation.
+    size_t live_ops = 0;
+    for (size_t i = 0; i < N; i++) live_ops += needed[i] && g.nodes[i].kind >= N_UNO;
+    if ((bp.n_nodes_bit + bp.n_nodes_bv) * 8 < bp.n_nodes_tt || bp.n_luts > 8 * live_ops + 64)
+      throw Fail{"the operations of this graph are field arithmetic, not logic: its inputs are hardly meant to be bits"};
     bp.eligible = true;
   } catch (const Fail& f) {
     bp.eligible = false;

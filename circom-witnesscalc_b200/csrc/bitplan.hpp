@@ -11,7 +11,7 @@
 //       TT(support, table)         a function of <= 6 bit-valued nodes given by its table of FIELD values, computed with
 //                                  the exact op semantics of alu.cuh (this is what proves circomlib's polynomial gates
 //                                  a*(1-2b-2c+4bc)+b+c-2bc bit-valued: interval arithmetic loses the correlation),
-//       BV                         a non-negative integer < 2^62 held as bit planes (BinSum's `lin`, the word arithmetic
+//       BV                         a non-negative integer below M held as bit planes (BinSum's `lin`, the word arithmetic
 //                                  of sha256compression_function.circom); sums stay a bit heap until somebody looks at
 //                                  their bits and are then compressed with full adders (carry-save, not ripple per term);
 //     anything else makes the graph ineligible (the throughput plan runs it as before).
@@ -36,6 +36,7 @@ struct BitOp { uint32_t x, y, z, w; };   // x: lut[7:0]; y: slot a | slot b << 1
 static const uint32_t BIT_NO_SLOT = 0xFFFFu;
 static const uint32_t BIT_NO_POS = 0xFFFFFFFFu;
 static const uint32_t BIT_SLOT_ZERO = 0, BIT_SLOT_ONES = 1;   // fixed planes: all zeros, all ones
+static const uint32_t BIT_CONTRACT = 0xFFFFFFFFu;
 
 struct BitPlanOptions {
   uint32_t max_support = 6;      // table size limit of the TT domain (2^6 field values)
@@ -47,11 +48,19 @@ struct BitPlan {
   bool eligible = false;
   std::string reason;            // why not, when not eligible
   uint32_t n_inputs = 0, n_witness = 0;
-  std::vector<uint32_t> inputs;  // pairs (input index, plane slot) of the live inputs: packed and CHECKED (bit contract) per input set
+  // triples (input index, plane slot or BIT_NO_SLOT, bit): bit = BIT_CONTRACT: the input must be 0 or 1 (checked per input
+  // set) and is its own plane; otherwise the plane is bit `bit` of the input reduced mod M (an input that is only ever
+  // taken apart with Shr/Band -- Num2Bits of a field element -- carries no contract).  Sorted by input index.
+  std::vector<uint32_t> inputs;
+  bool has_field_inputs = false;
   std::vector<BitOp> code;       // n_steps x 32 LUT instructions, one per lane (padding: dst = BIT_NO_SLOT, w = BIT_NO_POS)
   uint32_t n_steps = 0, n_slots = 2;
-  std::vector<int32_t> const_of_pos;   // per witness position: -1 = a bit plane, else index into const_vals
+  std::vector<int32_t> const_of_pos;   // per witness position: -1 = a bit plane, -2 = a wide value (below), else index into const_vals
   std::vector<U256> const_vals;
+  // witness values that are integers of several bits (Bits2Num sums, field inputs passed through): their planes are
+  // stored behind the W position planes of a group, at W + base + bit.  Triples (position, base, number of planes).
+  std::vector<uint32_t> wide;
+  uint32_t plane_stride = 0;     // plane words per group: n_witness + all wide planes
   // statistics
   uint64_t n_luts = 0, n_levels = 0, n_nodes_bit = 0, n_nodes_tt = 0, n_nodes_bv = 0, n_full_adders = 0, n_merged = 0;
 };

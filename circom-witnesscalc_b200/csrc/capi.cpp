@@ -143,6 +143,9 @@ int gw_graph_info(const gw_graph_t* graph, gw_graph_info_t* info) {
   info->n_inversions = (uint32_t)p.stats.inversions;
   info->threads = (uint32_t)graph->engine->max_threads; info->sets_per_thread = 1;
   info->n_narrow_instr = (uint32_t)p.stats.narrow_instrs;
+  const BitPlan& bp = graph->engine->bit_plan;
+  info->bit_eligible = graph->engine->bit_path_active() ? 1u : 0u;
+  info->bit_luts = (uint32_t)bp.n_luts; info->bit_steps = bp.n_steps; info->bit_wide = (uint32_t)(bp.wide.size() / 3);
   return 0;
 }
 

@@ -267,12 +267,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
 // input is 0 or 1); input sets that break it are handed to eval_batch_kernel through bad_list.
 struct BParams {
   const uint4* code; uint32_t n_steps, n_slots;
-  const uint2* in_list; uint32_t n_in;      // (input index, plane slot or BIT_NO_SLOT) of every input the typing looked at
+  const uint4* in_list; uint32_t n_in;      // {input index, plane slot or BIT_NO_SLOT, bit or BIT_CONTRACT, 0}, sorted by input index
   const uint4* inputs;                      // [B][I][2]
   uint32_t I, W;
   unsigned long long B;
   uint32_t n_groups;
-  uint32_t* planes;                         // [n_groups][W]: plane word of every witness position
+  uint32_t* planes; uint32_t plane_stride;  // [n_groups][plane_stride]: plane word of every witness position, then the planes of the wide values
   uint32_t* ok_words;                       // [n_groups]: bit k = input set 32 g + k satisfies the contract
   uint32_t* bad_list; uint32_t* n_bad;      // the other input sets, for the fallback launch
   uint32_t* status;                         // [B] or null (per-set flags: 0 for every set evaluated here)
@@ -301,17 +301,31 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   const unsigned long long row = (unsigned long long)g * 32u + lane;
   const bool in_range = row < p.B;
   if (lane == 0) { S[BIT_SLOT_ZERO] = 0u; S[BIT_SLOT_ONES] = 0xFFFFFFFFu; }
-  // pack + contract check: lane = input set
+  // pack + contract check: lane = input set.  A contract input must be 0 or 1 and is its own plane; of a field input
+  // (taken apart by the graph with Shr/Band) the planes are bits of the value reduced mod M, whatever the value.
   const uint4* in = p.inputs + (in_range ? row : 0ull) * p.I * 2;
   bool ok = in_range;
-#pragma unroll 4
+  uint32_t cur = 0xFFFFFFFFu;
+  fe v = fe_zero();
   for (uint32_t k = 0; k < p.n_in; k++) {
-    const uint2 e = __ldg(p.in_list + k);
-    const uint4 lo = __ldg(in + 2 * (size_t)e.x), hi = __ldg(in + 2 * (size_t)e.x + 1);
-    const bool is_bit = (lo.x <= 1u) && ((lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) == 0u);
-    ok = ok && is_bit;
-    const uint32_t word = __ballot_sync(0xFFFFFFFFu, in_range && (lo.x & 1u));
-    if (lane == 0 && e.y != BIT_NO_SLOT) S[e.y] = word;
+    const uint4 e = __ldg(p.in_list + k);                  // uniform
+    if (e.z == BIT_CONTRACT) {
+      const uint4 lo = __ldg(in + 2 * (size_t)e.x), hi = __ldg(in + 2 * (size_t)e.x + 1);
+      const bool is_bit = (lo.x <= 1u) && ((lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) == 0u);
+      ok = ok && is_bit;
+      const uint32_t word = __ballot_sync(0xFFFFFFFFu, in_range && (lo.x & 1u));
+      if (lane == 0 && e.y != BIT_NO_SLOT) S[e.y] = word;
+    } else {
+      if (e.x != cur) {                                    // Fr::new (graph.rs:376): the planes are bits of the canonical value
+        cur = e.x;
+        v = fe_reduce256(fe_from(__ldg(in + 2 * (size_t)e.x), __ldg(in + 2 * (size_t)e.x + 1)));
+      }
+      uint32_t limb = 0;
+#pragma unroll
+      for (uint32_t q = 0; q < 8; q++) limb = (q == (e.z >> 5)) ? v.l[q] : limb;
+      const uint32_t word = __ballot_sync(0xFFFFFFFFu, in_range && ((limb >> (e.z & 31u)) & 1u));
+      if (lane == 0) S[e.y] = word;
+    }
   }
   const uint32_t okw = __ballot_sync(0xFFFFFFFFu, ok);
   if (lane == 0) p.ok_words[g] = okw;
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   if (p.status != nullptr && ok) p.status[row] = 0u;
   if (okw == 0u) return;                                   // nobody in this group honours the contract
   __syncwarp();
-  uint32_t* planes = p.planes + (size_t)g * p.W;
+  uint32_t* planes = p.planes + (size_t)g * p.plane_stride;
   // the headers of the next BIT_PREFETCH steps are in flight while a step executes: one L2 round trip per step would
   // otherwise be the whole cost of a step (a handful of warps per SM cannot hide it)
   const uint32_t last = p.n_steps - 1u;
@@ -348,7 +362,8 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
 // witness row with two 512-byte coalesced streaming stores: the HBM-bound part of the bit-sliced path.
 __global__ void __launch_bounds__(256) bit_expand_kernel(const uint32_t* __restrict__ planes, const uint32_t* __restrict__ ok_words,
                                                          const int32_t* __restrict__ const_of_pos, const uint4* __restrict__ consts,
-                                                         uint4* __restrict__ out, uint32_t W, uint32_t n_groups, uint32_t tiles_per_group) {
+                                                         uint4* __restrict__ out, uint32_t W, uint32_t plane_stride, uint32_t n_groups,
+                                                         uint32_t tiles_per_group) {
   const uint32_t lane = threadIdx.x & 31u;
   const unsigned long long t = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const uint32_t g = (uint32_t)(t / tiles_per_group);
@@ -356,7 +371,7 @@ __global__ void __launch_bounds__(256) bit_expand_kernel(const uint32_t* __restr
   const uint32_t j0 = (uint32_t)(t % tiles_per_group) * 32u, j = j0 + lane;
   const uint32_t okw = __ldg(ok_words + g);
   if (okw == 0u) return;
-  const uint32_t word = j < W ? __ldg(planes + (size_t)g * W + j) : 0u;
+  const uint32_t word = j < W ? __ldg(planes + (size_t)g * plane_stride + j) : 0u;
   const int32_t cidx = j < W ? __ldg(const_of_pos + j) : -1;
   const uint32_t half = lane & 1u;
   for (uint32_t w = 0; w < 32u; w++) {
@@ -367,12 +382,40 @@ __global__ void __launch_bounds__(256) bit_expand_kernel(const uint32_t* __restr
       const uint32_t pz = h * 16u + (lane >> 1);
       const uint32_t wv = __shfl_sync(0xFFFFFFFFu, word, pz);
       const int32_t ci = __shfl_sync(0xFFFFFFFFu, cidx, pz);
-      if (j0 + pz < W) {
+      if (j0 + pz < W && ci != -2) {                           // -2: a wide value, written by bit_expand_wide_kernel
         uint4 v = make_uint4(half ? 0u : ((wv >> w) & 1u), 0u, 0u, 0u);
         if (ci >= 0) v = __ldg(consts + 2 * (size_t)ci + half);
         __stcs(row + 2 * (size_t)(j0 + pz) + half, v);
       }
     }
+  }
+}
+
+// Witness values that are integers of several bits (Bits2Num sums, field inputs passed through): one warp per (group,
+// wide value) transposes up to 256 planes into the 8 limbs of each of the group's 32 input sets.
+__global__ void __launch_bounds__(256) bit_expand_wide_kernel(const uint32_t* __restrict__ planes, const uint32_t* __restrict__ ok_words,
+                                                              const uint4* __restrict__ wide, uint32_t n_wide, uint32_t* __restrict__ out,
+                                                              uint32_t W, uint32_t plane_stride, uint32_t n_groups) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const unsigned long long t = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t g = (uint32_t)(t / n_wide);
+  if (g >= n_groups) return;
+  const uint4 d = __ldg(wide + (uint32_t)(t % n_wide));      // {position, base, number of planes, 0}
+  const uint32_t okw = __ldg(ok_words + g);
+  if (okw == 0u) return;
+  const uint32_t* src = planes + (size_t)g * plane_stride + W + d.y;
+  uint32_t P[8];
+#pragma unroll
+  for (uint32_t m = 0; m < 8; m++) P[m] = (32u * m + lane < d.z) ? __ldg(src + 32u * m + lane) : 0u;
+  for (uint32_t w = 0; w < 32u; w++) {
+    if (!((okw >> w) & 1u)) continue;
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t m = 0; m < 8; m++) {
+      const uint32_t limb = __ballot_sync(0xFFFFFFFFu, (P[m] >> w) & 1u);
+      mine = lane == m ? limb : mine;
+    }
+    if (lane < 8u) out[(((size_t)g * 32u + w) * W + d.x) * 8u + lane] = mine;
   }
 }
 
@@ -743,9 +786,11 @@ struct Engine::Dev {
   uint8_t* h_ring[3] = {nullptr, nullptr, nullptr}; uint32_t* h_flags[3] = {nullptr, nullptr, nullptr};
   size_t h_ring_bytes = 0, h_flags_n = 0;
   // bit-sliced path (bitplan.hpp): program tables, and per-launch scratch that grows with the largest batch seen
-  uint4* bit_code = nullptr; uint2* bit_inputs = nullptr; int32_t* bit_constpos = nullptr; uint4* bit_consts = nullptr;
+  uint4* bit_code = nullptr; uint4* bit_inputs = nullptr; int32_t* bit_constpos = nullptr; uint4* bit_consts = nullptr; uint4* bit_wide = nullptr;
   uint32_t* bit_planes = nullptr; uint32_t* bit_ok = nullptr; uint32_t* bit_bad = nullptr; uint32_t* bit_nbad = nullptr;
   size_t bit_groups = 0;
+  // feedback for the speculation on the bit contract: how many input sets of the last bit-sliced launch broke it
+  uint32_t* bit_nbad_host = nullptr; cudaEvent_t bit_nbad_ev = nullptr; size_t bit_nbad_sets = 0; bool bit_nbad_pending = false;
   // single-witness latency mode
   uint4* lat_code = nullptr; uint4* lat_first = nullptr; uint4* lat_jobs = nullptr; uint32_t* lat_njobs = nullptr; uint4* lat_waits = nullptr;
   unsigned long long* lat_clock = nullptr;
@@ -838,8 +883,9 @@ Engine::~Engine() {
     cudaGetDevice(&prev);
     cudaSetDevice(d->device);
     cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
-    cudaFree(d->bit_code); cudaFree(d->bit_inputs); cudaFree(d->bit_constpos); cudaFree(d->bit_consts);
+    cudaFree(d->bit_code); cudaFree(d->bit_inputs); cudaFree(d->bit_constpos); cudaFree(d->bit_consts); cudaFree(d->bit_wide);
     cudaFree(d->bit_planes); cudaFree(d->bit_ok); cudaFree(d->bit_bad); cudaFree(d->bit_nbad);
+    cudaFreeHost(d->bit_nbad_host); if (d->bit_nbad_ev) cudaEventDestroy(d->bit_nbad_ev);
     cudaFree(d->lat_code); cudaFree(d->lat_first); cudaFree(d->lat_jobs); cudaFree(d->lat_njobs); cudaFree(d->lat_waits); cudaFree(d->lat_clock); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
     for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
     for (int i = 0; i < 3; i++) { cudaFreeHost(d->h_ring[i]); cudaFreeHost(d->h_flags[i]); }
@@ -882,13 +928,21 @@ Engine::Dev* Engine::dev(int device) {
     CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
     CUDA_CHECK(cudaMalloc(&d->bit_code, bp.code.size() * sizeof(BitOp)));
     CUDA_CHECK(cudaMemcpy(d->bit_code, bp.code.data(), bp.code.size() * sizeof(BitOp), cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMalloc(&d->bit_inputs, std::max<size_t>(bp.inputs.size(), 2) * 4));
-    CUDA_CHECK(cudaMemcpy(d->bit_inputs, bp.inputs.data(), bp.inputs.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> quads;                             // triples padded to 16 bytes
+    for (size_t k = 0; k + 2 < bp.inputs.size(); k += 3) { quads.push_back(bp.inputs[k]); quads.push_back(bp.inputs[k + 1]); quads.push_back(bp.inputs[k + 2]); quads.push_back(0); }
+    CUDA_CHECK(cudaMalloc(&d->bit_inputs, std::max<size_t>(quads.size(), 4) * 4));
+    CUDA_CHECK(cudaMemcpy(d->bit_inputs, quads.data(), quads.size() * 4, cudaMemcpyHostToDevice));
+    quads.clear();
+    for (size_t k = 0; k + 2 < bp.wide.size(); k += 3) { quads.push_back(bp.wide[k]); quads.push_back(bp.wide[k + 1]); quads.push_back(bp.wide[k + 2]); quads.push_back(0); }
+    CUDA_CHECK(cudaMalloc(&d->bit_wide, std::max<size_t>(quads.size(), 4) * 4));
+    CUDA_CHECK(cudaMemcpy(d->bit_wide, quads.data(), quads.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&d->bit_constpos, std::max<size_t>(bp.const_of_pos.size(), 1) * 4));
     CUDA_CHECK(cudaMemcpy(d->bit_constpos, bp.const_of_pos.data(), bp.const_of_pos.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&d->bit_consts, std::max<size_t>(bp.const_vals.size(), 1) * 32));
     CUDA_CHECK(cudaMemcpy(d->bit_consts, bp.const_vals.data(), bp.const_vals.size() * 32, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&d->bit_nbad, 4));
+    CUDA_CHECK(cudaHostAlloc(&d->bit_nbad_host, 4, cudaHostAllocDefault));
+    CUDA_CHECK(cudaEventCreateWithFlags(&d->bit_nbad_ev, cudaEventDisableTiming));
   }
   devs[device] = d.get();
   return d.release();
@@ -908,7 +962,7 @@ void Engine::launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness,
     // scratch of the largest batch seen; cudaFree waits for the kernels that still use the old one
     cudaFree(d->bit_planes); d->bit_planes = nullptr; cudaFree(d->bit_ok); d->bit_ok = nullptr; cudaFree(d->bit_bad); d->bit_bad = nullptr;
     d->bit_groups = 0;
-    CUDA_CHECK(cudaMalloc(&d->bit_planes, n_groups * (size_t)std::max<uint32_t>(bp.n_witness, 1) * 4));
+    CUDA_CHECK(cudaMalloc(&d->bit_planes, n_groups * (size_t)std::max<uint32_t>(bp.plane_stride, 1) * 4));
     CUDA_CHECK(cudaMalloc(&d->bit_ok, n_groups * 4));
     CUDA_CHECK(cudaMalloc(&d->bit_bad, n_groups * 32 * 4));
     d->bit_groups = n_groups;
@@ -916,9 +970,9 @@ void Engine::launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness,
   CUDA_CHECK(cudaMemsetAsync(d->bit_nbad, 0, 4, s));
   BParams q;
   q.code = d->bit_code; q.n_steps = bp.n_steps; q.n_slots = bp.n_slots;
-  q.in_list = d->bit_inputs; q.n_in = (uint32_t)(bp.inputs.size() / 2);
+  q.in_list = d->bit_inputs; q.n_in = (uint32_t)(bp.inputs.size() / 3);
   q.inputs = (const uint4*)d_inputs; q.I = bp.n_inputs; q.W = bp.n_witness; q.B = B; q.n_groups = (uint32_t)n_groups;
-  q.planes = d->bit_planes; q.ok_words = d->bit_ok; q.bad_list = d->bit_bad; q.n_bad = d->bit_nbad; q.status = d_status;
+  q.planes = d->bit_planes; q.plane_stride = bp.plane_stride; q.ok_words = d->bit_ok; q.bad_list = d->bit_bad; q.n_bad = d->bit_nbad; q.status = d_status;
   // warps per CTA: as many as the plane files allow, but enough CTAs to cover the SMs twice
   int wpb = (int)std::min<size_t>(8, d->smem_max / ((size_t)bp.n_slots * 4));
   while (wpb > 1 && n_groups < (size_t)wpb * 2 * (size_t)d->sms) wpb--;
@@ -931,14 +985,28 @@ void Engine::launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness,
   const unsigned long long n_warp_tiles = (unsigned long long)n_groups * tiles;
   if (n_warp_tiles) {
     bit_expand_kernel<<<(unsigned)((n_warp_tiles + 7) / 8), 256, 0, s>>>(d->bit_planes, d->bit_ok, d->bit_constpos, d->bit_consts, (uint4*)d_witness,
-                                                                        bp.n_witness, (uint32_t)n_groups, tiles);
+                                                                        bp.n_witness, bp.plane_stride, (uint32_t)n_groups, tiles);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  const uint32_t n_wide = (uint32_t)(bp.wide.size() / 3);
+  if (n_wide) {
+    const unsigned long long n_warps = (unsigned long long)n_groups * n_wide;
+    bit_expand_wide_kernel<<<(unsigned)((n_warps + 7) / 8), 256, 0, s>>>(d->bit_planes, d->bit_ok, d->bit_wide, n_wide, (uint32_t*)d_witness,
+                                                                        bp.n_witness, bp.plane_stride, (uint32_t)n_groups);
     CUDA_CHECK(cudaGetLastError());
   }
 }
 
 void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream) {
   if (B == 0 || plan.code.empty()) return;
-  const bool bit = use_bit_path() && B >= (size_t)env_int("GW_BIT_MIN_SETS", 1);
+  // The bit-sliced plan speculates that the inputs under its contract are bits.  When most input sets of a launch were
+  // not (somebody feeds field elements to a graph that would also work on bits), the speculation is dropped for this
+  // graph: such batches would pay for both paths.  The count arrives asynchronously; it is looked at on the next launch.
+  if (d->bit_nbad_pending && cudaEventQuery(d->bit_nbad_ev) == cudaSuccess) {
+    d->bit_nbad_pending = false;
+    if (d->bit_nbad_sets >= 64 && (size_t)*d->bit_nbad_host * 2 > d->bit_nbad_sets) bit_disabled.store(true);
+  }
+  const bool bit = use_bit_path() && !bit_disabled.load() && B >= (size_t)env_int("GW_BIT_MIN_SETS", 1);
   if (bit) launch_bit(d, d_inputs, B, d_witness, d_status, stream);
   KParams p;
   p.row_map = bit ? d->bit_bad : nullptr; p.n_dev = bit ? d->bit_nbad : nullptr;
@@ -963,6 +1031,11 @@ void Engine::launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uin
   eval_batch_kernel<<<grid, T, base + (size_t)p.n_hot * 32, (cudaStream_t)stream>>>(p);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(d->last_kernel, (cudaStream_t)stream));
+  if (bit && !d->bit_nbad_pending) {
+    CUDA_CHECK(cudaMemcpyAsync(d->bit_nbad_host, d->bit_nbad, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_CHECK(cudaEventRecord(d->bit_nbad_ev, (cudaStream_t)stream));
+    d->bit_nbad_sets = B; d->bit_nbad_pending = true;
+  }
 }
 
 int Engine::device_max_threads(int device) { return dev(device)->max_threads; }

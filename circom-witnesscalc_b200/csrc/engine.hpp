@@ -2,6 +2,7 @@
 // This is the persistent state the reference does not have (it re-parses the graph on every
 // calc_witness call, /root/reference/src/lib.rs:129-130).
 #pragma once
+#include <atomic>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -23,6 +24,7 @@ class Engine {
   Graph graph;
   Plan plan;
   BitPlan bit_plan;           // bit-sliced plan (bitplan.hpp); used by every batch launch when eligible (GW_BITSLICE=0: never)
+  std::atomic<bool> bit_disabled{false};   // set when most input sets of a launch broke the bit contract (engine.cu: launch)
   int max_threads = 512;      // upper bound of threads per CTA (GW_THREADS); one persistent CTA per SM
   int threads_for(size_t B, int sms, int t_max) const;
   int device_max_threads(int device);   // threads per CTA (= input sets per SM and wave) the device allows for this plan
@@ -41,6 +43,9 @@ class Engine {
   void run_stream(const uint8_t* inputs, size_t B, int n_gpus, int first_device, size_t chunk_sets, const ChunkFn& fn);
   // single witness, latency mode (one CTA, intra-level node parallelism); host buffers
   void run_latency(int device, const uint8_t* inputs, uint8_t* witness, uint32_t* status, float* kernel_ms);
+  // a plan without LUTs is pure wiring: worth it only when field inputs are taken apart into bits (Num2Bits of a field element)
+  bool use_bit_path() const { return bit_plan.eligible && (bit_plan.n_luts > 0 || bit_plan.has_field_inputs); }
+  bool bit_path_active() const { return use_bit_path() && !bit_disabled.load(); }
   LatencyPlan lat_plan;
   bool lat_ready = false;
   std::string lat_error;      // why the latency plan could not be built (remembered: the compile is not repeated per call)
@@ -49,7 +54,6 @@ class Engine {
   struct Dev;
   Dev* dev(int device);
   void launch(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
-  bool use_bit_path() const { return bit_plan.eligible && bit_plan.n_luts > 0; }
   void launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness, uint32_t* d_status, void* stream);
   void ensure_staging(Dev* d, size_t chunk);
   void stream_on(int device, const uint8_t* inputs, size_t B, size_t first_set, size_t chunk_req, const ChunkFn& fn);

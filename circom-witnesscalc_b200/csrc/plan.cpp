@@ -862,6 +862,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
 
   bool use_chain = lo.chain;
   const int dbg_level = getenv("GW_LAT_DEBUG") ? atoi(getenv("GW_LAT_DEBUG")) : -1;
+  const uint32_t dbg_count = getenv("GW_LAT_DEBUG_N") ? (uint32_t)atoi(getenv("GW_LAT_DEBUG_N")) : 24u;
   auto schedule = [&](const uint32_t D) {
     LatencyPlan lp;
     lp.n_inputs = g0.inputs_size;
@@ -1209,7 +1210,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       }
       for (const auto& pw : pending_waits[L]) { lp.waits.push_back(n_phys - 1); lp.waits.push_back(pw[0]); lp.waits.push_back(pw[1]); lp.waits.push_back(0); }
       lp.est_cycles += (uint64_t)worst + LAT_LEVEL_OVERHEAD;
-      if (dbg_level >= 0 && L >= (uint32_t)dbg_level && L < (uint32_t)dbg_level + 24) {      // GW_LAT_DEBUG=<level>: dump 24 levels of the schedule
+      if (dbg_level >= 0 && L >= (uint32_t)dbg_level && L < (uint32_t)dbg_level + dbg_count) {      // GW_LAT_DEBUG=<level>: dump 24 (GW_LAT_DEBUG_N) levels of the schedule
         fprintf(stderr, "L%u worst %.0f:", L, worst);
         for (uint32_t w = 0; w < lo.n_warps; w++) { fprintf(stderr, " w%u[", w); for (const LOp* o : per_warp[w]) fprintf(stderr, "%llx ", (unsigned long long)lat_class(*o)); fprintf(stderr, "]"); }
         fprintf(stderr, "\n");

@@ -76,6 +76,11 @@ typedef struct {
   uint32_t threads;       /* threads per CTA */
   uint32_t sets_per_thread; /* input sets evaluated per thread */
   uint32_t n_narrow_instr; /* instructions computed on int64 (values the plan compiler proves to be small, isa.h F_NARROW) */
+  /* bit-sliced plan (Boolean graphs: 32 input sets per machine word, one 3-input LUT per lane) */
+  uint32_t bit_eligible;  /* 1: batch launches of this graph run bit-sliced (input sets that break the bit contract: generic kernel) */
+  uint32_t bit_luts;      /* LUT instructions per group of 32 input sets */
+  uint32_t bit_steps;     /* steps of 32 LUTs */
+  uint32_t bit_wide;      /* witness values assembled from several planes (Bits2Num sums, field inputs passed through) */
 } gw_graph_info_t;
 
 /* replaces storage::deserialize_witnesscalc_graph (src/storage.rs:214-249) + upload; parse once */

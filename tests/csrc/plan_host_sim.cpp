@@ -331,7 +331,8 @@ void sim_bit_free(BitSim* s) { delete s; }
 void sim_bit_info(BitSim* s, uint64_t* out) {
   const BitPlan& b = s->bp;
   out[0] = b.eligible; out[1] = b.n_steps; out[2] = b.n_slots; out[3] = b.n_luts; out[4] = b.n_levels; out[5] = b.n_nodes_bit;
-  out[6] = b.n_nodes_tt; out[7] = b.n_nodes_bv; out[8] = b.n_full_adders; out[9] = b.n_merged; out[10] = b.inputs.size() / 2; out[11] = b.const_vals.size();
+  out[6] = b.n_nodes_tt; out[7] = b.n_nodes_bv; out[8] = b.n_full_adders; out[9] = b.n_merged; out[10] = b.inputs.size() / 3; out[11] = b.const_vals.size();
+  out[12] = b.has_field_inputs; out[13] = b.wide.size() / 3; out[14] = b.plane_stride;
 }
 // inputs: n x I x 32 B (n <= 32), witness: n x W x 32 B; returns the mask of input sets that satisfy the bit contract
 // (only their rows are written), or -1 on a malformed plan
@@ -341,20 +342,28 @@ int64_t sim_bit_eval(BitSim* s, const uint8_t* inputs, uint32_t n, uint8_t* witn
   std::vector<uint32_t> S(b.n_slots, 0);
   S[BIT_SLOT_ONES] = 0xFFFFFFFFu;
   uint32_t ok = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
-  for (size_t k = 0; k < b.inputs.size(); k += 2) {
-    const uint32_t idx = b.inputs[k], slot = b.inputs[k + 1];
+  for (size_t k = 0; k + 2 < b.inputs.size() + 0 && k < b.inputs.size(); k += 3) {
+    const uint32_t idx = b.inputs[k], slot = b.inputs[k + 1], bit = b.inputs[k + 2];
     if (idx >= b.n_inputs) return -1;
     uint32_t word = 0;
     for (uint32_t w = 0; w < n; w++) {
       const uint8_t* v = inputs + ((size_t)w * b.n_inputs + idx) * 32;
-      bool is_bit = v[0] <= 1;
-      for (int q = 1; q < 32; q++) is_bit &= v[q] == 0;
-      if (!is_bit) ok &= ~(1u << w);
-      word |= (uint32_t)(v[0] & 1) << w;
+      if (bit == BIT_CONTRACT) {
+        bool is_bit = v[0] <= 1;
+        for (int q = 1; q < 32; q++) is_bit &= v[q] == 0;
+        if (!is_bit) ok &= ~(1u << w);
+        word |= (uint32_t)(v[0] & 1) << w;
+      } else {
+        if (bit >= 254) return -1;
+        fe x; memcpy(x.l, v, 32);
+        x = fe_reduce256(x);                                     // Fr::new (graph.rs:376)
+        word |= ((x.l[bit >> 5] >> (bit & 31)) & 1u) << w;
+      }
     }
     if (slot != BIT_NO_SLOT) { if (slot >= b.n_slots) return -1; S[slot] = word; }
   }
-  std::vector<uint32_t> planes(b.n_witness, 0);
+  if (b.plane_stride < b.n_witness) return -1;
+  std::vector<uint32_t> planes(b.plane_stride, 0);
   for (uint32_t st = 0; st < b.n_steps; st++) {
     uint32_t res[32]; 
     for (uint32_t lane = 0; lane < 32; lane++) {                 // all lanes read ...
@@ -367,7 +376,7 @@ int64_t sim_bit_eval(BitSim* s, const uint8_t* inputs, uint32_t n, uint8_t* witn
       const BitOp& op = b.code[(size_t)st * 32 + lane];
       const uint32_t dst = op.z >> 16;
       if (dst != BIT_NO_SLOT) { if (dst >= b.n_slots || dst < 2) return -1; S[dst] = res[lane]; }
-      if (op.w != BIT_NO_POS) { if (op.w >= b.n_witness) return -1; planes[op.w] = res[lane]; }
+      if (op.w != BIT_NO_POS) { if (op.w >= b.plane_stride) return -1; planes[op.w] = res[lane]; }
     }
   }
   for (uint32_t w = 0; w < n; w++) {
@@ -375,7 +384,14 @@ int64_t sim_bit_eval(BitSim* s, const uint8_t* inputs, uint32_t n, uint8_t* witn
     for (uint32_t j = 0; j < b.n_witness; j++) {
       uint8_t* dst = witness + ((size_t)w * b.n_witness + j) * 32;
       if (b.const_of_pos[j] >= 0) memcpy(dst, b.const_vals[(size_t)b.const_of_pos[j]].l, 32);
-      else { memset(dst, 0, 32); dst[0] = (planes[j] >> w) & 1; }
+      else if (b.const_of_pos[j] == -1) { memset(dst, 0, 32); dst[0] = (planes[j] >> w) & 1; }
+    }
+    for (size_t q = 0; q + 2 < b.wide.size() + 0 && q < b.wide.size(); q += 3) {
+      const uint32_t pos = b.wide[q], base = b.wide[q + 1], np = b.wide[q + 2];
+      if (pos >= b.n_witness || np > 256 || b.n_witness + base + np > b.plane_stride) return -1;
+      uint8_t* dst = witness + ((size_t)w * b.n_witness + pos) * 32;
+      memset(dst, 0, 32);
+      for (uint32_t p = 0; p < np; p++) dst[p >> 3] |= (uint8_t)(((planes[b.n_witness + base + p] >> w) & 1u) << (p & 7));
     }
   }
   return (int64_t)ok;

@@ -144,16 +144,19 @@ def test_sha256_is_all_bits_and_exact():
         assert res[b] == po.evaluate(nodes, rows[b], wit)
 
 
-@pytest.mark.parametrize("name", ["circuit1", "circuit2", "circuit5_poseidon", "circuit9_authV2", "circuit11_key_expansion"])
+@pytest.mark.parametrize("name", ["circuit5_poseidon", "circuit7_poseidon4", "poseidon2", "circuit9_authV2", "circuit11_key_expansion"])
 def test_field_graphs_are_not_eligible(name):
+    """field arithmetic on the inputs (Poseidon: every value would be a 254-bit table entry of a few "bit" inputs; authV2:
+    sums that can reach the modulus; circuit11: comparisons of integers)"""
     g = util.BitSimGraph(util.golden_graph(name))
     assert not g.info["eligible"] and g.reason
 
 
 def test_degenerate_plans_and_edge_graphs():
-    # Num2Bits of ONE field input: under the bit contract it collapses to wiring (no LUTs) -> the engine keeps the generic path
+    # Num2Bits + Bits2Num of ONE field input: pure wiring (no LUTs), the input is taken apart into the bits of its canonical
+    # value (no contract), `out` and the input itself are wide witness values
     g = util.BitSimGraph(util.golden_graph("circuit6_num2bits"))
-    assert g.info["eligible"] and g.info["n_luts"] == 0
+    assert g.info["eligible"] and g.info["n_luts"] == 0 and g.info["has_field_inputs"] and g.info["n_wide"] == 2
     # a plane at several witness positions, an input that is a witness signal itself, constants, an input nobody reads
     nodes = [(po.K_INPUT, 0), (po.K_INPUT, 1), (po.K_INPUT, 2), (po.K_INPUT, 3), (po.K_DUO, po.DUO["Mul"], 1, 2), (po.K_CONST, 5),
              (po.K_DUO, po.DUO["Mul"], 3, 3), (po.K_DUO, po.DUO["Sub"], 6, 3)]
@@ -165,6 +168,75 @@ def test_degenerate_plans_and_edge_graphs():
     assert ok == 0xFF                                 # x*x - x is 0 for bits only: the set with x = 5 must not take this path
     for b in range(8):
         assert res[b] == po.evaluate(nodes, rows[b], wit)
-    # a witness signal that is a small integer, not a bit: not eligible
+    # a witness signal that is a small integer, not a bit: a wide witness value
     nodes = [(po.K_INPUT, 0), (po.K_INPUT, 1), (po.K_INPUT, 2), (po.K_DUO, po.DUO["Add"], 1, 2)]
-    assert not util.BitSimGraph(po.serialize_graph(nodes, [0, 3], {"x": (1, 2)})).info["eligible"]
+    g = util.BitSimGraph(po.serialize_graph(nodes, [0, 3], {"x": (1, 2)}))
+    assert g.info["eligible"] and g.info["n_wide"] == 1
+    res, ok = g.eval([[1, 1, 1], [1, 0, 1], [1, 2, 0]])
+    assert ok == 3 and res[0] == [1, 2] and res[1] == [1, 1]
+
+
+def field_bits_graph(rnd: random.Random, n_field=3, n_bits=6, n_gates=80):
+    """Field inputs that the graph only takes apart (Num2Bits: (x >> k) & 1, masks) next to contract bits: logic on the
+    extracted bits, Bits2Num-style recomposition up to 250 bits (wide witness values), the inputs themselves as witness
+    signals.  Returns (nodes, witness_signals, input_map)."""
+    n_inputs = n_field + n_bits
+    nodes = [(po.K_INPUT, i) for i in range(n_inputs + 1)]
+    cache = {}
+
+    def const(v):
+        if v % M not in cache:
+            nodes.append((po.K_CONST, v % M))
+            cache[v % M] = len(nodes) - 1
+        return cache[v % M]
+
+    def duo(op, a, b):
+        nodes.append((po.K_DUO, po.DUO[op], a, b))
+        return len(nodes) - 1
+    wit = [0] + list(range(1, n_inputs + 1))
+    bits = list(range(n_field + 1, n_inputs + 1))
+    for f in range(1, n_field + 1):
+        ks = rnd.sample(range(0, 254), 40) + [0, 253, 254, 255, 300]
+        for k in ks:
+            bits.append(duo("Band", duo("Shr", f, const(k)), const(1)))
+            if rnd.random() < 0.5:
+                wit.append(bits[-1])
+        wit.append(duo("Band", duo("Shr", f, const(rnd.randrange(200))), const((1 << rnd.randrange(2, 40)) - 1)))   # a masked slice: wide
+    for _ in range(n_gates):
+        r = rnd.random()
+        pick = lambda: rnd.choice(bits)
+        if r < 0.3:
+            bits.append(duo("Mul", pick(), pick()))
+        elif r < 0.6:
+            a, b = pick(), pick()
+            bits.append(duo("Sub", duo("Add", a, b), duo("Mul", const(2), duo("Mul", a, b))))
+        elif r < 0.8:
+            lc = const(0)
+            for j in sorted(rnd.sample(range(250), rnd.choice([3, 40, 216]))):
+                lc = duo("Add", lc, duo("Mul", pick(), const(1 << j)))
+            wit.append(lc)                                 # Bits2Num: a wide witness value
+            continue
+        else:
+            bits.append(duo("Sub", const(1), pick()))
+        wit.append(bits[-1])
+    return nodes, wit, {"x": (1, n_inputs)}
+
+
+def test_field_inputs_taken_apart_into_bits_and_wide_outputs():
+    rnd = random.Random(606)
+    for t in range(8):
+        n_field, n_bits = rnd.choice([1, 3]), rnd.choice([0, 6])
+        nodes, wit, imap = field_bits_graph(rnd, n_field, n_bits)
+        g = util.BitSimGraph(po.serialize_graph(nodes, wit, imap))
+        assert g.info["eligible"] and g.info["has_field_inputs"] and g.info["n_wide"] >= n_field, g.reason
+        rows = []
+        for _ in range(32):
+            fv = [rnd.choice([0, 1, M - 1, M, M + 5, (1 << 256) - 1, (1 << 253), rnd.randrange(M), rnd.randrange(1 << 256)]) for _ in range(n_field)]
+            rows.append([1] + fv + [rnd.randrange(2) for _ in range(n_bits)])
+        if n_bits:
+            rows[7][n_field + 1] = 9                       # breaks the contract of a bit input; field inputs have none
+        res, ok = g.eval(rows)
+        assert ok == (0xFFFFFFFF & ~(1 << 7) if n_bits else 0xFFFFFFFF)
+        for b, row in enumerate(rows):
+            if res[b] is not None:
+                assert res[b] == po.evaluate(nodes, row, wit, "circom"), (t, b)

@@ -450,3 +450,79 @@ def test_bitsliced_sha256_bits_and_field_inputs(cwc):
     rows = field_rows + [0, 8, 63, 66]
     want = cref.CGraph(data).evaluate_batch(inp[rows], 4)
     assert (out[rows] == want).all()
+
+
+def test_bitsliced_field_inputs_wide_values_and_num2bits(cwc, monkeypatch):
+    """Field inputs that a graph only takes apart (Num2Bits: Shr + Band) carry no contract on the bit-sliced path: their
+    planes are the bits of the value reduced mod M (Fr::new, graph.rs:376), whatever the caller passes (0, M - 1, M,
+    2^256 - 1 ...); witness values that are integers of several bits (Bits2Num sums, the inputs themselves) are assembled
+    from their planes by bit_expand_wide_kernel.  Every row against the oracle, and against the generic kernel."""
+    from tests.test_bitplan import field_bits_graph
+    rnd = random.Random(707)
+    M = po.M
+    for t in range(6):
+        n_field, n_bits = rnd.choice([1, 3]), rnd.choice([0, 6])
+        nodes, wit, imap = field_bits_graph(rnd, n_field, n_bits)
+        data = po.serialize_graph(nodes, wit, imap)
+        g = cwc.Graph(data)
+        B = rnd.choice([1, 33, 200, 1029])
+        rows = []
+        for _ in range(B):
+            fv = [rnd.choice([0, 1, M - 1, M, M + 5, (1 << 256) - 1, 1 << 253, rnd.randrange(M), rnd.randrange(1 << 256)]) for _ in range(n_field)]
+            rows.append([1] + fv + [rnd.randrange(2) for _ in range(n_bits)])
+        bad = set()
+        if n_bits and B > 8:
+            bad = {7, B - 1}
+            for b in bad:
+                rows[b][n_field + 1] = rnd.choice([9, M - 1])
+        inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(B, len(rows[0]), 32)
+        out, flags = g.calc_witness_batch(inp, want_flags=True)
+        for b in sorted(set(range(0, B, max(1, B // 24))) | bad | {B - 1}):
+            assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, rows[b], wit, "circom"), (t, b, b in bad)
+        assert (flags[[b for b in range(B) if b not in bad]] == 0).all()
+        monkeypatch.setenv("GW_BITSLICE", "0")
+        g0 = cwc.Graph(data)
+        monkeypatch.delenv("GW_BITSLICE")
+        assert (g0.calc_witness_batch(inp) == out).all(), t
+    # circuit6 (Num2Bits(256)... of one field input + Bits2Num): pure wiring on the bit path; arbitrary 256-bit inputs
+    name = "circuit6_num2bits"
+    data = util.golden_graph(name)
+    nodes, wit, _ = po.deserialize_graph(data)
+    g = cwc.Graph(data)
+    rng = np.random.default_rng(66)
+    B = 32 * 41 + 3
+    vals = rng.integers(0, 1 << 64, size=(B, g.n_inputs, 4), dtype=np.uint64)     # arbitrary 256-bit values, mostly >= M
+    vals[:, 0, :] = 0
+    vals[:, 0, 0] = 1
+    vals[0, 1:, :] = 0
+    vals[1, 1:, :] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    vals[2::3, 1:, 3] &= np.uint64((1 << 61) - 1)                                    # a third of them below M
+    inp = vals.view(np.uint8).reshape(B, g.n_inputs, 32)
+    out = g.calc_witness_batch(inp)
+    for b in list(range(0, B, 97)) + [1, B - 1]:
+        assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, util.limbs_to_ints(vals[b]), wit, "circom"), b
+    monkeypatch.setenv("GW_BITSLICE", "0")
+    g0 = cwc.Graph(data)
+    monkeypatch.delenv("GW_BITSLICE")
+    assert (g0.calc_witness_batch(inp) == out).all()
+
+
+def test_bit_contract_speculation_is_dropped_when_inputs_are_field_elements(cwc):
+    """A Boolean graph fed field elements: every set breaks the contract and is evaluated by the generic kernel; after the
+    first such launch the engine stops speculating for this graph (both paths would be paid).  Results stay exact."""
+    from tests.test_bitplan import boolean_graph
+    rnd = random.Random(11)
+    nodes, wit, imap = boolean_graph(rnd, n_inputs=24, n_gates=300)
+    g = cwc.Graph(po.serialize_graph(nodes, wit, imap))
+    B = 256
+    for rep in range(3):
+        rows = [[1] + [rnd.randrange(po.M) for _ in range(24)] for _ in range(B)]
+        inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(B, 25, 32)
+        out = g.calc_witness_batch(inp)
+        for b in range(0, B, 37):
+            assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, rows[b], wit, "circom"), (rep, b)
+    rows = [[1] + [rnd.randrange(2) for _ in range(24)] for _ in range(B)]
+    inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(B, 25, 32)
+    out = g.calc_witness_batch(inp)
+    for b in range(0, B, 37):
+        assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, rows[b], wit, "circom"), b

@@ -269,9 +269,10 @@ class BitSimGraph:
         self.h = self.L.sim_bit_load(data, len(data), max_support, int(merge), err, 512)
         if not self.h:
             raise ValueError(err.value.decode())
-        info = (ctypes.c_uint64 * 12)()
+        info = (ctypes.c_uint64 * 15)()
         self.L.sim_bit_info(self.h, info)
-        keys = ["eligible", "n_steps", "n_slots", "n_luts", "n_levels", "n_bit", "n_tt", "n_bv", "n_full_adders", "n_merged", "n_inputs_checked", "n_consts"]
+        keys = ["eligible", "n_steps", "n_slots", "n_luts", "n_levels", "n_bit", "n_tt", "n_bv", "n_full_adders", "n_merged", "n_inputs_checked", "n_consts",
+                "has_field_inputs", "n_wide", "plane_stride"]
         self.info = dict(zip(keys, [int(x) for x in info]))
         self.reason = err.value.decode()
         nodes, wit, _ = po.deserialize_graph(data)
