@@ -292,6 +292,10 @@ __device__ __forceinline__ uint32_t lut3_eval(uint32_t lut, uint32_t a, uint32_t
   return (c & u1) | (~c & u0);
 }
 
+// SINGLE: one input set (the single-witness entry points): only bit 0 of a plane word means anything, so a LUT is one
+// table look-up (5 dependent instructions instead of the 3-level multiplexer tree) -- the step loop of one warp is a
+// pure latency chain: shared-memory read, LUT, write, __syncwarp.
+template <bool SINGLE>
 __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   extern __shared__ uint32_t bit_smem[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -337,17 +341,18 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   // the headers of the next BIT_PREFETCH steps are in flight while a step executes: one L2 round trip per step would
   // otherwise be the whole cost of a step (a handful of warps per SM cannot hide it)
   const uint32_t last = p.n_steps - 1u;
-  uint4 q[BIT_PREFETCH];
+  constexpr uint32_t PF = SINGLE ? 2u * BIT_PREFETCH : BIT_PREFETCH;   // one warp alone: a step is ~100 cycles, an L2 round trip 300+
+  uint4 q[PF];
 #pragma unroll
-  for (uint32_t k = 0; k < BIT_PREFETCH; k++) q[k] = __ldg(p.code + (size_t)min(1u + k, last) * 32u + lane);   // step 0 is the prologue above
-  for (uint32_t st = 1; st < p.n_steps; st += BIT_PREFETCH) {
+  for (uint32_t k = 0; k < PF; k++) q[k] = __ldg(p.code + (size_t)min(1u + k, last) * 32u + lane);   // step 0 is the prologue above
+  for (uint32_t st = 1; st < p.n_steps; st += PF) {
 #pragma unroll
-    for (uint32_t k = 0; k < BIT_PREFETCH; k++) {
+    for (uint32_t k = 0; k < PF; k++) {
       const uint4 ins = q[k];
-      q[k] = __ldg(p.code + (size_t)min(st + k + BIT_PREFETCH, last) * 32u + lane);
+      q[k] = __ldg(p.code + (size_t)min(st + k + PF, last) * 32u + lane);
       if (st + k < p.n_steps) {                              // uniform
         const uint32_t a = S[ins.y & 0xFFFFu], b = S[ins.y >> 16], c = S[ins.z & 0xFFFFu];
-        const uint32_t r = lut3_eval(ins.x, a, b, c);
+        const uint32_t r = SINGLE ? ((ins.x >> ((a & 1u) | ((b & 1u) << 1) | ((c & 1u) << 2))) & 1u) : lut3_eval(ins.x, a, b, c);
         const uint32_t dst = ins.z >> 16;
         if (dst != BIT_NO_SLOT) S[dst] = r;                  // never a slot another lane reads in this step (bitplan.cpp)
         if (ins.w != BIT_NO_POS) planes[ins.w] = r;
@@ -925,7 +930,8 @@ Engine::Dev* Engine::dev(int device) {
   if (plan.n_spill || plan.n_spill_narrow) CUDA_CHECK(cudaMalloc(&d->spill, ((size_t)plan.n_spill * 32 + (size_t)plan.n_spill_narrow * 8) * d->spill_threads));
   if (use_bit_path()) {
     const BitPlan& bp = bit_plan;
-    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
     CUDA_CHECK(cudaMalloc(&d->bit_code, bp.code.size() * sizeof(BitOp)));
     CUDA_CHECK(cudaMemcpy(d->bit_code, bp.code.data(), bp.code.size() * sizeof(BitOp), cudaMemcpyHostToDevice));
     std::vector<uint32_t> quads;                             // triples padded to 16 bytes
@@ -979,7 +985,8 @@ void Engine::launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness,
   if (wpb < 1) throw Error("bit-sliced plan: plane file does not fit shared memory");
   const int env_wpb = env_int("GW_BIT_WARPS", 0);
   if (env_wpb >= 1 && env_wpb <= wpb) wpb = env_wpb;
-  bit_eval_kernel<<<(unsigned)((n_groups + wpb - 1) / wpb), wpb * 32, (size_t)wpb * bp.n_slots * 4, s>>>(q);
+  if (B == 1) bit_eval_kernel<true><<<1, 32, (size_t)bp.n_slots * 4, s>>>(q);
+  else bit_eval_kernel<false><<<(unsigned)((n_groups + wpb - 1) / wpb), wpb * 32, (size_t)wpb * bp.n_slots * 4, s>>>(q);
   CUDA_CHECK(cudaGetLastError());
   const uint32_t tiles = (bp.n_witness + 31) / 32;
   const unsigned long long n_warp_tiles = (unsigned long long)n_groups * tiles;
@@ -1240,6 +1247,29 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
   Dev* d = dev(device);
   DeviceGuard on(device);
   std::lock_guard<std::mutex> lk(d->mu);
+  if (!d->lat_in) {
+    CUDA_CHECK(cudaMalloc(&d->lat_in, std::max<size_t>((size_t)plan.n_inputs * 32, 32)));
+    CUDA_CHECK(cudaMalloc(&d->lat_out, std::max<size_t>((size_t)plan.n_witness * 32, 32)));
+    CUDA_CHECK(cudaMalloc(&d->lat_status, 4));
+  }
+  // Boolean graphs: the bit-sliced plan IS the level-parallel plan -- its steps are up to 32 independent LUT nodes, one
+  // node per lane, values in a shared-memory plane file, __syncwarp between steps (no CTA barrier, no packets).  One
+  // input set occupies bit 0 of every plane word.  SHA-256(512): 8 058 steps against 7 010 levels of 256-bit
+  // instructions in the generic latency plan.  An input set that breaks the bit contract takes the generic plan below.
+  if (bit_path_active() && bit_plan.n_luts > 0 && env_int("GW_LAT_BIT", 1) != 0) {     // pure wiring (Num2Bits alone): three launches cost more than the generic kernel
+    CUDA_CHECK(cudaMemcpyAsync(d->lat_in, inputs, (size_t)plan.n_inputs * 32, cudaMemcpyHostToDevice, 0));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventRecord(e0, 0)); }
+    launch_bit(d, d->lat_in, 1, d->lat_out, d->lat_status, nullptr);
+    CUDA_CHECK(cudaEventRecord(d->last_kernel, 0));
+    if (kernel_ms) CUDA_CHECK(cudaEventRecord(e1, 0));
+    uint32_t n_bad = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_bad, d->bit_nbad, 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_CHECK(cudaMemcpyAsync(witness, d->lat_out, (size_t)plan.n_witness * 32, cudaMemcpyDeviceToHost, 0));
+    CUDA_CHECK(cudaStreamSynchronize(0));
+    if (kernel_ms) { CUDA_CHECK(cudaEventElapsedTime(kernel_ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    if (n_bad == 0) { if (status) *status = 0; return; }
+  }
   {
     std::lock_guard<std::mutex> lk2(mu);
     if (!lat_error.empty()) throw Error(lat_error);
@@ -1261,7 +1291,7 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     }
   }
   const LatencyPlan& lp = lat_plan;
-  const size_t in_b = (size_t)lp.n_inputs * 32, out_b = std::max<size_t>((size_t)lp.n_witness * 32, 32);
+  const size_t in_b = (size_t)lp.n_inputs * 32;
   const size_t smem = ((size_t)lp.n_slots * 2 + LAT_CTRL_BYTES / 16 + (size_t)lp.n_warps * 3 * LAT_RING_SLOTS) * 16;
 #ifdef GW_PROFILING
   const bool clocks = env_int("GW_LAT_CLOCKS", 0) != 0;
@@ -1279,9 +1309,6 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     CUDA_CHECK(cudaMemcpy(d->lat_njobs, lp.n_jobs.data(), lp.n_jobs.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&d->lat_waits, std::max<size_t>(lp.waits.size(), 4) * 4));
     CUDA_CHECK(cudaMemcpy(d->lat_waits, lp.waits.data(), lp.waits.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMalloc(&d->lat_in, std::max<size_t>(in_b, 32)));
-    CUDA_CHECK(cudaMalloc(&d->lat_out, out_b));
-    CUDA_CHECK(cudaMalloc(&d->lat_status, 4));
     if (clocks) CUDA_CHECK(cudaMalloc(&d->lat_clock, ((size_t)lp.n_levels + 1) * 8));
   }
   if (lp.n_levels == 0) return;

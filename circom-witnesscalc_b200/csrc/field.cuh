@@ -98,6 +98,49 @@ __device__ __forceinline__ uint32_t ptx_madc_hi_cc(uint32_t a, uint32_t b, uint3
 __device__ __forceinline__ uint32_t ptx_madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; GW_ASM("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 #endif
 
+// Pair accumulators.  One (mad.lo.cc, madc.hi.cc) pair becomes ONE IMAD.WIDE.U32(.X) whose 64-bit addend and result
+// are an aligned register pair.  Accumulators that live across a loop (the OP_DOT term loop) are therefore kept as
+// 64-bit values: with separate 32-bit registers ptxas re-pairs them around every loop iteration (measured on the
+// authV2 kernel, profiles/r02b: 37 IMAD.MOV.U32 next to the 64 IMAD.WIDE of one dot_mac -- moves that sit on the same
+// pipe as the multiplications).  acc = {lo = column c, hi = column c + 1}.
+#if defined(GW_CHAINS)
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void ptx_mac64_first(uint64_t& acc, uint32_t a, uint32_t b) {      // acc += a*b; CF = carry out
+  GW_ASM("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmad.lo.cc.u32 l, %1, %2, l;\n\tmadc.hi.cc.u32 h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}" : "+l"(acc) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void ptx_mac64_next(uint64_t& acc, uint32_t a, uint32_t b) {       // acc += a*b + CF; CF = carry out
+  GW_ASM("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmadc.lo.cc.u32 l, %1, %2, l;\n\tmadc.hi.cc.u32 h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}" : "+l"(acc) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void ptx_machi64_first(uint64_t& acc, uint32_t a, uint32_t b) {    // hi half += hi(a*b); CF = carry out
+  GW_ASM("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmad.hi.cc.u32 h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}" : "+l"(acc) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void ptx_add64_cc(uint64_t& acc, uint64_t v) { GW_ASM("add.cc.u64 %0, %0, %1;" : "+l"(acc) : "l"(v)); }
+__device__ __forceinline__ void ptx_addc64_cc(uint64_t& acc, uint64_t v) { GW_ASM("addc.cc.u64 %0, %0, %1;" : "+l"(acc) : "l"(v)); }
+#else
+inline void ptx_mac64_first(uint64_t& acc, uint32_t a, uint32_t b) {
+  const uint32_t l = ptx_mad_lo_cc(a, b, (uint32_t)acc), h = ptx_madc_hi_cc(a, b, (uint32_t)(acc >> 32));
+  acc = (uint64_t)l | ((uint64_t)h << 32);
+}
+inline void ptx_mac64_next(uint64_t& acc, uint32_t a, uint32_t b) {
+  const uint32_t l = ptx_madc_lo_cc(a, b, (uint32_t)acc), h = ptx_madc_hi_cc(a, b, (uint32_t)(acc >> 32));
+  acc = (uint64_t)l | ((uint64_t)h << 32);
+}
+inline void ptx_machi64_first(uint64_t& acc, uint32_t a, uint32_t b) {
+  const uint32_t h = ptx_mad_hi_cc(a, b, (uint32_t)(acc >> 32));
+  acc = (acc & 0xFFFFFFFFull) | ((uint64_t)h << 32);
+}
+inline void ptx_add64_cc(uint64_t& acc, uint64_t v) {
+  const uint32_t l = ptx_add_cc((uint32_t)acc, (uint32_t)v), h = ptx_addc_cc((uint32_t)(acc >> 32), (uint32_t)(v >> 32));
+  acc = (uint64_t)l | ((uint64_t)h << 32);
+}
+inline void ptx_addc64_cc(uint64_t& acc, uint64_t v) {
+  const uint32_t l = ptx_addc_cc((uint32_t)acc, (uint32_t)v), h = ptx_addc_cc((uint32_t)(acc >> 32), (uint32_t)(v >> 32));
+  acc = (uint64_t)l | ((uint64_t)h << 32);
+}
+#endif
+GW_HD uint64_t pair64(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+#endif
+
 // r = a + b (mod 2^256); returns the carry out
 GW_HD uint32_t u256_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #if defined(GW_CHAINS)
@@ -482,17 +525,23 @@ GW_HD_NOINLINE fe fe_mul_ni(const fe& a, const fe& b) { return fe_mul(a, b); }
 // never merged -- products are accumulated in place and the Montgomery reduction consumes e and o directly.
 struct dot_acc {
 #if defined(GW_CHAINS)
-  uint32_t e[16], o[15], K[9];   // K[k] counts lazy carries into column 8 + k: P = e + (o << 32) + (K << 256)
+  // E[k] = columns 2k, 2k+1 (the e[] pairs of u256_mul_wide); O[k] = columns 2k+1, 2k+2 (the o[] pairs); K[k] counts
+  // lazy carries into column 8 + k: P = E + (O << 32) + (K << 256)
+  uint64_t E[8], O[7]; uint32_t K[9];
 #else
   uint32_t P[16];
 #endif
 };
+#if defined(GW_CHAINS)
+GW_HD uint32_t dot_e(const dot_acc& A, int k) { return (k & 1) ? (uint32_t)(A.E[k >> 1] >> 32) : (uint32_t)A.E[k >> 1]; }   // e[k] = column k
+GW_HD uint32_t dot_o(const dot_acc& A, int k) { return k >= 14 ? 0u : (k & 1) ? (uint32_t)(A.O[k >> 1] >> 32) : (uint32_t)A.O[k >> 1]; }   // o[k] = column k + 1
+#endif
 GW_HD void dot_init(dot_acc& A) {
 #if defined(GW_CHAINS)
 #pragma unroll
-  for (int k = 0; k < 16; k++) A.e[k] = 0;
+  for (int k = 0; k < 8; k++) A.E[k] = 0;
 #pragma unroll
-  for (int k = 0; k < 15; k++) A.o[k] = 0;
+  for (int k = 0; k < 7; k++) A.O[k] = 0;
 #pragma unroll
   for (int k = 0; k < 9; k++) A.K[k] = 0;
 #else
@@ -503,7 +552,7 @@ GW_HD void dot_load(dot_acc& A, const uint32_t* p16) {   // P <- a 16-limb integ
   dot_init(A);
 #if defined(GW_CHAINS)
 #pragma unroll
-  for (int k = 0; k < 16; k++) A.e[k] = p16[k];
+  for (int k = 0; k < 8; k++) A.E[k] = pair64(p16[2 * k], p16[2 * k + 1]);
 #else
   for (int k = 0; k < 16; k++) A.P[k] = p16[k];
 #endif
@@ -511,32 +560,24 @@ GW_HD void dot_load(dot_acc& A, const uint32_t* p16) {   // P <- a 16-limb integ
 // P += a * b (8 x 8 limbs): the rows of u256_mul_wide; the carry out of every row chain is counted in K.
 GW_HD void dot_mac(dot_acc& A, const uint32_t* a, const uint32_t* b) {
 #if defined(GW_CHAINS)
-  uint32_t* e = A.e; uint32_t* o = A.o; uint32_t* K = A.K;
+  uint32_t* K = A.K;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const uint32_t bi = b[i];
     const int p = i & 1;
     {
-      const int c0 = i + p;
-      e[c0] = ptx_mad_lo_cc(a[p], bi, e[c0]);
-      e[c0 + 1] = ptx_madc_hi_cc(a[p], bi, e[c0 + 1]);
+      const int c0 = i + p;                // even: columns c0, c0+2, .. pair up in E
+      ptx_mac64_first(A.E[c0 >> 1], a[p], bi);
 #pragma unroll
-      for (int j = p + 2; j < 8; j += 2) {
-        e[i + j] = ptx_madc_lo_cc(a[j], bi, e[i + j]);
-        e[i + j + 1] = ptx_madc_hi_cc(a[j], bi, e[i + j + 1]);
-      }
+      for (int j = p + 2; j < 8; j += 2) ptx_mac64_next(A.E[(i + j) >> 1], a[j], bi);
       K[c0] = ptx_addc(K[c0], 0);          // carry out of the last pair (columns c0+6, c0+7) -> column c0+8
     }
     {
       const int q = 1 - p;
-      const int c0 = i + q - 1;
-      o[c0] = ptx_mad_lo_cc(a[q], bi, o[c0]);
-      o[c0 + 1] = ptx_madc_hi_cc(a[q], bi, o[c0 + 1]);
+      const int c0 = i + q - 1;            // even: o index of the odd column i + q
+      ptx_mac64_first(A.O[c0 >> 1], a[q], bi);
 #pragma unroll
-      for (int j = q + 2; j < 8; j += 2) {
-        o[i + j - 1] = ptx_madc_lo_cc(a[j], bi, o[i + j - 1]);
-        o[i + j] = ptx_madc_hi_cc(a[j], bi, o[i + j]);
-      }
+      for (int j = q + 2; j < 8; j += 2) ptx_mac64_next(A.O[(i + j - 1) >> 1], a[j], bi);
       K[c0 + 1] = ptx_addc(K[c0 + 1], 0);  // o[c0+8] is column c0+9
     }
   }
@@ -550,11 +591,10 @@ GW_HD void dot_mac(dot_acc& A, const uint32_t* a, const uint32_t* b) {
 // P += v (8 limbs) at limb offset `off` (0 or 8), carry propagated to the top
 GW_HD void dot_add256(dot_acc& A, const uint32_t* v, int off) {
 #if defined(GW_CHAINS)
-  uint32_t* P = A.e;
-  P[off] = ptx_add_cc(P[off], v[0]);
+  const int h = off >> 1;
+  ptx_add64_cc(A.E[h], pair64(v[0], v[1]));
 #pragma unroll
-  for (int i = 1; i < 7; i++) P[off + i] = ptx_addc_cc(P[off + i], v[i]);
-  P[off + 7] = ptx_addc_cc(P[off + 7], v[7]);
+  for (int i = 1; i < 4; i++) ptx_addc64_cc(A.E[h + i], pair64(v[2 * i], v[2 * i + 1]));
   A.K[off] = ptx_addc(A.K[off], 0);        // column off + 8 (K[8] = column 16 stays 0: P < 2^512)
 #else
   uint32_t* P = A.P;
@@ -571,48 +611,48 @@ GW_HD fe fe_mont_reduce_core(dot_acc& A) {
   fe r;
 #if defined(GW_CHAINS)
   // IMAD.WIDE accumulates into an ALIGNED register pair, so a column may only ever be the low half of a pair in one
-  // array: e[] holds pairs starting at even columns (e[k] = column k), o[] pairs starting at odd columns (o[k] = column
+  // array: E holds pairs starting at even columns (e[k] = column k), O pairs starting at odd columns (o[k] = column
   // k + 1).  Round i clears column i: its low word t = e[i] + o[i-1] + carry decides m; lo(m*M0) makes the column
   // 0 mod 2^32 (carry out = [t != 0] + the carries of forming t) and is never stored.
   // The array whose pairs START at column i takes hi(m*M0) and m*M2, m*M4, m*M6, the other one m*M1 .. m*M7; chain
   // carry-outs (columns i+8, i+9) are counted in K, which no later round reads.  Nothing is ever re-paired.
-  uint32_t* e = A.e; uint32_t* o = A.o; uint32_t* K = A.K;
+  uint32_t* K = A.K;
   uint32_t c = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     uint32_t t;
-    if (i == 0) { t = e[0]; }
-    else { const uint64_t s = (uint64_t)e[i] + o[i - 1] + c; t = (uint32_t)s; c = (uint32_t)(s >> 32); }
+    if (i == 0) { t = dot_e(A, 0); }
+    else { const uint64_t s = (uint64_t)dot_e(A, i) + dot_o(A, i - 1) + c; t = (uint32_t)s; c = (uint32_t)(s >> 32); }
     c += (t != 0u) ? 1u : 0u;
     const uint32_t m = t * MONT_INV32;
     if ((i & 1) == 0) {
-      // pairs starting at column i live in e
-      e[i + 1] = ptx_mad_hi_cc(m, MOD_L(0), e[i + 1]);
+      // pairs starting at column i live in E
+      ptx_machi64_first(A.E[i >> 1], m, MOD_L(0));
 #pragma unroll
-      for (int j = 2; j < 8; j += 2) { e[i + j] = ptx_madc_lo_cc(m, MOD_L(j), e[i + j]); e[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), e[i + j + 1]); }
+      for (int j = 2; j < 8; j += 2) ptx_mac64_next(A.E[(i + j) >> 1], m, MOD_L(j));
       K[i] = ptx_addc(K[i], 0);
-      o[i] = ptx_mad_lo_cc(m, MOD_L(1), o[i]); o[i + 1] = ptx_madc_hi_cc(m, MOD_L(1), o[i + 1]);
+      ptx_mac64_first(A.O[i >> 1], m, MOD_L(1));
 #pragma unroll
-      for (int j = 3; j < 8; j += 2) { o[i + j - 1] = ptx_madc_lo_cc(m, MOD_L(j), o[i + j - 1]); o[i + j] = ptx_madc_hi_cc(m, MOD_L(j), o[i + j]); }
+      for (int j = 3; j < 8; j += 2) ptx_mac64_next(A.O[(i + j - 1) >> 1], m, MOD_L(j));
       K[i + 1] = ptx_addc(K[i + 1], 0);
     } else {
-      // pairs starting at column i live in o (o[i - 1] = column i)
-      o[i] = ptx_mad_hi_cc(m, MOD_L(0), o[i]);
+      // pairs starting at column i live in O (o[i - 1] = column i)
+      ptx_machi64_first(A.O[(i - 1) >> 1], m, MOD_L(0));
 #pragma unroll
-      for (int j = 2; j < 8; j += 2) { o[i + j - 1] = ptx_madc_lo_cc(m, MOD_L(j), o[i + j - 1]); o[i + j] = ptx_madc_hi_cc(m, MOD_L(j), o[i + j]); }
+      for (int j = 2; j < 8; j += 2) ptx_mac64_next(A.O[(i + j - 1) >> 1], m, MOD_L(j));
       K[i] = ptx_addc(K[i], 0);
-      e[i + 1] = ptx_mad_lo_cc(m, MOD_L(1), e[i + 1]); e[i + 2] = ptx_madc_hi_cc(m, MOD_L(1), e[i + 2]);
+      ptx_mac64_first(A.E[(i + 1) >> 1], m, MOD_L(1));
 #pragma unroll
-      for (int j = 3; j < 8; j += 2) { e[i + j] = ptx_madc_lo_cc(m, MOD_L(j), e[i + j]); e[i + j + 1] = ptx_madc_hi_cc(m, MOD_L(j), e[i + j + 1]); }
+      for (int j = 3; j < 8; j += 2) ptx_mac64_next(A.E[(i + j) >> 1], m, MOD_L(j));
       K[i + 1] = ptx_addc(K[i + 1], 0);
     }
   }
   // columns 8..15: e + o + K + carry of column 7 (the caller's bound makes the total fit 256 bits)
   K[0] += c;
-  r.l[0] = ptx_add_cc(e[8], o[7]);
+  r.l[0] = ptx_add_cc(dot_e(A, 8), dot_o(A, 7));
 #pragma unroll
-  for (int k = 1; k < 7; k++) r.l[k] = ptx_addc_cc(e[8 + k], o[7 + k]);
-  r.l[7] = ptx_addc(e[15], o[14]);
+  for (int k = 1; k < 7; k++) r.l[k] = ptx_addc_cc(dot_e(A, 8 + k), dot_o(A, 7 + k));
+  r.l[7] = ptx_addc(dot_e(A, 15), dot_o(A, 14));
   r.l[0] = ptx_add_cc(r.l[0], K[0]);
 #pragma unroll
   for (int k = 1; k < 7; k++) r.l[k] = ptx_addc_cc(r.l[k], K[k]);

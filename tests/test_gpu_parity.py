@@ -162,8 +162,9 @@ def test_bad_inputs_return_errors(cwc):
         cwc.calc_witness_wtns('{"a": "1"}', b"not a graph file at all....")
 
 
-LATENCY_ENVS = [{}, {"GW_LAT_CHAIN": "0"}, {"GW_LAT_WARPS": "2", "GW_LAT_SLOW_WARPS": "1", "GW_LAT_D": "1"},
-                {"GW_LAT_WARPS": "5", "GW_LAT_D": "60", "GW_LAT_SPLIT": "0"}, {"GW_LAT_FUSE": "0"}]
+# GW_LAT_BIT=0: Boolean graphs (SHA-256, Num2Bits) also take the generic latency kernel instead of the bit-sliced plan
+LATENCY_ENVS = [{}, {"GW_LAT_BIT": "0"}, {"GW_LAT_CHAIN": "0", "GW_LAT_BIT": "0"}, {"GW_LAT_WARPS": "2", "GW_LAT_SLOW_WARPS": "1", "GW_LAT_D": "1"},
+                {"GW_LAT_WARPS": "5", "GW_LAT_D": "60", "GW_LAT_SPLIT": "0", "GW_LAT_BIT": "0"}, {"GW_LAT_FUSE": "0"}]
 
 
 @pytest.mark.parametrize("env", LATENCY_ENVS)
@@ -526,3 +527,21 @@ def test_bit_contract_speculation_is_dropped_when_inputs_are_field_elements(cwc)
     out = g.calc_witness_batch(inp)
     for b in range(0, B, 37):
         assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, rows[b], wit, "circom"), b
+
+
+def test_latency_mode_boolean_graph_uses_bit_plan_and_falls_back(cwc):
+    """Single witness of a Boolean graph: the bit-sliced plan is the level-parallel plan (one LUT node per lane); an input
+    set that breaks the bit contract is evaluated by the generic latency kernel in the same call.  Flags included."""
+    from tests.test_bitplan import boolean_graph
+    rnd = random.Random(515)
+    for t in range(4):
+        n_in = rnd.choice([5, 24])
+        nodes, wit, imap = boolean_graph(rnd, n_inputs=n_in, n_gates=200)
+        g = cwc.Graph(po.serialize_graph(nodes, wit, imap))
+        assert g.info["bit_eligible"] == 1
+        for broken in (False, True, False):
+            row = [1] + [rnd.randrange(2) for _ in range(n_in)]
+            if broken:
+                row[1 + rnd.randrange(n_in)] = rnd.choice([2, po.M - 1, rnd.randrange(po.M)])
+            out, ms = g.calc_witness_latency(np.frombuffer(util.pack_u256(row), dtype=np.uint8).reshape(n_in + 1, 32))
+            assert util.unpack_u256(out.tobytes()) == po.evaluate(nodes, row, wit, "circom"), (t, broken)
