@@ -279,6 +279,7 @@ struct BParams {
 };
 
 static const uint32_t BIT_PREFETCH = 4;
+static const uint32_t BIT_CHUNK = 16;      // single-set kernel: steps per TMA chunk of its header ring (3 stages)
 
 __device__ __forceinline__ uint32_t lut3_eval(uint32_t lut, uint32_t a, uint32_t b, uint32_t c) {
   // branch-free (the 32 lanes hold 32 different tables): a multiplexer tree over the 8 table bits spread to masks
@@ -311,6 +312,28 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   bool ok = in_range;
   uint32_t cur = 0xFFFFFFFFu;
   fe v = fe_zero();
+  if (SINGLE) {
+    // one input set: lane = entry of the input list (32 entries per pass instead of one dependent L2 round trip each)
+    ok = true;
+    for (uint32_t k0 = 0; k0 < p.n_in; k0 += 32u) {
+      const uint32_t k = k0 + lane;
+      if (k < p.n_in) {
+        const uint4 e = __ldg(p.in_list + k);
+        const uint4 lo = __ldg(p.inputs + 2 * (size_t)e.x), hi = __ldg(p.inputs + 2 * (size_t)e.x + 1);
+        if (e.z == BIT_CONTRACT) {
+          ok = ok && (lo.x <= 1u) && ((lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) == 0u);
+          if (e.y != BIT_NO_SLOT) S[e.y] = lo.x & 1u;
+        } else {
+          const fe w = fe_reduce256(fe_from(lo, hi));
+          uint32_t limb = 0;
+#pragma unroll
+          for (uint32_t q = 0; q < 8; q++) limb = (q == (e.z >> 5)) ? w.l[q] : limb;
+          S[e.y] = (limb >> (e.z & 31u)) & 1u;
+        }
+      }
+    }
+    ok = __all_sync(0xFFFFFFFFu, ok) && lane == 0;        // lane 0 stands for the input set below
+  } else
   for (uint32_t k = 0; k < p.n_in; k++) {
     const uint4 e = __ldg(p.in_list + k);                  // uniform
     if (e.z == BIT_CONTRACT) {
@@ -340,8 +363,53 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   uint32_t* planes = p.planes + (size_t)g * p.plane_stride;
   // the headers of the next BIT_PREFETCH steps are in flight while a step executes: one L2 round trip per step would
   // otherwise be the whole cost of a step (a handful of warps per SM cannot hide it)
+  if (SINGLE) {
+    // One warp alone: a step is a ~100-cycle dependent chain, an L2 round trip for its header three times that, and
+    // ptxas batches register prefetches at the end of the unrolled body.  So the LUT headers come through a 3-stage
+    // shared-memory ring filled by TMA bulk copies (BIT_CHUNK steps = 8 KB each) that complete on an mbarrier per stage;
+    // chunk c + 2 is requested when chunk c starts.  Layout: [plane file][3 mbarriers][ring], see launch_bit.
+    const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(bit_smem);
+    const uint32_t bar_s = smem_s + ((p.n_slots * 4u + 15u) & ~15u), ring_s = bar_s + 32u;
+    const uint32_t n_chunks = (p.n_steps - 1u + BIT_CHUNK - 1u) / BIT_CHUNK;     // steps 1 .. n_steps - 1
+    if (lane < 3u) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8u * lane) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    auto request = [&](uint32_t c) {
+      if (c >= n_chunks || lane != 0u) return;
+      const uint32_t stage = c % 3u, first = 1u + c * BIT_CHUNK;
+      const uint32_t bytes = min(BIT_CHUNK, p.n_steps - first) * 512u, bar = bar_s + 8u * stage;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // earlier generic reads of the stage vs the async write
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ring_s + stage * (BIT_CHUNK * 512u)), "l"(p.code + (size_t)first * 32u), "r"(bytes), "r"(bar) : "memory");
+    };
+    request(0); request(1);
+    for (uint32_t c = 0; c < n_chunks; c++) {
+      const uint32_t stage = c % 3u, parity = (c / 3u) & 1u, bar = bar_s + 8u * stage;
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      __syncwarp();                                                         // every lane is done with chunk c - 1: its stage may be refilled
+      request(c + 2u);
+      const uint32_t n = min(BIT_CHUNK, p.n_steps - 1u - c * BIT_CHUNK);
+      const uint32_t src = ring_s + stage * (BIT_CHUNK * 512u) + lane * 16u;
+      uint4 nxt;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(nxt.x), "=r"(nxt.y), "=r"(nxt.z), "=r"(nxt.w) : "r"(src));
+      for (uint32_t k = 0; k < n; k++) {
+        const uint4 ins = nxt;
+        if (k + 1u < n) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(nxt.x), "=r"(nxt.y), "=r"(nxt.z), "=r"(nxt.w) : "r"(src + (k + 1u) * 512u));
+        const uint32_t a = S[ins.y & 0xFFFFu], b = S[ins.y >> 16], cc = S[ins.z & 0xFFFFu];
+        const uint32_t r = (ins.x >> ((a & 1u) | ((b & 1u) << 1) | ((cc & 1u) << 2))) & 1u;
+        const uint32_t dst = ins.z >> 16;
+        if (dst != BIT_NO_SLOT) S[dst] = r;
+        if (ins.w != BIT_NO_POS) planes[ins.w] = r;
+        __syncwarp();
+      }
+    }
+    return;
+  }
   const uint32_t last = p.n_steps - 1u;
-  constexpr uint32_t PF = SINGLE ? 2u * BIT_PREFETCH : BIT_PREFETCH;   // one warp alone: a step is ~100 cycles, an L2 round trip 300+
+  constexpr uint32_t PF = BIT_PREFETCH;
   uint4 q[PF];
 #pragma unroll
   for (uint32_t k = 0; k < PF; k++) q[k] = __ldg(p.code + (size_t)min(1u + k, last) * 32u + lane);   // step 0 is the prologue above
@@ -352,7 +420,7 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
       q[k] = __ldg(p.code + (size_t)min(st + k + PF, last) * 32u + lane);
       if (st + k < p.n_steps) {                              // uniform
         const uint32_t a = S[ins.y & 0xFFFFu], b = S[ins.y >> 16], c = S[ins.z & 0xFFFFu];
-        const uint32_t r = SINGLE ? ((ins.x >> ((a & 1u) | ((b & 1u) << 1) | ((c & 1u) << 2))) & 1u) : lut3_eval(ins.x, a, b, c);
+        const uint32_t r = lut3_eval(ins.x, a, b, c);
         const uint32_t dst = ins.z >> 16;
         if (dst != BIT_NO_SLOT) S[dst] = r;                  // never a slot another lane reads in this step (bitplan.cpp)
         if (ins.w != BIT_NO_POS) planes[ins.w] = r;
@@ -985,7 +1053,8 @@ void Engine::launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness,
   if (wpb < 1) throw Error("bit-sliced plan: plane file does not fit shared memory");
   const int env_wpb = env_int("GW_BIT_WARPS", 0);
   if (env_wpb >= 1 && env_wpb <= wpb) wpb = env_wpb;
-  if (B == 1) bit_eval_kernel<true><<<1, 32, (size_t)bp.n_slots * 4, s>>>(q);
+  const size_t single_smem = (((size_t)bp.n_slots * 4 + 15) & ~(size_t)15) + 32 + 3 * (size_t)BIT_CHUNK * 512;     // plane file, mbarriers, header ring
+  if (B == 1 && single_smem <= d->smem_max) bit_eval_kernel<true><<<1, 32, single_smem, s>>>(q);
   else bit_eval_kernel<false><<<(unsigned)((n_groups + wpb - 1) / wpb), wpb * 32, (size_t)wpb * bp.n_slots * 4, s>>>(q);
   CUDA_CHECK(cudaGetLastError());
   const uint32_t tiles = (bp.n_witness + 31) / 32;
