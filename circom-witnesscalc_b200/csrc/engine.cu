@@ -267,7 +267,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) eval_batch_kernel(const KParam
 // input is 0 or 1); input sets that break it are handed to eval_batch_kernel through bad_list.
 struct BParams {
   const uint4* code; uint32_t n_steps, n_slots;
-  const uint4* in_list; uint32_t n_in;      // {input index, plane slot or BIT_NO_SLOT, bit or BIT_CONTRACT, 0}, sorted by input index
+  uint32_t warp_bytes;                      // shared memory per warp: plane file (+ mbarriers + header ring), a multiple of 16
+  const uint4* in_list; uint32_t n_in;      // {input index, plane slot or BIT_NO_SLOT, bit or BIT_CONTRACT, 0}: contract inputs first, then the bits of field inputs
+  uint32_t n_contract;                      // the first n_contract entries of in_list are the contract inputs (batch kernels: the rest comes from the tables below)
+  const uint32_t* field_inputs; uint32_t n_field;   // input indices of the field inputs
+  const uint32_t* field_slots;              // [n_field][256]: plane slot of bit b of field input f, or BIT_NO_SLOT
   const uint4* inputs;                      // [B][I][2]
   uint32_t I, W;
   unsigned long long B;
@@ -279,7 +283,7 @@ struct BParams {
 };
 
 static const uint32_t BIT_PREFETCH = 4;
-static const uint32_t BIT_CHUNK = 16;      // single-set kernel: steps per TMA chunk of its header ring (3 stages)
+static const uint32_t BIT_CHUNK_SINGLE = 16, BIT_CHUNK_BATCH = 8;      // steps per TMA chunk of a warp's header ring (3 stages)
 
 __device__ __forceinline__ uint32_t lut3_eval(uint32_t lut, uint32_t a, uint32_t b, uint32_t c) {
   // branch-free (the 32 lanes hold 32 different tables): a multiplexer tree over the 8 table bits spread to masks
@@ -296,13 +300,17 @@ __device__ __forceinline__ uint32_t lut3_eval(uint32_t lut, uint32_t a, uint32_t
 // SINGLE: one input set (the single-witness entry points): only bit 0 of a plane word means anything, so a LUT is one
 // table look-up (5 dependent instructions instead of the 3-level multiplexer tree) -- the step loop of one warp is a
 // pure latency chain: shared-memory read, LUT, write, __syncwarp.
-template <bool SINGLE>
+// RING: the LUT headers of a warp come through its own 3-stage shared-memory ring filled by TMA bulk copies (CH steps per
+// chunk) instead of register prefetches: a warp's step is a dependent chain of ~100-200 cycles, an L2 round trip for the
+// header is longer than that, and ptxas batches register prefetches at the end of the unrolled body.  Costs shared
+// memory (fewer resident groups per SM), so large batches may prefer the register variant (launch_bit).
+template <bool SINGLE, bool RING>
 __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   extern __shared__ uint32_t bit_smem[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t g = blockIdx.x * (blockDim.x >> 5) + warp;
   if (g >= p.n_groups) return;
-  uint32_t* S = bit_smem + (size_t)warp * p.n_slots;
+  uint32_t* S = bit_smem + (size_t)warp * (p.warp_bytes >> 2);          // [plane file][3 mbarriers][ring] per warp
   const unsigned long long row = (unsigned long long)g * 32u + lane;
   const bool in_range = row < p.B;
   if (lane == 0) { S[BIT_SLOT_ZERO] = 0u; S[BIT_SLOT_ONES] = 0xFFFFFFFFu; }
@@ -310,8 +318,6 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   // (taken apart by the graph with Shr/Band) the planes are bits of the value reduced mod M, whatever the value.
   const uint4* in = p.inputs + (in_range ? row : 0ull) * p.I * 2;
   bool ok = in_range;
-  uint32_t cur = 0xFFFFFFFFu;
-  fe v = fe_zero();
   if (SINGLE) {
     // one input set: lane = entry of the input list (32 entries per pass instead of one dependent L2 round trip each)
     ok = true;
@@ -333,25 +339,36 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
       }
     }
     ok = __all_sync(0xFFFFFFFFu, ok) && lane == 0;        // lane 0 stands for the input set below
-  } else
-  for (uint32_t k = 0; k < p.n_in; k++) {
-    const uint4 e = __ldg(p.in_list + k);                  // uniform
-    if (e.z == BIT_CONTRACT) {
-      const uint4 lo = __ldg(in + 2 * (size_t)e.x), hi = __ldg(in + 2 * (size_t)e.x + 1);
-      const bool is_bit = (lo.x <= 1u) && ((lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) == 0u);
-      ok = ok && is_bit;
-      const uint32_t word = __ballot_sync(0xFFFFFFFFu, in_range && (lo.x & 1u));
-      if (lane == 0 && e.y != BIT_NO_SLOT) S[e.y] = word;
-    } else {
-      if (e.x != cur) {                                    // Fr::new (graph.rs:376): the planes are bits of the canonical value
-        cur = e.x;
-        v = fe_reduce256(fe_from(__ldg(in + 2 * (size_t)e.x), __ldg(in + 2 * (size_t)e.x + 1)));
+  } else {
+    // contract inputs: 32 list entries per coalesced load, then one ballot per entry
+    for (uint32_t k0 = 0; k0 < p.n_contract; k0 += 32u) {
+      const uint4 mine = (k0 + lane < p.n_contract) ? __ldg(p.in_list + k0 + lane) : make_uint4(0, BIT_NO_SLOT, 0, 0);
+      const uint32_t n = min(32u, p.n_contract - k0);
+      for (uint32_t k = 0; k < n; k++) {
+        const uint32_t ex = __shfl_sync(0xFFFFFFFFu, mine.x, k), ey = __shfl_sync(0xFFFFFFFFu, mine.y, k);
+        const uint4 lo = __ldg(in + 2 * (size_t)ex), hi = __ldg(in + 2 * (size_t)ex + 1);
+        ok = ok && (lo.x <= 1u) && ((lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) == 0u);
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, in_range && (lo.x & 1u));
+        if (lane == 0 && ey != BIT_NO_SLOT) S[ey] = word;
       }
-      uint32_t limb = 0;
+    }
+    // field inputs (Fr::new, graph.rs:376: the planes are bits of the canonical value): a 32 x 32 bit transpose across
+    // the warp per limb -- lane j ends up with the plane word of bit 32 q + j -- instead of one ballot per bit
+    for (uint32_t f = 0; f < p.n_field; f++) {
+      const uint32_t ix = __ldg(p.field_inputs + f);
+      const fe w = fe_reduce256(fe_from(__ldg(in + 2 * (size_t)ix), __ldg(in + 2 * (size_t)ix + 1)));
 #pragma unroll
-      for (uint32_t q = 0; q < 8; q++) limb = (q == (e.z >> 5)) ? v.l[q] : limb;
-      const uint32_t word = __ballot_sync(0xFFFFFFFFu, in_range && ((limb >> (e.z & 31u)) & 1u));
-      if (lane == 0) S[e.y] = word;
+      for (uint32_t q = 0; q < 8; q++) {
+        uint32_t x = in_range ? w.l[q] : 0u;
+#pragma unroll
+        for (uint32_t j = 16; j >= 1; j >>= 1) {
+          const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+          const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+          x = (lane & j) ? (((y >> j) & m) | (x & (m << j))) : ((x & m) | ((y & m) << j));
+        }
+        const uint32_t slot = __ldg(p.field_slots + f * 256u + q * 32u + lane);
+        if (slot != BIT_NO_SLOT) S[slot] = x;
+      }
     }
   }
   const uint32_t okw = __ballot_sync(0xFFFFFFFFu, ok);
@@ -363,12 +380,10 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
   uint32_t* planes = p.planes + (size_t)g * p.plane_stride;
   // the headers of the next BIT_PREFETCH steps are in flight while a step executes: one L2 round trip per step would
   // otherwise be the whole cost of a step (a handful of warps per SM cannot hide it)
-  if (SINGLE) {
-    // One warp alone: a step is a ~100-cycle dependent chain, an L2 round trip for its header three times that, and
-    // ptxas batches register prefetches at the end of the unrolled body.  So the LUT headers come through a 3-stage
-    // shared-memory ring filled by TMA bulk copies (BIT_CHUNK steps = 8 KB each) that complete on an mbarrier per stage;
-    // chunk c + 2 is requested when chunk c starts.  Layout: [plane file][3 mbarriers][ring], see launch_bit.
-    const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(bit_smem);
+  if (RING) {
+    // chunk c + 2 is requested when chunk c starts; a chunk completes on the mbarrier of its stage
+    constexpr uint32_t BIT_CHUNK = SINGLE ? BIT_CHUNK_SINGLE : BIT_CHUNK_BATCH;
+    const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(S);
     const uint32_t bar_s = smem_s + ((p.n_slots * 4u + 15u) & ~15u), ring_s = bar_s + 32u;
     const uint32_t n_chunks = (p.n_steps - 1u + BIT_CHUNK - 1u) / BIT_CHUNK;     // steps 1 .. n_steps - 1
     if (lane < 3u) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8u * lane) : "memory");
@@ -399,7 +414,7 @@ __global__ void __launch_bounds__(256) bit_eval_kernel(const BParams p) {
         const uint4 ins = nxt;
         if (k + 1u < n) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(nxt.x), "=r"(nxt.y), "=r"(nxt.z), "=r"(nxt.w) : "r"(src + (k + 1u) * 512u));
         const uint32_t a = S[ins.y & 0xFFFFu], b = S[ins.y >> 16], cc = S[ins.z & 0xFFFFu];
-        const uint32_t r = (ins.x >> ((a & 1u) | ((b & 1u) << 1) | ((cc & 1u) << 2))) & 1u;
+        const uint32_t r = SINGLE ? ((ins.x >> ((a & 1u) | ((b & 1u) << 1) | ((cc & 1u) << 2))) & 1u) : lut3_eval(ins.x, a, b, cc);
         const uint32_t dst = ins.z >> 16;
         if (dst != BIT_NO_SLOT) S[dst] = r;
         if (ins.w != BIT_NO_POS) planes[ins.w] = r;
@@ -444,8 +459,8 @@ __global__ void __launch_bounds__(256) bit_expand_kernel(const uint32_t* __restr
   const uint32_t j0 = (uint32_t)(t % tiles_per_group) * 32u, j = j0 + lane;
   const uint32_t okw = __ldg(ok_words + g);
   if (okw == 0u) return;
-  const uint32_t word = j < W ? __ldg(planes + (size_t)g * plane_stride + j) : 0u;
   const int32_t cidx = j < W ? __ldg(const_of_pos + j) : -1;
+  const uint32_t word = (j < W && cidx == -1) ? __ldg(planes + (size_t)g * plane_stride + j) : 0u;   // constants and wide values have no plane
   const uint32_t half = lane & 1u;
   for (uint32_t w = 0; w < 32u; w++) {
     if (!((okw >> w) & 1u)) continue;
@@ -859,7 +874,7 @@ struct Engine::Dev {
   uint8_t* h_ring[3] = {nullptr, nullptr, nullptr}; uint32_t* h_flags[3] = {nullptr, nullptr, nullptr};
   size_t h_ring_bytes = 0, h_flags_n = 0;
   // bit-sliced path (bitplan.hpp): program tables, and per-launch scratch that grows with the largest batch seen
-  uint4* bit_code = nullptr; uint4* bit_inputs = nullptr; int32_t* bit_constpos = nullptr; uint4* bit_consts = nullptr; uint4* bit_wide = nullptr;
+  uint4* bit_code = nullptr; uint4* bit_inputs = nullptr; uint32_t* bit_field_inputs = nullptr; uint32_t* bit_field_slots = nullptr; uint32_t bit_n_contract = 0, bit_n_field = 0; int32_t* bit_constpos = nullptr; uint4* bit_consts = nullptr; uint4* bit_wide = nullptr;
   uint32_t* bit_planes = nullptr; uint32_t* bit_ok = nullptr; uint32_t* bit_bad = nullptr; uint32_t* bit_nbad = nullptr;
   size_t bit_groups = 0;
   // feedback for the speculation on the bit contract: how many input sets of the last bit-sliced launch broke it
@@ -956,7 +971,7 @@ Engine::~Engine() {
     cudaGetDevice(&prev);
     cudaSetDevice(d->device);
     cudaFree(d->code); cudaFree(d->consts); cudaFree(d->spill);
-    cudaFree(d->bit_code); cudaFree(d->bit_inputs); cudaFree(d->bit_constpos); cudaFree(d->bit_consts); cudaFree(d->bit_wide);
+    cudaFree(d->bit_code); cudaFree(d->bit_inputs); cudaFree(d->bit_constpos); cudaFree(d->bit_consts); cudaFree(d->bit_wide); cudaFree(d->bit_field_inputs); cudaFree(d->bit_field_slots);
     cudaFree(d->bit_planes); cudaFree(d->bit_ok); cudaFree(d->bit_bad); cudaFree(d->bit_nbad);
     cudaFreeHost(d->bit_nbad_host); if (d->bit_nbad_ev) cudaEventDestroy(d->bit_nbad_ev);
     cudaFree(d->lat_code); cudaFree(d->lat_first); cudaFree(d->lat_jobs); cudaFree(d->lat_njobs); cudaFree(d->lat_waits); cudaFree(d->lat_clock); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
@@ -998,12 +1013,28 @@ Engine::Dev* Engine::dev(int device) {
   if (plan.n_spill || plan.n_spill_narrow) CUDA_CHECK(cudaMalloc(&d->spill, ((size_t)plan.n_spill * 32 + (size_t)plan.n_spill_narrow * 8) * d->spill_threads));
   if (use_bit_path()) {
     const BitPlan& bp = bit_plan;
-    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
-    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+    CUDA_CHECK(cudaFuncSetAttribute(bit_eval_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
     CUDA_CHECK(cudaMalloc(&d->bit_code, bp.code.size() * sizeof(BitOp)));
     CUDA_CHECK(cudaMemcpy(d->bit_code, bp.code.data(), bp.code.size() * sizeof(BitOp), cudaMemcpyHostToDevice));
-    std::vector<uint32_t> quads;                             // triples padded to 16 bytes
-    for (size_t k = 0; k + 2 < bp.inputs.size(); k += 3) { quads.push_back(bp.inputs[k]); quads.push_back(bp.inputs[k + 1]); quads.push_back(bp.inputs[k + 2]); quads.push_back(0); }
+    // input list as 16-byte entries, the contract inputs first (the batch kernel reads those and takes the field inputs
+    // from the per-bit slot tables; the single-set kernel walks the whole list)
+    std::vector<uint32_t> quads, finputs, fslots;
+    for (int pass = 0; pass < 2; pass++)
+      for (size_t k = 0; k + 2 < bp.inputs.size(); k += 3) {
+        const bool contract = bp.inputs[k + 2] == BIT_CONTRACT;
+        if (contract != (pass == 0)) continue;
+        quads.push_back(bp.inputs[k]); quads.push_back(bp.inputs[k + 1]); quads.push_back(bp.inputs[k + 2]); quads.push_back(0);
+        if (contract) { d->bit_n_contract++; continue; }
+        if (finputs.empty() || finputs.back() != bp.inputs[k]) { finputs.push_back(bp.inputs[k]); fslots.resize(fslots.size() + 256, BIT_NO_SLOT); }
+        if (bp.inputs[k + 2] < 256) fslots[(finputs.size() - 1) * 256 + bp.inputs[k + 2]] = bp.inputs[k + 1];
+      }
+    d->bit_n_field = (uint32_t)finputs.size();
+    CUDA_CHECK(cudaMalloc(&d->bit_field_inputs, std::max<size_t>(finputs.size(), 1) * 4));
+    CUDA_CHECK(cudaMemcpy(d->bit_field_inputs, finputs.data(), finputs.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->bit_field_slots, std::max<size_t>(fslots.size(), 1) * 4));
+    CUDA_CHECK(cudaMemcpy(d->bit_field_slots, fslots.data(), fslots.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&d->bit_inputs, std::max<size_t>(quads.size(), 4) * 4));
     CUDA_CHECK(cudaMemcpy(d->bit_inputs, quads.data(), quads.size() * 4, cudaMemcpyHostToDevice));
     quads.clear();
@@ -1044,18 +1075,36 @@ void Engine::launch_bit(Dev* d, const void* d_inputs, size_t B, void* d_witness,
   CUDA_CHECK(cudaMemsetAsync(d->bit_nbad, 0, 4, s));
   BParams q;
   q.code = d->bit_code; q.n_steps = bp.n_steps; q.n_slots = bp.n_slots;
-  q.in_list = d->bit_inputs; q.n_in = (uint32_t)(bp.inputs.size() / 3);
+  q.in_list = d->bit_inputs; q.n_in = (uint32_t)(bp.inputs.size() / 3); q.n_contract = d->bit_n_contract;
+  q.field_inputs = d->bit_field_inputs; q.n_field = d->bit_n_field; q.field_slots = d->bit_field_slots;
   q.inputs = (const uint4*)d_inputs; q.I = bp.n_inputs; q.W = bp.n_witness; q.B = B; q.n_groups = (uint32_t)n_groups;
   q.planes = d->bit_planes; q.plane_stride = bp.plane_stride; q.ok_words = d->bit_ok; q.bad_list = d->bit_bad; q.n_bad = d->bit_nbad; q.status = d_status;
-  // warps per CTA: as many as the plane files allow, but enough CTAs to cover the SMs twice
-  int wpb = (int)std::min<size_t>(8, d->smem_max / ((size_t)bp.n_slots * 4));
-  while (wpb > 1 && n_groups < (size_t)wpb * 2 * (size_t)d->sms) wpb--;
-  if (wpb < 1) throw Error("bit-sliced plan: plane file does not fit shared memory");
-  const int env_wpb = env_int("GW_BIT_WARPS", 0);
-  if (env_wpb >= 1 && env_wpb <= wpb) wpb = env_wpb;
-  const size_t single_smem = (((size_t)bp.n_slots * 4 + 15) & ~(size_t)15) + 32 + 3 * (size_t)BIT_CHUNK * 512;     // plane file, mbarriers, header ring
-  if (B == 1 && single_smem <= d->smem_max) bit_eval_kernel<true><<<1, 32, single_smem, s>>>(q);
-  else bit_eval_kernel<false><<<(unsigned)((n_groups + wpb - 1) / wpb), wpb * 32, (size_t)wpb * bp.n_slots * 4, s>>>(q);
+  // shared memory per warp (group): the plane file, and for the ring variants 3 mbarriers + 3 chunks of LUT headers
+  const size_t planes_b = ((size_t)bp.n_slots * 4 + 15) & ~(size_t)15;
+  const size_t single_b = planes_b + 32 + 3 * (size_t)BIT_CHUNK_SINGLE * 512, ring_b = planes_b + 32 + 3 * (size_t)BIT_CHUNK_BATCH * 512;
+  if (planes_b > d->smem_max) throw Error("bit-sliced plan: plane file does not fit shared memory");
+  if (B == 1 && single_b <= d->smem_max) {
+    q.warp_bytes = (uint32_t)single_b;
+    bit_eval_kernel<true, true><<<1, 32, single_b, s>>>(q);
+  } else {
+    // ring variant unless it would leave an SM with fewer resident groups than the batch can give it (GW_BIT_RING=0/1 forces)
+    const int env_ring = env_int("GW_BIT_RING", -1);
+    const size_t fit_ring = d->smem_max / ring_b, fit_reg = d->smem_max / planes_b;
+    const size_t per_sm = (n_groups + (size_t)d->sms - 1) / (size_t)d->sms;
+    // (a short program -- Num2Bits: 24 steps -- is over before a ring pays for its set-up: measured, profiles/r02k)
+    bool ring = ring_b <= d->smem_max && bp.n_steps >= 128 && (per_sm <= fit_ring || fit_ring * 2 >= fit_reg);
+    if (env_ring == 0) ring = false; else if (env_ring == 1 && ring_b <= d->smem_max) ring = true;
+    const size_t wb = ring ? ring_b : planes_b;
+    // warps per CTA: as many as shared memory allows, but enough CTAs to cover the SMs twice
+    int wpb = (int)std::min<size_t>(8, d->smem_max / wb);
+    while (wpb > 1 && n_groups < (size_t)wpb * 2 * (size_t)d->sms) wpb--;
+    const int env_wpb = env_int("GW_BIT_WARPS", 0);
+    if (env_wpb >= 1 && env_wpb <= wpb) wpb = env_wpb;
+    q.warp_bytes = (uint32_t)wb;
+    const unsigned grid = (unsigned)((n_groups + wpb - 1) / wpb);
+    if (ring) bit_eval_kernel<false, true><<<grid, wpb * 32, (size_t)wpb * wb, s>>>(q);
+    else bit_eval_kernel<false, false><<<grid, wpb * 32, (size_t)wpb * wb, s>>>(q);
+  }
   CUDA_CHECK(cudaGetLastError());
   const uint32_t tiles = (bp.n_witness + 31) / 32;
   const unsigned long long n_warp_tiles = (unsigned long long)n_groups * tiles;
@@ -1333,11 +1382,13 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     CUDA_CHECK(cudaEventRecord(d->last_kernel, 0));
     if (kernel_ms) CUDA_CHECK(cudaEventRecord(e1, 0));
     uint32_t n_bad = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n_bad, d->bit_nbad, 4, cudaMemcpyDeviceToHost, 0));
-    CUDA_CHECK(cudaMemcpyAsync(witness, d->lat_out, (size_t)plan.n_witness * 32, cudaMemcpyDeviceToHost, 0));
-    CUDA_CHECK(cudaStreamSynchronize(0));
+    CUDA_CHECK(cudaMemcpy(&n_bad, d->bit_nbad, 4, cudaMemcpyDeviceToHost));     // 4 bytes decide which buffer is worth copying
     if (kernel_ms) { CUDA_CHECK(cudaEventElapsedTime(kernel_ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
-    if (n_bad == 0) { if (status) *status = 0; return; }
+    if (n_bad == 0) {
+      CUDA_CHECK(cudaMemcpy(witness, d->lat_out, (size_t)plan.n_witness * 32, cudaMemcpyDeviceToHost));
+      if (status) *status = 0;
+      return;
+    }
   }
   {
     std::lock_guard<std::mutex> lk2(mu);

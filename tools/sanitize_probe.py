@@ -56,6 +56,23 @@ out = g.calc_witness_batch(inp)
 for b in (0, 5, 33, 69):
     assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, rows[b], wit, "circom"), b
 n_ok += 1
+# the same Boolean graph, ONE input set: single-set bit kernel (TMA-fed header ring, mbarriers), then a set that breaks the
+# contract (generic latency kernel in the same call)
+for row in (rows[0], rows[5]):
+    lat, _ = g.calc_witness_latency(np.frombuffer(util.pack_u256(row), dtype=np.uint8).reshape(25, 32))
+    assert util.unpack_u256(lat.tobytes()) == po.evaluate(nodes, row, wit, "circom")
+n_ok += 1
+# field inputs taken apart into bits, wide witness values (bit_expand_wide_kernel)
+from tests.test_bitplan import field_bits_graph  # noqa: E402
+nodes, wit, imap = field_bits_graph(rnd, 3, 6)
+g = cwc.Graph(po.serialize_graph(nodes, wit, imap))
+rows = [[1] + [rnd.choice([0, po.M - 1, po.M + 5, (1 << 256) - 1, rnd.randrange(1 << 256)]) for _ in range(3)] + [rnd.randrange(2) for _ in range(6)] for _ in range(45)]
+rows[7][4] = 9
+inp = np.frombuffer(b"".join(util.pack_u256(r) for r in rows), dtype=np.uint8).reshape(45, 10, 32)
+out = g.calc_witness_batch(inp)
+for b in (0, 7, 31, 32, 44):
+    assert util.unpack_u256(out[b].tobytes()) == po.evaluate(nodes, rows[b], wit, "circom"), b
+n_ok += 1
 # streaming path
 g = cwc.Graph(util.golden_graph("circuit5_poseidon"))
 got = []
