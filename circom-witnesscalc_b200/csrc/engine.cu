@@ -768,6 +768,93 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
   if (p.status != nullptr && st) atomicOr(p.status, st);
 }
 
+// ---- single-witness latency mode, dataflow plan (plan.hpp: LatencyPlan::dataflow) -----------------------------------
+// No level barrier.  Every warp -- the ones that take the long operations included -- walks its own stream of packets:
+// chunks of the stream arrive in a 3-stage shared-memory ring by TMA (requested by the warp itself two chunks ahead), a
+// packet's wait vector says how many packets of each other warp must be complete before it starts (its operands, and the
+// last readers of the values whose slots it overwrites), progress counters in shared memory are published after every
+// packet.  Inside a packet one lane = one instruction, as in the level plan; the packets of a warp are ordered by
+// __syncwarp.  The plan compiler's emission order makes the waits acyclic (plan.cpp).
+struct DParams {
+  const uint4* code; const uint32_t* stream_off; const uint32_t* stream_chunks; uint32_t n_warps, chunk_slots;
+  const uint4* inputs; uint4* out; uint32_t* status; uint32_t n_slots;
+  unsigned long long* clocks; uint32_t clock_rows;   // profiling aid (GW_LAT_CLOCKS, -DGW_PROFILING): [warp][row]{start, after wait, end, first opcode}
+};
+static const uint32_t DF_CTRL_BYTES = 384;  // 16 progress words (64 B) + 3 mbarriers x up to 12 warps (288 B), 16 B aligned
+
+__global__ void __launch_bounds__(LAT_MAX_THREADS) eval_dataflow_kernel(const DParams p) {
+  extern __shared__ uint4 lat_smem[];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(lat_smem);
+  const uint32_t bar0_s = smem_s + 64u;
+  if (tid < 16) reinterpret_cast<volatile uint32_t*>(lat_smem)[tid] = 0;
+  if (tid < 3u * p.n_warps) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s + 8u * tid) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (warp >= p.n_warps) return;
+  uint32_t st = 0;
+  LatCtx cx;
+  cx.inputs = p.inputs; cx.out = p.out; cx.slots_s = smem_s + DF_CTRL_BYTES; cx.dbg = 0;
+  const uint32_t chunk_bytes = p.chunk_slots * 16u;
+  const uint32_t ring_s = cx.slots_s + 32u * p.n_slots + warp * 3u * chunk_bytes;
+  const uint32_t n_chunks = __ldg(p.stream_chunks + warp);
+  const uint4* stream = p.code + __ldg(p.stream_off + warp);
+  auto request = [&](uint32_t c) {
+    if (c >= n_chunks || lane != 0u) return;
+    const uint32_t stage = c % 3u, bar = bar0_s + 8u * (3u * warp + stage);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // earlier generic reads of the stage vs the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(chunk_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ring_s + stage * chunk_bytes), "l"(stream + (size_t)c * p.chunk_slots), "r"(chunk_bytes), "r"(bar) : "memory");
+  };
+  request(0); request(1);
+  for (uint32_t c = 0; c < n_chunks; c++) {
+    const uint32_t stage = c % 3u, parity = (c / 3u) & 1u, bar = bar0_s + 8u * (3u * warp + stage);
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    __syncwarp();                                                         // every lane is done with chunk c - 1: its stage may be refilled
+    request(c + 2u);
+    uint32_t pk_s = ring_s + stage * chunk_bytes;
+    const uint32_t end_s = pk_s + chunk_bytes;
+    while (pk_s < end_s) {
+      const uint4 desc = lds128(pk_s);            // {slots, headers | lanes << 16, wait vector, packet number}
+      if (desc.x == 0u) break;
+#ifdef GW_PROFILING
+      unsigned long long tc0 = 0, tc1 = 0;
+      if (p.clocks) tc0 = clock64();
+#endif
+      if (desc.z != 0u) {
+        // lane k waits for warp k
+        if (lane < p.n_warps && lane != warp) {
+          uint32_t need;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(need) : "r"(pk_s + 16u * desc.z + 4u * lane));
+          if (need) while (flag_read(smem_s + 4u * lane) < need) { }
+        }
+        __threadfence_block();                    // acquire: the value-file loads below come after the counters were seen
+        __syncwarp();
+      }
+      const uint32_t nh = desc.y & 0xFFFFu, lanes = desc.y >> 16;
+#ifdef GW_PROFILING
+      if (p.clocks) tc1 = clock64();
+#endif
+      if (lane < lanes) for (uint32_t i = lane; i < nh; i += lanes) lat_exec(cx, pk_s, lds128(pk_s + 16u * (1u + i)), &st);
+      __syncwarp();
+      // release: the value-file stores of all lanes (ordered before lane 0 by __syncwarp) become visible before the counter
+      if (lane == 0) flag_publish(smem_s + 4u * warp, desc.w);
+#ifdef GW_PROFILING
+      if (p.clocks && lane == 0 && desc.w <= p.clock_rows) {
+        unsigned long long* c = p.clocks + ((size_t)warp * p.clock_rows + (desc.w - 1u)) * 4;
+        const uint4 h0 = lds128(pk_s + 16u);
+        c[0] = tc0; c[1] = tc1; c[2] = clock64(); c[3] = (unsigned long long)(h0.x & 0xFFu) | ((unsigned long long)lanes << 8) | ((unsigned long long)(h0.y & 0xFFFFFFu) << 16);
+      }
+#endif
+      pk_s += 16u * desc.x;
+    }
+  }
+  if (p.status != nullptr && st) atomicOr(p.status, st);
+}
+
 // ---- integer-pipe microbenchmark (roofline denominator for multiplication-heavy graphs) ---------
 // WHICH = 0: rows of (mad.lo.cc, madc.hi.cc) pairs exactly as in u256_mul_wide -> IMAD.WIDE.U32(.X)
 //            with carry predicates; counts one op per 32x32+64 multiply-accumulate,
@@ -880,6 +967,7 @@ struct Engine::Dev {
   // feedback for the speculation on the bit contract: how many input sets of the last bit-sliced launch broke it
   uint32_t* bit_nbad_host = nullptr; cudaEvent_t bit_nbad_ev = nullptr; size_t bit_nbad_sets = 0; bool bit_nbad_pending = false;
   // single-witness latency mode
+  uint32_t* lat_soff = nullptr; uint32_t* lat_schunks = nullptr;
   uint4* lat_code = nullptr; uint4* lat_first = nullptr; uint4* lat_jobs = nullptr; uint32_t* lat_njobs = nullptr; uint4* lat_waits = nullptr;
   unsigned long long* lat_clock = nullptr;
   uint4* lat_in = nullptr; uint4* lat_out = nullptr; uint32_t* lat_status = nullptr;
@@ -974,6 +1062,7 @@ Engine::~Engine() {
     cudaFree(d->bit_code); cudaFree(d->bit_inputs); cudaFree(d->bit_constpos); cudaFree(d->bit_consts); cudaFree(d->bit_wide); cudaFree(d->bit_field_inputs); cudaFree(d->bit_field_slots);
     cudaFree(d->bit_planes); cudaFree(d->bit_ok); cudaFree(d->bit_bad); cudaFree(d->bit_nbad);
     cudaFreeHost(d->bit_nbad_host); if (d->bit_nbad_ev) cudaEventDestroy(d->bit_nbad_ev);
+    cudaFree(d->lat_soff); cudaFree(d->lat_schunks);
     cudaFree(d->lat_code); cudaFree(d->lat_first); cudaFree(d->lat_jobs); cudaFree(d->lat_njobs); cudaFree(d->lat_waits); cudaFree(d->lat_clock); cudaFree(d->lat_in); cudaFree(d->lat_out); cudaFree(d->lat_status);
     for (int i = 0; i < 2; i++) { cudaFree(d->d_in[i]); cudaFree(d->d_out[i]); cudaFree(d->d_status[i]); if (d->stream[i]) cudaStreamDestroy(d->stream[i]); }
     for (int i = 0; i < 3; i++) { cudaFreeHost(d->h_ring[i]); cudaFreeHost(d->h_flags[i]); }
@@ -1003,6 +1092,7 @@ Engine::Dev* Engine::dev(int device) {
   if (t_max < 32) throw Error("register file does not fit shared memory: lower GW_REGS");
   d->max_threads = t_max;
   CUDA_CHECK(cudaFuncSetAttribute(eval_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
+  CUDA_CHECK(cudaFuncSetAttribute(eval_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));
   CUDA_CHECK(cudaFuncSetAttribute(eval_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_max));   // per device, not per graph
   CUDA_CHECK(cudaEventCreateWithFlags(&d->last_kernel, cudaEventDisableTiming));
   CUDA_CHECK(cudaMalloc(&d->code, plan.code.size() * sizeof(Instr)));
@@ -1396,15 +1486,25 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     if (!lat_ready) {
       cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
       LatencyOptions lo;
-      lo.n_warps = (uint32_t)env_int("GW_LAT_WARPS", (int)lo.n_warps);
+      // GW_LAT_MODE=level: the level-synchronous plan (control warp, CTA barrier per level); default: the dataflow plan
+      const char* lat_mode = getenv("GW_LAT_MODE");
+      lo.dataflow = !(lat_mode && strcmp(lat_mode, "level") == 0);
+      // dataflow: no control warp
+      // (measured on authV2, profiles/r02o: 6 + 3 warps 16.3 ms, 7 + 3: 16.9, 8 + 4: 17.6, 7 + 3 with warp 0 alone on its
+      // sub-partition: 18.1 -- every extra warp of dependent carry chains slows its sub-partition's other warps down)
+      lo.n_warps = (uint32_t)env_int("GW_LAT_WARPS", lo.dataflow ? 6 : (int)lo.n_warps);
+      lo.n_slow_warps = (uint32_t)env_int("GW_LAT_SLOW_WARPS", lo.dataflow ? 3 : (int)lo.n_slow_warps);
+      lo.exclusive_warp0 = env_int("GW_LAT_EXCL", 0) != 0;
       lo.packet_slots = LAT_RING_SLOTS;
+      const size_t df_rings = std::min<size_t>(12, lo.n_warps + lo.n_slow_warps + (lo.exclusive_warp0 ? 2 : 0));     // physical warps, empty ones included
+      if (lo.dataflow) lo.max_slots = (uint32_t)std::min<size_t>((prop.sharedMemPerBlockOptin / 16 - DF_CTRL_BYTES / 16 - df_rings * 3 * LAT_RING_SLOTS) / 2, 0xFFFF);
+      else
       lo.max_slots = (uint32_t)std::min<size_t>((prop.sharedMemPerBlockOptin / 16 - LAT_CTRL_BYTES / 16 - (size_t)lo.n_warps * 3 * LAT_RING_SLOTS) / 2, 0xFFFF);
-      lo.n_slow_warps = (uint32_t)env_int("GW_LAT_SLOW_WARPS", (int)lo.n_slow_warps);
       lo.slow_levels = (uint32_t)env_int("GW_LAT_D", 0);
       lo.split_dot = env_int("GW_LAT_SPLIT", 1) != 0;
       lo.fuse = env_int("GW_LAT_FUSE", 1) != 0;
       lo.chain = env_int("GW_LAT_CHAIN", 1) != 0;
-      if ((lo.n_warps + 1 + lo.n_slow_warps) * 32 > (uint32_t)LAT_MAX_THREADS) throw Error("GW_LAT_WARPS + GW_LAT_SLOW_WARPS must not exceed 11");
+      if (!lo.dataflow && (lo.n_warps + 1 + lo.n_slow_warps) * 32 > (uint32_t)LAT_MAX_THREADS) throw Error("GW_LAT_WARPS + GW_LAT_SLOW_WARPS must not exceed 11");
       try { lat_plan = compile_latency_plan(graph, lo); }
       catch (const Error& e) { lat_error = e.what(); throw; }
       lat_ready = true;
@@ -1412,6 +1512,65 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
   }
   const LatencyPlan& lp = lat_plan;
   const size_t in_b = (size_t)lp.n_inputs * 32;
+  if (lp.dataflow) {
+    const uint32_t NW = lp.n_phys_warps;
+    if (!d->lat_code) {
+      CUDA_CHECK(cudaMalloc(&d->lat_code, std::max<size_t>(lp.code.size(), 1) * sizeof(Instr)));
+      CUDA_CHECK(cudaMemcpy(d->lat_code, lp.code.data(), lp.code.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMalloc(&d->lat_soff, NW * 4)); CUDA_CHECK(cudaMalloc(&d->lat_schunks, NW * 4));
+      CUDA_CHECK(cudaMemcpy(d->lat_soff, lp.stream_off.data(), NW * 4, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(d->lat_schunks, lp.stream_chunks.data(), NW * 4, cudaMemcpyHostToDevice));
+    }
+    DParams q;
+    q.code = d->lat_code; q.stream_off = d->lat_soff; q.stream_chunks = d->lat_schunks; q.n_warps = NW; q.chunk_slots = lp.chunk_slots;
+    q.inputs = d->lat_in; q.out = d->lat_out; q.status = status ? d->lat_status : nullptr; q.n_slots = lp.n_slots;
+    const size_t smem_df = DF_CTRL_BYTES + (size_t)lp.n_slots * 32 + (size_t)NW * 3 * lp.chunk_slots * 16;
+    q.clocks = nullptr; q.clock_rows = 0;
+#ifdef GW_PROFILING
+    unsigned long long* d_clk = nullptr;
+    uint32_t max_rows = 0;
+    if (env_int("GW_LAT_CLOCKS", 0) != 0) {
+      // rows per warp are not stored in the plan: bound them by the packets in the streams
+      max_rows = (uint32_t)std::min<uint64_t>(lp.n_rows, 1u << 20);
+      CUDA_CHECK(cudaMalloc(&d_clk, (size_t)NW * max_rows * 32));
+      CUDA_CHECK(cudaMemset(d_clk, 0, (size_t)NW * max_rows * 32));
+      q.clocks = d_clk; q.clock_rows = max_rows;
+    }
+#endif
+    CUDA_CHECK(cudaMemcpyAsync(d->lat_in, inputs, in_b, cudaMemcpyHostToDevice, 0));
+    if (status) CUDA_CHECK(cudaMemsetAsync(d->lat_status, 0, 4, 0));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventRecord(e0, 0)); }
+    eval_dataflow_kernel<<<1, NW * 32, smem_df, 0>>>(q);
+    CUDA_CHECK(cudaGetLastError());
+    if (kernel_ms) CUDA_CHECK(cudaEventRecord(e1, 0));
+    CUDA_CHECK(cudaMemcpyAsync(witness, d->lat_out, (size_t)lp.n_witness * 32, cudaMemcpyDeviceToHost, 0));
+    if (status) CUDA_CHECK(cudaMemcpyAsync(status, d->lat_status, 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_CHECK(cudaStreamSynchronize(0));
+    if (kernel_ms) { CUDA_CHECK(cudaEventElapsedTime(kernel_ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+#ifdef GW_PROFILING
+    if (d_clk) {
+      // GW_LAT_CLOCKS=1: one line per packet "warp row start wait_end end opcode lanes" (cycles since the first packet)
+      std::vector<unsigned long long> c((size_t)NW * max_rows * 4);
+      CUDA_CHECK(cudaMemcpy(c.data(), d_clk, c.size() * 8, cudaMemcpyDeviceToHost));
+      cudaFree(d_clk);
+      const char* path = getenv("GW_LAT_CLOCKS_FILE");
+      FILE* f = fopen(path && *path ? path : "gw_lat_clocks.txt", "w");
+      if (f) {
+        unsigned long long t0 = ~0ull;
+        for (size_t k = 0; k < c.size(); k += 4) if (c[k + 2] && c[k] < t0) t0 = c[k];
+        for (uint32_t w = 0; w < NW; w++)
+          for (uint32_t r = 0; r < max_rows; r++) {
+            const unsigned long long* e = &c[((size_t)w * max_rows + r) * 4];
+            if (!e[2]) break;
+            fprintf(f, "%u %u %llu %llu %llu %llu %llu %llx\n", w, r, e[0] - t0, e[1] - t0, e[2] - t0, e[3] & 0xFF, (e[3] >> 8) & 0xFF, e[3] >> 16);
+          }
+        fclose(f);
+      }
+    }
+#endif
+    return;
+  }
   const size_t smem = ((size_t)lp.n_slots * 2 + LAT_CTRL_BYTES / 16 + (size_t)lp.n_warps * 3 * LAT_RING_SLOTS) * 16;
 #ifdef GW_PROFILING
   const bool clocks = env_int("GW_LAT_CLOCKS", 0) != 0;

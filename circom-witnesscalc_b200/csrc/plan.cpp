@@ -1087,6 +1087,47 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
     // if the packet would exceed `cap` slots (0 = no limit).  Header k belongs to lane k mod lanes, so a lane finds the
     // instructions of its chain at k = lane, lane + lanes, ...; shorter chains are padded with OP_NOP.
     // returns {offset, slots, headers, lanes}
+    // build_packet: the packet itself (pk_out), not yet placed; `reserve` = slots the caller appends behind it (they count
+    // against `cap`).  returns {headers, chains taken}
+    auto build_packet = [&](const std::vector<const LOp*>& list, size_t from, uint32_t cap, uint32_t reserve, std::vector<Instr>& pk) {
+      size_t n = std::min<size_t>(32, list.size() - from);
+      for (;; n = (n + 1) / 2) {
+        size_t rows = n ? 1 : 0;
+        for (size_t k = 0; k < n; k++) { size_t len = 0; for (const LOp* o = list[from + k]; o; o = o->chain_next >= 0 ? &ops[(size_t)o->chain_next] : nullptr) len++; rows = std::max(rows, len); }
+        const uint32_t nh = (uint32_t)(rows * n);
+        std::vector<Instr> hs(nh, make_instr(OP_NOP, 0, 0, 0, 0, 0)), extra, tmp;
+        std::vector<uint32_t> ebase(nh, 0);
+        for (size_t k = 0; k < n; k++) {
+          size_t r = 0;
+          for (const LOp* o = list[from + k]; o; o = o->chain_next >= 0 ? &ops[(size_t)o->chain_next] : nullptr, r++) {
+            tmp.clear();
+            hs[r * n + k] = header(*o, tmp);
+            ebase[r * n + k] = (uint32_t)extra.size();
+            extra.insert(extra.end(), tmp.begin(), tmp.end());
+          }
+        }
+        pk.assign(1 + nh, make_instr(OP_NOP, 0, 0, 0, 0, 0));
+        for (uint32_t i = 0; i < nh; i++) {
+          const uint32_t rb = 1 + nh + ebase[i];       // where this header's extras start in the packet
+          pk[1 + i] = rebase_header(hs[i], rb);
+          if ((hs[i].x & 0xFFu) == OP_DOT) {            // the term slots of an OP_DOT tail carry constant offsets too
+            const uint32_t nt = hs[i].y & 0xFFu;
+            for (uint32_t t = 0; t < nt; t++) {
+              Instr& sl = extra[ebase[i] + hs[i].z + (t >> 1)];
+              uint32_t& lo_w = (t & 1) ? sl.z : sl.x; uint32_t& ci = (t & 1) ? sl.w : sl.y;
+              const uint32_t kind = lo_w & 0xFu;
+              if (kind == T_MAC || kind == T_CONST) ci += rb;
+            }
+          }
+        }
+        pk.insert(pk.end(), extra.begin(), extra.end());
+        if (!cap || pk.size() + reserve <= cap || n <= 1) {
+          if (cap && pk.size() + reserve > cap) throw Error("latency plan: one chain does not fit a packet");
+          for (uint32_t i = 0; i < nh; i++) lp.n_instrs += (hs[i].x & 0xFFu) != OP_NOP;
+          return std::array<uint32_t, 2>{nh, (uint32_t)n};
+        }
+      }
+    };
     auto emit_packet = [&](const std::vector<const LOp*>& list, size_t from, uint32_t cap) {
       size_t n = std::min<size_t>(32, list.size() - from);
       std::vector<Instr> pk;
@@ -1130,6 +1171,193 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       }
     };
 
+    if (lo.dataflow) {
+      // ---- 3'. dataflow plan: per-warp instruction streams, no level barrier --------------------------------------
+      // Every warp (main and slow alike) walks its own stream of packets in order; a packet names, per other warp, how
+      // many of that warp's packets must be complete before it may start (operands produced there, and readers there
+      // of the values whose slots it overwrites).  Levels survive only as the order of emission, which is what makes
+      // the waits acyclic: a packet only ever waits for packets emitted before it, and a warp runs its packets in the
+      // order of emission.  A simple timing model (finish time per packet) steers the warp assignment.
+      // Physical warps: a warp's SM sub-partition (its own multiplier pipe) is its index mod 4.  Warp 0 takes the most
+      // critical instructions of every level and keeps its sub-partition to itself: warps 4 and 8 stay empty (measured:
+      // three warps of dependent carry chains on one sub-partition run 1.5x slower each, profiles/r02n).
+      std::vector<uint32_t> phys;                          // logical warp (mains first, then slows) -> physical warp
+      for (uint32_t skip = lo.exclusive_warp0 ? 2u : 0u;; skip--) {       // leave warps 4 and 8 empty, or only 4, or none: whatever fits 12 warps
+        phys.clear();
+        for (uint32_t id = 0; phys.size() < lo.n_warps + lo.n_slow_warps; id++) if (!(id > 0 && id % 4 == 0 && id / 4 <= skip)) phys.push_back(id);
+        if (phys.back() < 12 || skip == 0) break;
+      }
+      const uint32_t NW = phys.back() + 1;
+      if (NW > 12) throw Error("latency plan: more than 12 warps");
+      const uint32_t C = lo.packet_slots, WV = 3;          // chunk capacity (16 B slots); slots of a wait vector (12 words)
+      const uint64_t HOP = 150, ROW = 250;                 // cycles: a value crossing warps (publish + poll), fixed cost of a packet
+      auto df_cost = [&](const LOp& o) -> uint64_t {
+        switch (o.opc) {
+          case OP_MUL: return 920; case OP_SQR: return 780; case OP_POW5: return 2480;
+          case OP_DOT: { uint32_t n = 0; for (const PTerm& t : o.terms) n += t.kind == 0; return n ? 264 + 800ull * n : 300; }
+          case OP_ADD: case OP_SUB: return 80;
+          case OP_DIV: return 42700; case OP_INV: return 41750; case OP_POW: return 450000; case OP_IDIV: case OP_MOD: return 40000;
+          default: return 60;
+        }
+      };
+      const size_t NO = ops.size();
+      std::vector<int32_t> def_of(NV, -1);
+      for (size_t k = 0; k < NO; k++) if (ops[k].val != 0xFFFFFFFFu) def_of[ops[k].val] = (int32_t)k;
+      std::vector<uint64_t> blevel(NO, 0);                 // longest path from the start of the instruction to a sink
+      for (size_t k = 0; k < NO; k++) blevel[k] = df_cost(ops[k]);
+      for (size_t k = NO; k-- > 0;)
+        for_operands(ops[k], [&](uint32_t v) { const int32_t d = def_of[v]; if (d >= 0) blevel[(size_t)d] = std::max(blevel[(size_t)d], df_cost(ops[(size_t)d]) + blevel[k]); });
+      std::vector<std::vector<Instr>> stream(NW);
+      std::vector<uint32_t> fill(NW, 0);                   // slots used in the current chunk of each stream
+      std::vector<uint32_t> n_rows(NW, 0);
+      std::vector<std::vector<uint64_t>> row_finish(NW);   // timing model: finish time of packet r (0-based) of warp w
+      std::vector<uint64_t> t_warp(NW, 0);
+      std::vector<std::array<uint32_t, 12>> known(NW);     // what each warp has already waited for
+      for (auto& k : known) k.fill(0);
+      std::vector<uint32_t> prod_w(NV, 0xFFFFFFFFu), prod_r(NV, 0);   // producer (warp, 1-based packet number) of each value
+      std::vector<std::array<uint32_t, 12>> slot_busy;     // per slot: per warp, the last packet that touches its current value
+      std::vector<std::array<uint32_t, 12>> war_of(NO);    // per instruction: the busy vector of its destination slot's previous value
+      std::vector<uint32_t> fifo;                          // free slots, oldest first: their readers finished long ago
+      size_t fifo_head = 0;
+      const std::array<uint32_t, 12> zero12 = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      auto ready_time = [&](const LOp& o, uint32_t w) {
+        uint64_t t = 0;
+        for_operands(o, [&](uint32_t v) { if (prod_w[v] != 0xFFFFFFFFu) t = std::max(t, row_finish[prod_w[v]][prod_r[v] - 1] + (prod_w[v] != w ? HOP : 0)); });
+        return t;
+      };
+      auto close_chunk = [&](uint32_t w) {
+        if (fill[w] == 0) return;
+        // terminator descriptor (size 0) if there is room, then padding up to the chunk boundary
+        while (fill[w] < C) { stream[w].push_back(make_instr(OP_NOP, 0, 0, 0, 0, 0)); stream[w].back().x = 0; fill[w]++; }
+        fill[w] = 0;
+      };
+      // emits the instructions list[from ..] (one class, independent) as packets of warp w; returns how many it took
+      auto emit_df = [&](uint32_t w, const std::vector<const LOp*>& list, size_t from, uint64_t cost) {
+        // requirement vector: producers of the operands, and whoever touched the previous values of the destination slots
+        std::array<uint32_t, 12> req = zero12;
+        std::vector<Instr> pk;
+        const auto bp = build_packet(list, from, C, WV, pk);
+        const size_t n = bp[1];
+        for (size_t k = 0; k < n; k++) {
+          const LOp& o = *list[from + k];
+          for_operands(o, [&](uint32_t v) { if (prod_w[v] != 0xFFFFFFFFu && prod_w[v] != w) req[prod_w[v]] = std::max(req[prod_w[v]], prod_r[v]); });
+          const std::array<uint32_t, 12>& wr = war_of[(size_t)(&o - ops.data())];
+          for (uint32_t x = 0; x < NW; x++) if (x != w) req[x] = std::max(req[x], wr[x]);
+        }
+        bool need = false;
+        for (uint32_t x = 0; x < NW; x++) { if (req[x] > known[w][x]) { need = true; known[w][x] = req[x]; } }
+        uint32_t wait_off = 0;
+        if (need) {
+          wait_off = (uint32_t)pk.size();
+          for (uint32_t q = 0; q < WV; q++) { Instr sl; sl.x = known[w][4 * q]; sl.y = known[w][4 * q + 1]; sl.z = known[w][4 * q + 2]; sl.w = known[w][4 * q + 3]; pk.push_back(sl); }
+        }
+        if (pk.size() > C) throw Error("latency plan: packet larger than a chunk");
+        if (fill[w] + pk.size() > C) close_chunk(w);
+        const uint32_t row = ++n_rows[w];
+        pk[0].x = (uint32_t)pk.size(); pk[0].y = bp[0] | ((uint32_t)n << 16); pk[0].z = wait_off; pk[0].w = row;
+        stream[w].insert(stream[w].end(), pk.begin(), pk.end());
+        fill[w] += (uint32_t)pk.size();
+        if (fill[w] == C) fill[w] = 0;
+        // timing model
+        uint64_t start = t_warp[w];
+        if (need) for (uint32_t x = 0; x < NW; x++) if (x != w && req[x]) start = std::max(start, row_finish[x][req[x] - 1] + HOP);
+        for (size_t k = 0; k < n; k++) start = std::max(start, ready_time(*list[from + k], w));
+        const uint64_t end = start + ROW + cost;
+        t_warp[w] = end; row_finish[w].push_back(end);
+        // bookkeeping: producers, slot users
+        for (size_t k = 0; k < n; k++) {
+          const LOp& o = *list[from + k];
+          for_operands(o, [&](uint32_t v) { if (slot_of[v] >= 0) slot_busy[(size_t)slot_of[v]][w] = std::max(slot_busy[(size_t)slot_of[v]][w], row); });
+          if (o.val != 0xFFFFFFFFu) { prod_w[o.val] = w; prod_r[o.val] = row; if (slot_of[o.val] >= 0) slot_busy[(size_t)slot_of[o.val]][w] = std::max(slot_busy[(size_t)slot_of[o.val]][w], row); }
+        }
+        lp.n_rows++;
+        lp.n_waits_df += need;
+        return n;
+      };
+      std::vector<uint32_t> mains, slows;
+      for (uint32_t L = 0; L < n_levels; L++) {
+        mains.clear(); slows.clear();
+        for (uint32_t k : by_level[L]) { if (ops[k].slow) slows.push_back(k); else mains.push_back(k); }
+        // destination slots of everything issued at this level; the previous value's users become the instruction's WAR waits
+        for (uint32_t k : by_level[L]) {
+          const LOp& o = ops[k];
+          war_of[k] = zero12;
+          if (o.val == 0xFFFFFFFFu || last_use[o.val] < 0) continue;
+          uint32_t sl;
+          if (fifo_head < fifo.size()) { sl = fifo[fifo_head++]; war_of[k] = slot_busy[sl]; slot_busy[sl] = zero12; }
+          else { sl = n_slots++; slot_busy.push_back(zero12); if (n_slots > lo.max_slots) throw Error("latency plan: graph is too wide for the shared-memory value file"); }
+          slot_of[o.val] = (int32_t)sl;
+          dying[(size_t)last_use[o.val]].push_back(o.val);
+        }
+        // bundles: one class, operands ready at about the same time, at most 32; the most critical bundle picks its warp first
+        struct It { uint64_t cls, cost, ready, bl; const LOp* op; };
+        std::vector<It> items;
+        for (uint32_t k : mains) items.push_back({lat_class(ops[k]), df_cost(ops[k]), ready_time(ops[k], 0xFFFFFFFFu), blevel[k], &ops[k]});
+        std::stable_sort(items.begin(), items.end(), [](const It& a, const It& b) { return a.cls != b.cls ? a.cls < b.cls : a.ready < b.ready; });
+        struct Bundle { size_t a, b; uint64_t bl; };
+        std::vector<Bundle> bundles;
+        for (size_t a = 0; a < items.size();) {
+          size_t b = a; uint64_t bl = 0;
+          while (b < items.size() && b - a < 32 && items[b].cls == items[a].cls && items[b].ready <= items[a].ready + 400) { bl = std::max(bl, items[b].bl); b++; }
+          bundles.push_back({a, b, bl});
+          a = b;
+        }
+        std::stable_sort(bundles.begin(), bundles.end(), [](const Bundle& x, const Bundle& y) { return x.bl > y.bl; });
+        const uint64_t level_bl = bundles.empty() ? 0 : bundles[0].bl;
+        std::vector<const LOp*> list;
+        uint32_t width = 0;
+        for (const Bundle& bd : bundles) {
+          list.clear();
+          for (size_t k = bd.a; k < bd.b; k++) list.push_back(items[k].op);
+          width += (uint32_t)list.size();
+          // warp 0 is reserved for the critical bundles of the level (those on the longest remaining path)
+          const bool critical = !lo.exclusive_warp0 || lo.n_warps == 1 || bd.bl * 100 >= level_bl * 98;
+          uint32_t best = phys[critical ? 0 : 1]; uint64_t best_end = ~0ull;
+          for (uint32_t lw = critical ? 0 : 1; lw < lo.n_warps; lw++) {
+            const uint32_t w = phys[lw];
+            uint64_t rdy = 0;
+            for (const LOp* o : list) rdy = std::max(rdy, ready_time(*o, w));
+            const uint64_t end = std::max(t_warp[w], rdy) + ROW + items[bd.a].cost;
+            if (end < best_end) { best_end = end; best = w; }
+          }
+          for (size_t from = 0; from < list.size();) from += emit_df(best, list, from, items[bd.a].cost);
+        }
+        lp.max_level_width = std::max(lp.max_level_width, width);
+        // long ops: packets of up to 32 lanes of one opcode on the slow warp that is free first
+        std::stable_sort(slows.begin(), slows.end(), [&](uint32_t a, uint32_t b) { return ops[a].opc < ops[b].opc; });
+        for (size_t a = 0; a < slows.size();) {
+          size_t b = a;
+          while (b < slows.size() && b - a < 32 && ops[slows[b]].opc == ops[slows[a]].opc) b++;
+          list.clear();
+          for (size_t k = a; k < b; k++) list.push_back(&ops[slows[k]]);
+          uint32_t best = phys[lo.n_warps]; uint64_t best_end = ~0ull;
+          for (uint32_t lw = lo.n_warps; lw < lo.n_warps + lo.n_slow_warps; lw++) {
+            const uint32_t w = phys[lw];
+            uint64_t rdy = 0;
+            for (const LOp* o : list) rdy = std::max(rdy, ready_time(*o, w));
+            const uint64_t end = std::max(t_warp[w], rdy);
+            if (end < best_end) { best_end = end; best = w; }
+          }
+          for (size_t from = 0; from < list.size();) from += emit_df(best, list, from, df_cost(*list[0]));
+          a = b;
+        }
+        for (uint32_t v : dying[L]) fifo.push_back((uint32_t)slot_of[v]);
+      }
+      // streams -> code: whole chunks, back to back
+      lp.dataflow = true; lp.chunk_slots = C;
+      lp.stream_off.assign(NW, 0); lp.stream_chunks.assign(NW, 0);
+      for (uint32_t w = 0; w < NW; w++) {
+        close_chunk(w);
+        lp.stream_off[w] = (uint32_t)lp.code.size();
+        lp.stream_chunks[w] = (uint32_t)(stream[w].size() / C);
+        lp.code.insert(lp.code.end(), stream[w].begin(), stream[w].end());
+      }
+      for (uint32_t w = 0; w < NW; w++) lp.est_cycles = std::max<uint64_t>(lp.est_cycles, t_warp[w]);
+      lp.n_levels = n_levels;
+      lp.n_slots = std::max(n_slots, 1u);
+      lp.n_phys_warps = NW;
+      return lp;
+    }
     std::vector<uint32_t> mains, slows;
     for (uint32_t L = 0; L < n_levels; L++) {
       mains.clear(); slows.clear();
@@ -1260,7 +1488,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
   // chains trade levels for lane parallelism (instructions of different shapes cannot share a warp): keep whichever
   // schedule the cost model likes better (Poseidon / EdDSA graphs: chains; bit-level graphs like SHA-256: none)
   LatencyPlan a = plan_for(false);
-  if (!lo.chain) return a;
+  if (!lo.chain || lo.dataflow) return a;      // dataflow: an S-box is one OP_POW5 already; other chains would only serialise a lane
   LatencyPlan b = plan_for(true);
   return b.est_cycles < a.est_cycles ? b : a;
 }

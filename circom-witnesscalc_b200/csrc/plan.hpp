@@ -87,6 +87,8 @@ struct LatencyOptions {
   bool fuse = true;              // OP_DOT / OP_SHRAND fusion (off: one instruction per graph node)
   bool chain = true;             // run single-reader chains (x^2 -> x^4 -> x^5) in one lane inside one level
   uint32_t max_chain = 4;        // instructions per chain
+  bool dataflow = false;         // per-warp packet streams with wait vectors instead of level barriers (eval_dataflow_kernel)
+  bool exclusive_warp0 = false;  // dataflow: warp 0 takes the critical instructions and shares its SM sub-partition with nobody (measured: no gain)
 };
 struct LatencyPlan {
   std::vector<Instr> code;
@@ -99,6 +101,15 @@ struct LatencyPlan {
   uint32_t max_level_width = 0;
   uint64_t n_instrs = 0, n_slow = 0, n_split = 0, n_chained = 0;
   uint64_t est_cycles = 0;            // cost model: sum over levels of the slowest warp + per-level overhead
+  // dataflow plan (LatencyOptions::dataflow): code = the streams of warps 0 .. n_warps + n_slow_warps - 1, each a whole
+  // number of chunks of chunk_slots slots.  A chunk holds packets back to back: slot 0 of a packet = {slots of the packet
+  // (0: the chunk ends here), headers | lanes << 16, packet-relative slot of its wait vector (0: none), the packet's
+  // 1-based number in its warp's stream}; headers and extras as in a level-plan packet; the wait vector is 12 words:
+  // how many packets of warp k must be complete before this one starts.
+  bool dataflow = false;
+  std::vector<uint32_t> stream_off, stream_chunks;
+  uint32_t chunk_slots = 0, n_phys_warps = 0;     // stream_off / stream_chunks have n_phys_warps entries (some may be empty)
+  uint64_t n_rows = 0, n_waits_df = 0;
 };
 LatencyPlan compile_latency_plan(const Graph& g, const LatencyOptions& opt);
 

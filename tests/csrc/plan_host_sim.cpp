@@ -189,7 +189,7 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
   LatencyPlan lp;
   try {
     LatencyOptions o;
-    if (opts) { if (opts[0]) o.n_warps = opts[0]; if (opts[1]) o.n_slow_warps = opts[1]; o.slow_levels = opts[2]; o.split_dot = opts[3] != 0; o.fuse = opts[4] != 0; if (opts[5]) o.packet_slots = opts[5]; o.chain = opts[6] != 0; }
+    if (opts) { if (opts[0]) o.n_warps = opts[0]; if (opts[1]) o.n_slow_warps = opts[1]; o.slow_levels = opts[2]; o.split_dot = opts[3] != 0; o.fuse = opts[4] != 0; if (opts[5]) o.packet_slots = opts[5]; o.chain = opts[6] != 0; o.dataflow = opts[7] != 0; }
     lp = compile_latency_plan(s->g, o);
   } catch (const std::exception& e) { s->err = e.what(); return -2; }
   std::vector<fe> slots(lp.n_slots, fe_zero());
@@ -248,6 +248,61 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
     if ((ins.x & F_OUT) && op != OP_TERN) { if (ins.w >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
     return true;
   };
+  if (lp.dataflow) {
+    // Dataflow plan: every warp walks its own stream; a packet may start when the progress counters of the other warps
+    // have reached its wait vector.  The simulator picks the next runnable warp by policy -- mode 0: lowest warp first
+    // (slow warps as late as possible), mode 1: highest warp first (slow warps as early as possible), mode >= 2: pseudo-
+    // random with seed `mode` -- so that a missing wait (operand not yet produced, slot overwritten before its last
+    // reader) shows up as a wrong witness, and a cyclic wait as a deadlock (-4).
+    const uint32_t NW = lp.n_phys_warps, C = lp.chunk_slots;
+    if (lp.stream_off.size() != NW || C == 0) return -1;
+    std::vector<uint32_t> progress(NW, 0), chunk(NW, 0), off(NW, 0);
+    uint64_t rng = 0x9E3779B97F4A7C15ull * (uint64_t)(mode + 1), n_headers = 0;
+    auto cursor = [&](uint32_t w, size_t* pk) {            // next packet of warp w, or false at the end of its stream
+      while (chunk[w] < lp.stream_chunks[w]) {
+        const size_t base = (size_t)lp.stream_off[w] + (size_t)chunk[w] * C;
+        if (off[w] < C && lp.code[base + off[w]].x != 0) { *pk = base + off[w]; return true; }
+        chunk[w]++; off[w] = 0;
+      }
+      return false;
+    };
+    auto runnable = [&](uint32_t w, size_t pk) {
+      const Instr& d = lp.code[pk];
+      if (!d.z) return true;
+      for (uint32_t x = 0; x < NW; x++) {
+        const Instr& sl = lp.code[pk + d.z + x / 4];
+        const uint32_t need = (x & 3) == 0 ? sl.x : (x & 3) == 1 ? sl.y : (x & 3) == 2 ? sl.z : sl.w;
+        if (x != w && progress[x] < need) return false;
+      }
+      return true;
+    };
+    for (;;) {
+      std::vector<uint32_t> cand;
+      bool any_left = false;
+      for (uint32_t w = 0; w < NW; w++) { size_t pk; if (cursor(w, &pk)) { any_left = true; if (runnable(w, pk)) cand.push_back(w); } }
+      if (!any_left) break;
+      if (cand.empty()) return -4;
+      uint32_t w;
+      if (mode == 0) w = cand.front(); else if (mode == 1) w = cand.back();
+      else { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; w = cand[(size_t)(rng % cand.size())]; }
+      size_t pk; cursor(w, &pk);
+      const Instr d = lp.code[pk];
+      const uint32_t nh = d.y & 0xFFFFu, lanes = d.y >> 16;
+      if (d.x > C - off[w] || nh + 1 > d.x || lanes > 32 || (nh && !lanes) || d.w != progress[w] + 1) return -1;
+      std::vector<W> writes;
+      for (uint32_t lane = 0; lane < lanes; lane++) {
+        overlay.clear();
+        for (uint32_t k = lane; k < nh; k += lanes) { if (!exec(pk, lp.code[pk + 1 + k], writes)) return -1; n_headers++; }
+      }
+      overlay.clear();
+      for (const W& x : writes) slots[x.dst] = x.v;
+      progress[w] = d.w;
+      off[w] += d.x;
+    }
+    out8[0] = lp.n_levels; out8[1] = lp.n_slots; out8[2] = lp.n_instrs; out8[3] = lp.max_level_width; out8[4] = st;
+    out8[5] = lp.est_cycles; out8[6] = lp.n_rows; out8[7] = lp.slow_levels; out8[8] = lp.n_waits_df;
+    return 0;
+  }
   std::vector<uint32_t> next_job(lp.n_slow_warps, 0);
   auto run_job = [&](uint32_t w, uint32_t j) {
     const uint32_t* e = &lp.jobs[((size_t)w * lp.max_jobs + j) * 4];

@@ -163,8 +163,12 @@ def test_bad_inputs_return_errors(cwc):
 
 
 # GW_LAT_BIT=0: Boolean graphs (SHA-256, Num2Bits) also take the generic latency kernel instead of the bit-sliced plan
-LATENCY_ENVS = [{}, {"GW_LAT_BIT": "0"}, {"GW_LAT_CHAIN": "0", "GW_LAT_BIT": "0"}, {"GW_LAT_WARPS": "2", "GW_LAT_SLOW_WARPS": "1", "GW_LAT_D": "1"},
-                {"GW_LAT_WARPS": "5", "GW_LAT_D": "60", "GW_LAT_SPLIT": "0", "GW_LAT_BIT": "0"}, {"GW_LAT_FUSE": "0"}]
+# GW_LAT_MODE=level: the level-synchronous kernel (eval_latency_kernel); default: the dataflow kernel (eval_dataflow_kernel)
+LATENCY_ENVS = [{}, {"GW_LAT_MODE": "level"}, {"GW_LAT_BIT": "0"}, {"GW_LAT_MODE": "level", "GW_LAT_CHAIN": "0", "GW_LAT_BIT": "0"},
+                {"GW_LAT_WARPS": "2", "GW_LAT_SLOW_WARPS": "1", "GW_LAT_D": "1"}, {"GW_LAT_MODE": "level", "GW_LAT_WARPS": "2", "GW_LAT_SLOW_WARPS": "1", "GW_LAT_D": "1"},
+                {"GW_LAT_WARPS": "5", "GW_LAT_D": "60", "GW_LAT_SPLIT": "0", "GW_LAT_BIT": "0"},
+                {"GW_LAT_MODE": "level", "GW_LAT_WARPS": "5", "GW_LAT_D": "60", "GW_LAT_SPLIT": "0", "GW_LAT_BIT": "0"}, {"GW_LAT_FUSE": "0"},
+                {"GW_LAT_MODE": "level", "GW_LAT_FUSE": "0"}]
 
 
 @pytest.mark.parametrize("env", LATENCY_ENVS)

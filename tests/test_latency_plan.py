@@ -17,6 +17,12 @@ VARIANTS = [
     dict(n_warps=1, n_slow_warps=1, slow_levels=1),       # everything serialised, readers right behind the long ops
     dict(n_warps=3, slow_levels=3, packet_slots=24),      # tiny packets: wide levels are cut into many physical levels
     dict(n_warps=12, n_slow_warps=2, slow_levels=40),
+    # dataflow plan: per-warp packet streams with wait vectors; the simulator's `mode` picks the interleaving of the warps
+    dict(dataflow=True),
+    dict(dataflow=True, n_warps=1, n_slow_warps=1, slow_levels=1),
+    dict(dataflow=True, n_warps=3, slow_levels=3, packet_slots=24),
+    dict(dataflow=True, n_warps=8, n_slow_warps=4, fuse=False),
+    dict(dataflow=True, split_dot=False),
 ]
 
 
@@ -32,7 +38,7 @@ def test_random_graphs_all_ops(vi):
         g = util.SimGraph(po.serialize_graph(nodes, wit, imap), 12)
         for row in _rows(rnd, 6, 2):
             want = po.evaluate(nodes, row, wit, "circom")
-            for mode in (0, 1):
+            for mode in ((0, 1, 2, 3, 11) if VARIANTS[vi].get("dataflow") else (0, 1)):
                 got, info = g.eval_latency(row, mode=mode, **VARIANTS[vi])
                 assert got == want, (vi, t, mode)
 
@@ -60,7 +66,7 @@ def test_division_chains_and_parallel_divisions():
     for row in _rows(rnd, 6, 3) + [[1, 0, 0, 0, 0, 0, 0]]:              # division by zero -> 0 (graph.rs:109)
         want = po.evaluate(nodes, row, wit, "circom")
         for kw in VARIANTS:
-            for mode in (0, 1):
+            for mode in ((0, 1, 2, 7) if kw.get("dataflow") else (0, 1)):
                 got, info = g.eval_latency(row, mode=mode, **kw)
                 assert got == want, (kw, mode)
 
@@ -76,6 +82,7 @@ def test_edge_graphs():
         for row in _rows(rnd, n_in, 2):
             for mode in (0, 1):
                 assert g.eval_latency(row, mode=mode)[0] == po.evaluate(nodes, row, wit, "circom")
+                assert g.eval_latency(row, mode=mode, dataflow=True)[0] == po.evaluate(nodes, row, wit, "circom")
 
 
 @pytest.mark.parametrize("name", ["circuit5_poseidon", "circuit6_num2bits", "circuit11_key_expansion", "circuit8_sha256_512", "circuit9_authV2"])
@@ -85,8 +92,9 @@ def test_golden_circuits(name):
     buf = po.build_input_buffer(nodes, imap, po.deserialize_inputs(util.golden_inputs(name)))
     want = po.parse_wtns(util.golden_wtns(name))
     g = util.SimGraph(data, 12)
-    for kw in (dict(), dict(chain=False), dict(n_warps=2, slow_levels=2, packet_slots=40)):
-        for mode in (0, 1):
+    for kw in (dict(), dict(chain=False), dict(n_warps=2, slow_levels=2, packet_slots=40), dict(dataflow=True), dict(dataflow=True, n_warps=8),
+               dict(dataflow=True, n_warps=2, slow_levels=2, packet_slots=48)):
+        for mode in ((0, 1, 5) if kw.get("dataflow") else (0, 1)):
             got, info = g.eval_latency(buf, mode=mode, **kw)
             assert got == want, (name, kw, mode)
     got, info = g.eval_latency(buf)
@@ -108,5 +116,5 @@ def test_poseidon_like_graphs():
         g = util.SimGraph(po.serialize_graph(nodes, wit, imap), 12)
         row = _rows(rnd, 6, 1)[0]
         want = po.evaluate(nodes, row, wit, "circom")
-        for mode in (0, 1):
+        for mode in (0, 1, 2 + seed):
             assert g.eval_latency(row, mode=mode, **VARIANTS[seed % len(VARIANTS)])[0] == want, (seed, mode)
