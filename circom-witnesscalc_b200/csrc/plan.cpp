@@ -1190,14 +1190,17 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       const uint32_t NW = phys.back() + 1;
       if (NW > 12) throw Error("latency plan: more than 12 warps");
       const uint32_t C = lo.packet_slots, WV = 3;          // chunk capacity (16 B slots); slots of a wait vector (12 words)
-      const uint64_t HOP = 150, ROW = 250;                 // cycles: a value crossing warps (publish + poll), fixed cost of a packet
+      // cycles, measured in place per packet with 6 + 3 warps on the SM (profiles/r02p/clocks_authv2.summary.txt: medians
+      // from after the wait to the publish, interpreter included): about 650 cycles of fetch / decode / stores around the
+      // arithmetic, and the arithmetic itself 1.3 - 1.5x slower than alone on the SM
+      const uint64_t HOP = 150, ROW = 300;                 // a value crossing warps (publish + poll); descriptor + wait between two packets
       auto df_cost = [&](const LOp& o) -> uint64_t {
         switch (o.opc) {
-          case OP_MUL: return 920; case OP_SQR: return 780; case OP_POW5: return 2480;
-          case OP_DOT: { uint32_t n = 0; for (const PTerm& t : o.terms) n += t.kind == 0; return n ? 264 + 800ull * n : 300; }
-          case OP_ADD: case OP_SUB: return 80;
-          case OP_DIV: return 42700; case OP_INV: return 41750; case OP_POW: return 450000; case OP_IDIV: case OP_MOD: return 40000;
-          default: return 60;
+          case OP_MUL: return 1870; case OP_SQR: return 1580; case OP_POW5: return 3420;
+          case OP_DOT: { uint32_t n = 0; for (const PTerm& t : o.terms) n += t.kind == 0; return 1300 + 750ull * n + 60ull * (uint32_t)o.terms.size(); }
+          case OP_ADD: case OP_SUB: return 720;
+          case OP_DIV: return 53700; case OP_INV: return 52700; case OP_POW: return 500000; case OP_IDIV: case OP_MOD: return 50000;
+          default: return 700;
         }
       };
       const size_t NO = ops.size();
@@ -1482,7 +1485,9 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
     LatencyPlan first = schedule(24);
     if (first.n_slow == 0) return first;
     const double avg = std::max(200.0, (double)first.est_cycles / std::max(1u, first.n_levels));
-    const uint32_t D = (uint32_t)std::min(4096.0, std::max(2.0, 42000.0 / avg + 2.0));
+    // (dataflow plan: nothing waits at level boundaries, but a reader placed early in its warp's stream blocks what
+    // follows it until the long operation is done -- twice the distance measured best on authV2, profiles/r02q)
+    const uint32_t D = (uint32_t)std::min(4096.0, std::max(2.0, (lo.dataflow ? 2.0 * 53700.0 : 42000.0) / avg + 2.0));
     return schedule(D);
   };
   // chains trade levels for lane parallelism (instructions of different shapes cannot share a warp): keep whichever
