@@ -117,13 +117,17 @@ int gw_calc_witness_batch_device(gw_graph_t *graph, int device, const void *d_in
 /* Calls on one graph and device may come from any thread and any stream: the library runs the kernels of one graph
  * on one device one after the other (they share a per-device scratch area), in the order the calls were made. */
 
-/* single-witness latency mode (BASELINE config 5): ONE input set (n_inputs x 32 B, host) is evaluated by one
- * CTA: the graph is scheduled into dependency levels, the independent instructions of a level are spread over
- * the lanes of the main warps, the long operations (Div, Pow, Idiv, Mod) run asynchronously on dedicated warps;
- * witness is n_witness x 32 B (host).  *kernel_ms (optional) receives the device time of the kernel alone.
- * Fails with "latency plan: graph is too wide ..." when the values alive at one level do not fit the shared
- * memory of one SM.  gw_calc_witness / gw_graph_calc_witness use this mode for their single witness and fall
- * back to the throughput kernel with a batch of one in that case. */
+/* single-witness latency mode (BASELINE config 5): ONE input set (n_inputs x 32 B, host), parallel across the nodes
+ * of the graph's dependency levels; witness is n_witness x 32 B (host).  *kernel_ms (optional) receives the device time
+ * of the kernels alone.
+ *   - Boolean graphs (SHA-256, Num2Bits, comparators; gw_graph_info_t.bit_luts > 0) run their bit-sliced plan with
+ *     one warp: a step = up to 32 independent LUT nodes, one per lane.  An input set that breaks the plan's contract
+ *     (an input that must be 0 or 1 and is not) is evaluated by the generic kernel below in the same call.
+ *   - everything else: one CTA; every warp walks its own stream of packets (one instruction per lane), packets wait on
+ *     progress counters of the other warps; the long operations (Div, Pow, Idiv, Mod) have warps of their own.
+ * Fails with "latency plan: graph is too wide ..." when the values alive at once do not fit the shared memory of one
+ * SM.  gw_calc_witness / gw_graph_calc_witness use this mode for their single witness and fall back to the throughput
+ * kernel with a batch of one in that case. */
 int gw_calc_witness_latency(gw_graph_t *graph, int device, const uint8_t *inputs, uint8_t *witness, uint32_t *flags,
                             float *kernel_ms, gw_status_t *status);
 
