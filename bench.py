@@ -507,7 +507,8 @@ def main():
                    lambda: config_batch(cwc, torch, "2a: circuit6_num2bits x 65536", "circuit6_num2bits", 65536, 6, peaks, imad_lo),
                    lambda: config_batch(cwc, torch, "2b: circuit7_poseidon4 x 65536", "circuit7_poseidon4", 65536, 7, peaks, imad_lo),
                    lambda: config_batch(cwc, torch, "3: circuit8_sha256_512 x 16384", "circuit8_sha256_512", 16384, 8, peaks, imad_lo),
-                   lambda: config_single(cwc, "5: circuit9_authV2, single witness, latency mode vs one CPU thread", "circuit9_authV2")):
+                   lambda: config_single(cwc, "5: circuit9_authV2, single witness, latency mode vs one CPU thread", "circuit9_authV2"),
+                   lambda: config_single(cwc, "5 (same mode, a graph with wide levels): circuit8_sha256_512, single witness vs one CPU thread", "circuit8_sha256_512")):
             try:
                 configs.append(fn())
             except Exception as e:      # a failing side config must not take the headline line with it

@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
 struct DParams {
   const uint4* code; const uint32_t* stream_off; const uint32_t* stream_chunks; uint32_t n_warps, chunk_slots;
   const uint4* inputs; uint4* out; uint32_t* status; uint32_t n_slots;
+  uint32_t dbg;            // GW_LAT_DBG, -DGW_PROFILING timing experiments: 1 = no witness stores, 2 = publish without fence / atomic, 4 = poll with plain volatile loads
   unsigned long long* clocks; uint32_t clock_rows;   // profiling aid (GW_LAT_CLOCKS, -DGW_PROFILING): [warp][row]{start, after wait, end, first opcode}
 };
 static const uint32_t DF_CTRL_BYTES = 384;  // 16 progress words (64 B) + 3 mbarriers x up to 12 warps (288 B), 16 B aligned
@@ -796,7 +797,7 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_dataflow_kernel(const DP
   if (warp >= p.n_warps) return;
   uint32_t st = 0;
   LatCtx cx;
-  cx.inputs = p.inputs; cx.out = p.out; cx.slots_s = smem_s + DF_CTRL_BYTES; cx.dbg = 0;
+  cx.inputs = p.inputs; cx.out = p.out; cx.slots_s = smem_s + DF_CTRL_BYTES; cx.dbg = p.dbg;
   const uint32_t chunk_bytes = p.chunk_slots * 16u;
   const uint32_t ring_s = cx.slots_s + 32u * p.n_slots + warp * 3u * chunk_bytes;
   const uint32_t n_chunks = __ldg(p.stream_chunks + warp);
@@ -831,6 +832,10 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_dataflow_kernel(const DP
         if (lane < p.n_warps && lane != warp) {
           uint32_t need;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(need) : "r"(pk_s + 16u * desc.z + 4u * lane));
+#ifdef GW_PROFILING
+          if (need && (p.dbg & 4u)) { uint32_t have; do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(have) : "r"(smem_s + 4u * lane) : "memory"); } while (have < need); }
+          else
+#endif
           if (need) while (flag_read(smem_s + 4u * lane) < need) { }
         }
         __threadfence_block();                    // acquire: the value-file loads below come after the counters were seen
@@ -843,6 +848,10 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_dataflow_kernel(const DP
       if (lane < lanes) for (uint32_t i = lane; i < nh; i += lanes) lat_exec(cx, pk_s, lds128(pk_s + 16u * (1u + i)), &st);
       __syncwarp();
       // release: the value-file stores of all lanes (ordered before lane 0 by __syncwarp) become visible before the counter
+#ifdef GW_PROFILING
+      if (p.dbg & 2u) { if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_s + 4u * warp), "r"(desc.w) : "memory"); }
+      else
+#endif
       if (lane == 0) flag_publish(smem_s + 4u * warp, desc.w);
 #ifdef GW_PROFILING
       if (p.clocks && lane == 0 && desc.w <= p.clock_rows) {
@@ -1527,7 +1536,10 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     q.code = d->lat_code; q.stream_off = d->lat_soff; q.stream_chunks = d->lat_schunks; q.n_warps = NW; q.chunk_slots = lp.chunk_slots;
     q.inputs = d->lat_in; q.out = d->lat_out; q.status = status ? d->lat_status : nullptr; q.n_slots = lp.n_slots;
     const size_t smem_df = DF_CTRL_BYTES + (size_t)lp.n_slots * 32 + (size_t)NW * 3 * lp.chunk_slots * 16;
-    q.clocks = nullptr; q.clock_rows = 0;
+    q.clocks = nullptr; q.clock_rows = 0; q.dbg = 0;
+#ifdef GW_PROFILING
+    q.dbg = (uint32_t)env_int("GW_LAT_DBG", 0);
+#endif
 #ifdef GW_PROFILING
     unsigned long long* d_clk = nullptr;
     uint32_t max_rows = 0;
