@@ -210,7 +210,8 @@ class Graph:
         rc = _L.gw_inputs_parse_batch(self._h, text, len(text), n_threads, ctypes.byref(out), ctypes.byref(n), ctypes.byref(st))
         _check(rc, st)
         nbytes = n.value * self.n_inputs * 32
-        arr = np.frombuffer(ctypes.string_at(out.value, nbytes), dtype=np.uint8).reshape(n.value, self.n_inputs, 32).copy()
+        arr = np.ctypeslib.as_array(ctypes.cast(out, ctypes.POINTER(ctypes.c_uint8)), shape=(max(nbytes, 1),))[:nbytes]
+        arr = arr.reshape(n.value, self.n_inputs, 32).copy()           # one copy out of the malloc'ed buffer
         _libc.free(out)
         return arr
 

@@ -197,12 +197,9 @@ int gw_inputs_parse_batch(const gw_graph_t* graph, const char* text, size_t text
                           size_t* n_sets, gw_status_t* status) {
   if (!graph || !text || !inputs || !n_sets) { set_status(status, ERROR, "null argument"); return 1; }
   return guarded(status, [&]() {
-    std::vector<U256> rows;
-    size_t n = parse_inputs_batch(graph->engine->graph, text, text_len, n_threads, rows);
-    uint8_t* out = (uint8_t*)malloc(std::max<size_t>(rows.size() * sizeof(U256), 1));
-    if (!out) throw Error("Failed to allocate memory for the input buffer");
-    memcpy(out, rows.data(), rows.size() * sizeof(U256));
-    *inputs = out; *n_sets = n;
+    U256* rows = nullptr;
+    size_t n = parse_inputs_batch(graph->engine->graph, text, text_len, n_threads, &rows);
+    *inputs = (uint8_t*)rows; *n_sets = n;
   });
 }
 

@@ -25,6 +25,7 @@ struct U256 {
 U256 u256_from_le_bytes_mod_order(const uint8_t* p, size_t n);   // Fr::from_le_bytes_mod_order, storage.rs:28
 U256 u256_from_u64(uint64_t v);
 bool u256_parse_dec(const std::string& s, U256* out);            // U256::from_str_radix(s, 10), lib.rs:208
+bool u256_parse_dec_digits(const char* s, size_t n, U256* out);  // the same for a run of decimal digits (no underscores)
 extern const U256 BN254_M;
 
 enum NodeKind : uint8_t { N_INPUT = 0, N_CONST = 1, N_UNO = 2, N_DUO = 3, N_TRES = 4 };

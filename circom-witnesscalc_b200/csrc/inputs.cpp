@@ -1,5 +1,6 @@
 #include "inputs.hpp"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -83,6 +84,11 @@ struct J {
 U256 parse_scalar(J& j, const std::string& key, bool in_array) {
   char c = j.peek();
   if (c == '"') {
+    // the common case, without a std::string: "<decimal digits>"
+    const char* q = j.p + 1;
+    while (q < j.end && *q >= '0' && *q <= '9') q++;
+    U256 fast;
+    if (q < j.end && *q == '"' && q > j.p + 1 && u256_parse_dec_digits(j.p + 1, (size_t)(q - j.p - 1), &fast)) { j.p = q + 1; return fast; }
     std::string s = j.str();
     U256 v;
     if (!u256_parse_dec(s, &v)) throw Error("Failed to calculate witness: InputFieldNumberParseError(\"" + s + "\")");
@@ -174,23 +180,27 @@ static void split_records(const char* text, size_t len, std::vector<std::pair<si
     for (; i < len; i++) if (!(text[i] == ' ' || text[i] == '\t' || text[i] == '\n' || text[i] == '\r')) throw Error("Failed to parse inputs: invalid JSON: trailing characters");
     return;
   }
+  // JSON Lines: memchr finds the line ends (this scan is the serial part of the batch parser)
   size_t ls = 0;
-  for (size_t k = 0; k <= len; k++) {
-    if (k == len || text[k] == '\n') {
-      size_t a = ls, b = k;
-      while (a < b && (text[a] == ' ' || text[a] == '\t' || text[a] == '\r')) a++;
-      while (b > a && (text[b - 1] == ' ' || text[b - 1] == '\t' || text[b - 1] == '\r')) b--;
-      if (b > a) rec.emplace_back(a, b);
-      ls = k + 1;
-    }
+  while (ls <= len) {
+    const char* nl = ls < len ? (const char*)memchr(text + ls, '\n', len - ls) : nullptr;
+    const size_t k = nl ? (size_t)(nl - text) : len;
+    size_t a = ls, b = k;
+    while (a < b && (text[a] == ' ' || text[a] == '\t' || text[a] == '\r')) a++;
+    while (b > a && (text[b - 1] == ' ' || text[b - 1] == '\t' || text[b - 1] == '\r')) b--;
+    if (b > a) rec.emplace_back(a, b);
+    ls = k + 1;
   }
 }
 
-size_t parse_inputs_batch(const Graph& g, const char* text, size_t len, int n_threads, std::vector<U256>& out) {
+size_t parse_inputs_batch(const Graph& g, const char* text, size_t len, int n_threads, U256** out_rows) {
   std::vector<std::pair<size_t, size_t>> rec;
   split_records(text, len, rec);
   const size_t n = rec.size(), I = g.inputs_size;
-  out.assign(n * I, u256_from_u64(0));
+  // every row is written whole by the thread that parses its record: no zero fill, no second copy
+  U256* out = (U256*)malloc(std::max<size_t>(n * I * sizeof(U256), 1));
+  if (!out) throw Error("Failed to allocate memory for the input buffer");
+  *out_rows = out;
   if (n == 0) return 0;
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
   n_threads = (int)std::min<size_t>((size_t)n_threads, (n + 63) / 64);
@@ -216,7 +226,7 @@ size_t parse_inputs_batch(const Graph& g, const char* text, size_t len, int n_th
   for (int t = 1; t < n_threads; t++) th.emplace_back(work);
   work();
   for (auto& t : th) t.join();
-  if (err_rec != (size_t)-1) throw Error("input set " + std::to_string(err_rec + 1) + ": " + err);
+  if (err_rec != (size_t)-1) { free(out); *out_rows = nullptr; throw Error("input set " + std::to_string(err_rec + 1) + ": " + err); }
   return n;
 }
 

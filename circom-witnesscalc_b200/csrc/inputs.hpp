@@ -19,7 +19,8 @@ std::vector<U256> build_inputs_buffer(const Graph& g, const InputList& inputs);
 // JSON array of objects is accepted too) -> n_sets x inputs_size x 32 B packed little-endian rows, parsed by
 // n_threads host threads (0 = hardware concurrency).  Every row goes through deserialize_inputs +
 // build_inputs_buffer, so values, errors and missing-key behaviour are those of the single-witness path.
-// Errors name the 1-based record.  `out` is resized to n_sets * inputs_size.
-size_t parse_inputs_batch(const Graph& g, const char* text, size_t len, int n_threads, std::vector<U256>& out);
+// Errors name the 1-based record.  *out_rows receives a malloc'ed buffer of n_sets * inputs_size values (caller frees;
+// null after an error).
+size_t parse_inputs_batch(const Graph& g, const char* text, size_t len, int n_threads, U256** out_rows);
 
 }  // namespace gw
