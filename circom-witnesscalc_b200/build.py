@@ -14,6 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libcircom_witnesscalc.so")
+# the same library with -DGW_PROFILING: per-packet clocks, timing experiments and the fault injection that the watchdog
+# test needs (tests/test_gpu_parity.py); loaded through GW_LIB_PATH only
+LIB_PROF = os.path.join(HERE, "lib_variants", "libcwc_prof.so")
 BIN = os.path.join(HERE, "bin", "calc-witness")
 BIN_BATCH = os.path.join(HERE, "bin", "calc-witness-batch")
 # the reference's own C embedding example (examples/calc_witness.c), compiled UNCHANGED from where it lies against this
@@ -42,6 +45,11 @@ def build(force=False, verbose=False):
                "-Xptxas", "-v" if verbose else "-O3", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
         if verbose:
             print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    if force or _newer(LIB_PROF, deps):
+        os.makedirs(os.path.dirname(LIB_PROF), exist_ok=True)
+        cmd = [NVCC, "-shared", "-Xcompiler", "-fPIC,-O3", "-std=c++17", "-O3", "-lineinfo", *ARCH, "-DGW_PROFILING",
+               "-o", LIB_PROF] + [os.path.join(CSRC, s) for s in SOURCES]
         subprocess.check_call(cmd)
     if force or _newer(BIN, [LIB, os.path.join(CSRC, "calc_witness_main.cpp")]):
         cmd = ["g++", "-O2", "-std=c++17", "-o", BIN, os.path.join(CSRC, "calc_witness_main.cpp"),

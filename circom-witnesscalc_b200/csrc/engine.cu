@@ -780,9 +780,13 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_latency_kernel(const LPa
 struct DParams {
   const uint4* code; const uint32_t* stream_off; const uint32_t* stream_chunks; uint32_t n_warps, chunk_slots;
   const uint4* inputs; uint4* out; uint32_t* status; uint32_t n_slots;
-  uint32_t dbg;            // GW_LAT_DBG, -DGW_PROFILING timing experiments: 1 = no witness stores, 2 = publish without fence / atomic, 4 = poll with plain volatile loads
+  uint32_t watchdog;       // polls after which a wait gives up (DF_WATCHDOG_SPINS; GW_LAT_WATCHDOG)
+  uint32_t dbg;            // GW_LAT_DBG, -DGW_PROFILING experiments: 1 = no witness stores, 2 = publish without fence / atomic, 4 = poll with plain
+                           // volatile loads, 8 = fault injection: warp 1's first wait can never be satisfied (watchdog test)
   unsigned long long* clocks; uint32_t clock_rows;   // profiling aid (GW_LAT_CLOCKS, -DGW_PROFILING): [warp][row]{start, after wait, end, first opcode}
 };
+static const uint32_t DF_ABORT_WORD = 15;              // control word 15: set by a warp whose wait ran into the watchdog; everybody leaves
+static const uint32_t DF_WATCHDOG_SPINS = 1u << 28;    // polls of one wait (tens of seconds: the longest real wait is a Pow, < 1 ms)
 static const uint32_t DF_CTRL_BYTES = 384;  // 16 progress words (64 B) + 3 mbarriers x up to 12 warps (288 B), 16 B aligned
 
 __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_dataflow_kernel(const DParams p) {
@@ -836,10 +840,26 @@ __global__ void __launch_bounds__(LAT_MAX_THREADS) eval_dataflow_kernel(const DP
           if (need && (p.dbg & 4u)) { uint32_t have; do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(have) : "r"(smem_s + 4u * lane) : "memory"); } while (have < need); }
           else
 #endif
-          if (need) while (flag_read(smem_s + 4u * lane) < need) { }
+#ifdef GW_PROFILING
+          if ((p.dbg & 8u) && warp == 1u && need) need += 1000000u;
+#endif
+          if (need) {
+            // watchdog: a wait that no packet will ever satisfy (a plan-compiler bug) must end as an error, not as a hung GPU
+            uint32_t spins = 0;
+            while (flag_read(smem_s + 4u * lane) < need) {
+              if ((++spins & 0xFFFFu) == 0u && (flag_read(smem_s + 4u * DF_ABORT_WORD) != 0u || spins > p.watchdog)) {
+                flag_publish(smem_s + 4u * DF_ABORT_WORD, 1u);
+                break;
+              }
+            }
+          }
         }
         __threadfence_block();                    // acquire: the value-file loads below come after the counters were seen
         __syncwarp();
+        if (flag_read(smem_s + 4u * DF_ABORT_WORD) != 0u) {       // warp-uniform: read after the __syncwarp
+          if (lane == 0 && p.status != nullptr) atomicOr(p.status, 0x80000000u);
+          return;
+        }
       }
       const uint32_t nh = desc.y & 0xFFFFu, lanes = desc.y >> 16;
 #ifdef GW_PROFILING
@@ -1534,9 +1554,10 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     }
     DParams q;
     q.code = d->lat_code; q.stream_off = d->lat_soff; q.stream_chunks = d->lat_schunks; q.n_warps = NW; q.chunk_slots = lp.chunk_slots;
-    q.inputs = d->lat_in; q.out = d->lat_out; q.status = status ? d->lat_status : nullptr; q.n_slots = lp.n_slots;
+    q.inputs = d->lat_in; q.out = d->lat_out; q.status = d->lat_status; q.n_slots = lp.n_slots;
     const size_t smem_df = DF_CTRL_BYTES + (size_t)lp.n_slots * 32 + (size_t)NW * 3 * lp.chunk_slots * 16;
     q.clocks = nullptr; q.clock_rows = 0; q.dbg = 0;
+    q.watchdog = (uint32_t)env_int("GW_LAT_WATCHDOG", (int)DF_WATCHDOG_SPINS);
 #ifdef GW_PROFILING
     q.dbg = (uint32_t)env_int("GW_LAT_DBG", 0);
 #endif
@@ -1552,16 +1573,20 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
     }
 #endif
     CUDA_CHECK(cudaMemcpyAsync(d->lat_in, inputs, in_b, cudaMemcpyHostToDevice, 0));
-    if (status) CUDA_CHECK(cudaMemsetAsync(d->lat_status, 0, 4, 0));
+    CUDA_CHECK(cudaMemsetAsync(d->lat_status, 0, 4, 0));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventRecord(e0, 0)); }
     eval_dataflow_kernel<<<1, NW * 32, smem_df, 0>>>(q);
     CUDA_CHECK(cudaGetLastError());
     if (kernel_ms) CUDA_CHECK(cudaEventRecord(e1, 0));
+    uint32_t h_status = 0;
     CUDA_CHECK(cudaMemcpyAsync(witness, d->lat_out, (size_t)lp.n_witness * 32, cudaMemcpyDeviceToHost, 0));
-    if (status) CUDA_CHECK(cudaMemcpyAsync(status, d->lat_status, 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_CHECK(cudaMemcpyAsync(&h_status, d->lat_status, 4, cudaMemcpyDeviceToHost, 0));
     CUDA_CHECK(cudaStreamSynchronize(0));
     if (kernel_ms) { CUDA_CHECK(cudaEventElapsedTime(kernel_ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    // (the "latency plan:" prefix makes gw_calc_witness fall back to the throughput kernel, capi.cpp)
+    if (h_status & 0x80000000u) throw Error("latency plan: a packet waited for progress that never came (watchdog); please report the graph");
+    if (status) *status = h_status;
 #ifdef GW_PROFILING
     if (d_clk) {
       // GW_LAT_CLOCKS=1: one line per packet "warp row start wait_end end opcode lanes" (cycles since the first packet)

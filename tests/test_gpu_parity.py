@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the Python oracle and the
 committed golden .wtns files.  Bit-exact comparison everywhere (integer arithmetic)."""
 import importlib
+import os
 import random
 
 import numpy as np
@@ -549,3 +550,37 @@ def test_latency_mode_boolean_graph_uses_bit_plan_and_falls_back(cwc):
                 row[1 + rnd.randrange(n_in)] = rnd.choice([2, po.M - 1, rnd.randrange(po.M)])
             out, ms = g.calc_witness_latency(np.frombuffer(util.pack_u256(row), dtype=np.uint8).reshape(n_in + 1, 32))
             assert util.unpack_u256(out.tobytes()) == po.evaluate(nodes, row, wit, "circom"), (t, broken)
+
+
+def test_dataflow_watchdog_turns_a_stuck_wait_into_an_error_and_a_fallback(tmp_path):
+    """A wait that no packet satisfies (injected in the -DGW_PROFILING build of the library: GW_LAT_DBG=8) must not hang the
+    GPU: the kernel's watchdog ends it, gw_calc_witness_latency reports it, and the drop-in gw_calc_witness falls back to
+    the throughput kernel and still returns the right .wtns."""
+    import subprocess
+    import sys
+    prof = os.path.join(util.ROOT, "circom-witnesscalc_b200", "lib_variants", "libcwc_prof.so")
+    if not os.path.exists(prof):
+        pytest.skip("profiling build of the library not present")
+    code = r'''
+import importlib, sys
+sys.path.insert(0, %r)
+import numpy as np
+from tests import util
+from tests.util import po
+cwc = importlib.import_module("circom-witnesscalc_b200")
+name = "circuit5_poseidon"
+data = util.golden_graph(name)
+nodes, wit, imap = po.deserialize_graph(data)
+g = cwc.Graph(data)
+buf = po.build_input_buffer(nodes, imap, po.deserialize_inputs(util.golden_inputs(name)))
+try:
+    g.calc_witness_latency(np.frombuffer(util.pack_u256(buf), dtype=np.uint8).reshape(g.n_inputs, 32))
+    print("NO-ERROR")
+except cwc.WitnessCalcError as e:
+    print("ERR", e)
+print("WTNS-OK" if cwc.calc_witness_wtns(util.golden_inputs(name), data) == util.golden_wtns(name) else "WTNS-BAD")
+''' % util.ROOT
+    env = dict(os.environ, GW_LIB_PATH=prof, GW_LAT_DBG="8", GW_LAT_WATCHDOG="262144", GW_LAT_WARPS="3")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert "ERR" in r.stdout and "watchdog" in r.stdout, r.stdout + r.stderr
+    assert "WTNS-OK" in r.stdout, r.stdout + r.stderr
