@@ -39,6 +39,10 @@ pub struct gw_graph_info_t {
     pub threads: u32,
     pub sets_per_thread: u32,
     pub n_narrow_instr: u32,
+    pub bit_eligible: u32,
+    pub bit_luts: u32,
+    pub bit_steps: u32,
+    pub bit_wide: u32,
 }
 
 pub type gw_witness_chunk_fn = unsafe extern "C" fn(
