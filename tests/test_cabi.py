@@ -91,3 +91,20 @@ def test_reference_c_example_links_unchanged(cwc, tmp_path):
     # CLI contract of the reference binary (calc-witness.rs:13-19): wrong argc -> usage on stderr, exit 1
     r = subprocess.run([cwc.CLI_PATH], capture_output=True, text=True)
     assert r.returncode == 1 and "Usage:" in r.stderr and "<graph.bin> <inputs.json> <witness.wtns>" in r.stderr
+
+
+def test_info_struct_is_the_same_in_the_header_the_python_binding_and_the_rust_shim():
+    """gw_graph_info_t is filled by the library: a binding with fewer fields would be written past its end"""
+    import re
+    hdr = open(os.path.join(util.ROOT, "include", "graph_witness.h")).read()
+    end = hdr.index("} gw_graph_info_t;")
+    body = hdr[hdr.rindex("typedef struct", 0, end):end]
+    c_fields = re.findall(r"^\s*(uint64_t|uint32_t)\s+(\w+);", body, re.M)
+    cwc = importlib.import_module("circom-witnesscalc_b200")
+    py_fields = [(("uint64_t" if t is ctypes.c_uint64 else "uint32_t"), n) for n, t in cwc.gw_graph_info_t._fields_]
+    assert c_fields == py_fields and len(c_fields) >= 24
+    rs = open(os.path.join(util.ROOT, "rust-shim", "src", "ffi.rs")).read()
+    rbody = rs[rs.index("pub struct gw_graph_info_t"):]
+    rbody = rbody[:rbody.index("}")]
+    rs_fields = [(("uint64_t" if t == "u64" else "uint32_t"), n) for n, t in re.findall(r"pub (\w+): (u64|u32),", rbody)]
+    assert rs_fields == c_fields
