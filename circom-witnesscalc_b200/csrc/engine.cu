@@ -645,6 +645,14 @@ __device__ __forceinline__ void lat_exec(const LatCtx& cx, uint32_t pk_s, const 
     const fe x4 = fe_sqr(x2);
     if (d4 != 0xFFFFu) { cx.out[2 * (size_t)(ins.z + d4)] = fe_lo(x4); cx.out[2 * (size_t)(ins.z + d4) + 1] = fe_hi(x4); }
     R = fe_mul(x4, A);
+  } else if (op == OP_POW4) {
+    // the S-box of a rewritten S-box link (plan.cpp: rewrite_sbox_links): x^2 to the witness, x^4 to its slot and the witness
+    const fe x2 = fe_sqr(slot_load(ins.y));
+    if (ins.z != NO_POS) { cx.out[2 * (size_t)ins.z] = fe_lo(x2); cx.out[2 * (size_t)ins.z + 1] = fe_hi(x2); }
+    R = fe_sqr(x2);
+  } else if (op == OP_MULADD) {
+    const fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z), C = operand(ins.x & F_C_CONST, ins.w);
+    R = fe_add(fe_mul(A, Bv), C);
   } else if (op == OP_ADD || op == OP_SUB) {
     const fe A = operand(ins.x & F_A_CONST, ins.y), Bv = operand(ins.x & F_B_CONST, ins.z);
     R = (op == OP_ADD) ? fe_add(A, Bv) : fe_sub(A, Bv);
@@ -659,7 +667,7 @@ __device__ __forceinline__ void lat_exec(const LatCtx& cx, uint32_t pk_s, const 
     R = Rr;
   }
   if (dst != NO_DST) { sts128(cx.slots_s + 32u * dst, fe_lo(R)); sts128(cx.slots_s + 32u * dst + 16u, fe_hi(R)); }
-  if ((ins.x & F_OUT) && op != OP_TERN && !(cx.dbg & 1u)) { cx.out[2 * (size_t)ins.w] = fe_lo(R); cx.out[2 * (size_t)ins.w + 1] = fe_hi(R); }
+  if ((ins.x & F_OUT) && op != OP_TERN && op != OP_MULADD && !(cx.dbg & 1u)) { cx.out[2 * (size_t)ins.w] = fe_lo(R); cx.out[2 * (size_t)ins.w + 1] = fe_hi(R); }
 }
 // one instruction of a slow-warp job: its packet stays in global memory, only the rare operations occur
 __device__ __forceinline__ void lat_exec_slow(const LatCtx& cx, const uint4* pk, const uint4 ins, uint32_t* st) {
@@ -1534,6 +1542,8 @@ void Engine::run_latency(int device, const uint8_t* inputs, uint8_t* witness, ui
       lo.slow_levels = (uint32_t)env_int("GW_LAT_D", 0);
       lo.split_dot = env_int("GW_LAT_SPLIT", 1) != 0;
       lo.fuse = env_int("GW_LAT_FUSE", 1) != 0;
+      lo.sbox_links = env_int("GW_LAT_LINKS", 1) != 0;           // 0: never, 1: where the timing model prefers it, 2: always
+      lo.force_sbox_links = env_int("GW_LAT_LINKS", 1) == 2;
       lo.chain = env_int("GW_LAT_CHAIN", 1) != 0;
       if (!lo.dataflow && (lo.n_warps + 1 + lo.n_slow_warps) * 32 > (uint32_t)LAT_MAX_THREADS) throw Error("GW_LAT_WARPS + GW_LAT_SLOW_WARPS must not exceed 11");
       try { lat_plan = compile_latency_plan(graph, lo); }

@@ -34,6 +34,9 @@ enum Opcode : uint32_t {
   OP_POW5 = 55,      // dst <- a^5 with a^2, a^4 also stored as witness values (Poseidon S-box: x2 = x*x; x4 = x2*x2; x5 = x4*x);
                      // .y = register of a | d4 << 16, .z = witness position of a^2 (NO_POS: none), a^4 goes to position
                      // .z + d4 (d4 = 0xFFFF: none), .w = position of a^5 (F_OUT).  Throughput plan only.
+  OP_POW4 = 56,      // dst <- a^4, a^2 stored at witness position .z (NO_POS: none), a^4 at .w (F_OUT).  Latency plans only.
+  OP_MULADD = 57,    // dst <- a * b + c (mod M); .w is operand c, so a witness store is a separate OP_OUT (like TernCond).
+                     // Latency plans only: S-box to S-box links, plan.cpp rewrite_sbox_links.
   OP_NOP = 63,
 };
 

@@ -31,7 +31,7 @@ std::vector<uint8_t> liveness(const Graph& g) {
   return needed;
 }
 
-inline bool op_has_b_host(uint32_t op) { return op < 32 || op == OP_TERN; }
+inline bool op_has_b_host(uint32_t op) { return op < 32 || op == OP_TERN || op == OP_MULADD; }
 
 fe to_fe(const U256& v) { fe r; memcpy(r.l, v.l, 32); return r; }
 U256 to_u256(const fe& v) { U256 r; memcpy(r.l, v.l, 32); return r; }
@@ -583,6 +583,117 @@ uint64_t fuse_pow5(MacroProgram& mp) {
   return n_fused;
 }
 
+// Latency plans: take one multiplication per Poseidon round off the critical path.  A partial round is
+//   x5 = x^5 (one OP_POW5);  y = S*x5 + (older terms);  next S-box input = y
+// i.e. four dependent multiplications from S-box input to S-box input.  With t = S*x computed beside x^2 and x^4,
+//   y = t * x^4 + (older terms)
+// is three: x -> x^2 -> x^4 -> y (x^5 itself is still computed, for the witness and its other readers, but nobody on the
+// path waits for it).  Pattern: an OP_DOT whose value is the input of an OP_POW5 and which has exactly one product term on
+// the result of another OP_POW5.  The S-box becomes OP_POW4 + Mul, the linear combination an early OP_DOT + OP_MULADD; the
+// new values get node ids behind the graph's.  Field arithmetic is exact, so every value is what it was.
+uint64_t rewrite_sbox_links(MacroProgram& mp) {
+  const size_t N0 = mp.g.nodes.size();
+  std::vector<int32_t> pow5_of(N0, -1);
+  std::vector<uint8_t> sbox_in(N0, 0), rewritten(N0, 0);
+  for (size_t q = 0; q < mp.mops.size(); q++) if (mp.mops[q].opc == OP_POW5) { pow5_of[mp.mops[q].node] = (int32_t)q; sbox_in[mp.mops[q].in[0]] = 1; }
+  // which S-boxes get split, and by which linear combination
+  std::vector<int32_t> link_of(mp.mops.size(), -1);       // per OP_DOT: index of the product term on an S-box result
+  for (size_t q = 0; q < mp.mops.size(); q++) {
+    const MOp& d = mp.mops[q];
+    if (d.opc != OP_DOT || d.narrow || d.node >= N0 || !sbox_in[d.node]) continue;
+    int32_t hit = -1, n_hit = 0;
+    for (size_t k = 0; k < d.terms.size(); k++) if (d.terms[k].kind == 0 && d.terms[k].node < N0 && pow5_of[d.terms[k].node] >= 0) { hit = (int32_t)k; n_hit++; }
+    if (n_hit != 1 || rewritten[d.terms[(size_t)hit].node]) continue;      // one link per S-box
+    rewritten[d.terms[(size_t)hit].node] = 1;
+    link_of[q] = hit;
+  }
+  auto new_node = [&](bool is_const, const U256& cv) {
+    const uint32_t id = (uint32_t)mp.g.nodes.size();
+    mp.g.nodes.push_back(Node{N_DUO, (uint8_t)OP_MUL, 0, 0, 0});      // a value id only: never evaluated as a graph node
+    mp.needed.push_back(1); mp.is_const.push_back(is_const ? 1 : 0); mp.const_val.push_back(cv);
+    mp.ty.rng.push_back(VRange()); mp.ty.narrow.push_back(0);
+    mp.out_start.push_back(mp.out_start.back());
+    return id;
+  };
+  std::vector<int32_t> dot_of(N0, -1);                    // per node: the OP_DOT that defines it
+  for (size_t q = 0; q < mp.mops.size(); q++) if (mp.mops[q].opc == OP_DOT && mp.mops[q].node < N0) dot_of[mp.mops[q].node] = (int32_t)q;
+  uint64_t n_expanded = 0;
+  std::vector<uint32_t> x4_of(N0, 0), t_of(N0, 0);        // per S-box result: the ids of x^4 and of t = S*x
+  std::vector<MOp> out; out.reserve(mp.mops.size() + mp.mops.size() / 4);
+  uint64_t n = 0;
+  // the product term of each link, needed when its S-box is met (the S-box comes first in the list)
+  std::vector<PTerm> term_of(N0);
+  for (size_t q = 0; q < mp.mops.size(); q++) if (link_of[q] >= 0) term_of[mp.mops[q].terms[(size_t)link_of[q]].node] = mp.mops[q].terms[(size_t)link_of[q]];
+  for (size_t q = 0; q < mp.mops.size(); q++) {
+    const MOp& m = mp.mops[q];
+    if (m.opc == OP_POW5 && m.node < N0 && rewritten[m.node]) {
+      const uint32_t x = m.in[0], n4 = new_node(false, U256()), nt = new_node(false, U256());
+      x4_of[m.node] = n4; t_of[m.node] = nt;
+      MOp p4; p4.node = n4; p4.opc = OP_POW4; p4.n_in = 1; p4.in[0] = x; p4.pos2 = m.pos2; p4.pos4 = m.pos4;
+      out.push_back(p4);
+      MOp t; t.node = nt; t.opc = OP_DOT; PTerm pt = term_of[m.node]; pt.node = x; t.terms.push_back(pt); t.ncs = 1;
+      out.push_back(t);
+      MOp m5; m5.node = m.node; m5.opc = OP_MUL; m5.n_in = 2; m5.in[0] = n4; m5.in[1] = x;
+      out.push_back(m5);
+      n++;
+      continue;
+    }
+    if (link_of[q] >= 0) {
+      const uint32_t v = m.terms[(size_t)link_of[q]].node;
+      // The older terms.  One of them may itself be a linear combination that reads the PREVIOUS round's S-box result
+      // (circomlib's sparse mix: s_j' = s_j + S'_j * x5): left alone, x5 -> s_j' -> this sum is a three-deep side path
+      // that the shortened chain now overtakes.  So such an operand is written out (its terms scaled by the coefficient,
+      // equal values merged: sum_j S_j * s_j' = sum_j S_j * s_j + (sum_j S_j S'_j) * x5), and the sum waits for x5 only.
+      struct Coef { uint32_t node; fe c; };                  // signed coefficients as field elements; node 0xFFFFFFFF = the constant
+      std::vector<Coef> acc;
+      auto add_coef = [&](uint32_t node, const fe& c) {
+        for (Coef& a : acc) if (a.node == node) { a.c = fe_add(a.c, c); return; }
+        acc.push_back(Coef{node, c});
+      };
+      auto coef_of = [&](const PTerm& t) { const fe c = t.kind == 1 ? fe_small(1) : to_fe(t.c); return t.neg ? fe_neg(c) : c; };
+      bool expanded = false;
+      for (size_t k = 0; k < m.terms.size(); k++) {
+        if ((int32_t)k == link_of[q]) continue;
+        const PTerm& t = m.terms[k];
+        const MOp* du = (t.kind != 2 && t.node < N0 && dot_of[t.node] >= 0) ? &mp.mops[(size_t)dot_of[t.node]] : nullptr;
+        bool reads_sbox = false;
+        if (du) for (const PTerm& u : du->terms) reads_sbox |= u.kind == 0 && u.node < N0 && rewritten[u.node];
+        if (du && reads_sbox && !du->narrow) {
+          const fe c = coef_of(t);
+          for (const PTerm& u : du->terms) add_coef(u.kind == 2 ? 0xFFFFFFFFu : u.node, fe_mul(c, coef_of(u)));
+          expanded = true;
+        } else add_coef(t.kind == 2 ? 0xFFFFFFFFu : t.node, coef_of(t));
+      }
+      std::vector<PTerm> rest;
+      if (!expanded || acc.size() > 8) { for (size_t k = 0; k < m.terms.size(); k++) if ((int32_t)k != link_of[q]) rest.push_back(m.terms[k]); }
+      else {
+        for (const Coef& a : acc) {
+          if (fe_is_zero(a.c)) continue;
+          if (a.node == 0xFFFFFFFFu) rest.push_back(PTerm{2, false, 0, to_u256(a.c)});
+          else if (u256_eq(a.c.l, fe_small(1).l)) rest.push_back(PTerm{1, false, a.node, U256()});
+          else rest.push_back(PTerm{0, false, a.node, to_u256(a.c)});
+        }
+        n_expanded++;
+      }
+      uint32_t c_node;
+      if (rest.size() == 1 && rest[0].kind == 1 && !rest[0].neg) c_node = rest[0].node;           // a plain value: no early sum needed
+      else if (rest.empty()) c_node = new_node(true, u256_from_u64(0));
+      else {
+        c_node = new_node(false, U256());
+        MOp e; e.node = c_node; e.opc = OP_DOT; e.terms = rest;
+        const double b = dot_bound(e.terms); e.ncs = b <= 2.0 ? 1 : b <= 4.0 ? 2 : 3;
+        out.push_back(e);
+      }
+      MOp ma; ma.node = m.node; ma.opc = OP_MULADD; ma.n_in = 3; ma.in[0] = t_of[v]; ma.in[1] = x4_of[v]; ma.in[2] = c_node;
+      out.push_back(ma);
+      continue;
+    }
+    out.push_back(m);
+  }
+  mp.mops.swap(out);
+  return n;
+}
+
 }  // namespace
 
 Plan compile_plan(const Graph& g0, const PlanOptions& opt) {
@@ -818,6 +929,8 @@ uint32_t lat_cost(const LOp& o) {
     case OP_MUL: return 1100 + around;
     case OP_SQR: return 950 + around;
     case OP_POW5: return 950 + 950 + 1100 + around + 100;
+    case OP_POW4: return 950 + 950 + around + 100;
+    case OP_MULADD: return 1100 + 80 + around;
     case OP_DOT: {
       uint32_t c = 1500;
       for (const PTerm& t : o.terms) c += t.kind == 0 ? 800u : 100u;
@@ -846,7 +959,27 @@ const uint32_t LAT_LEVEL_OVERHEAD = 500;   // cycles per level around the instru
 
 }  // namespace
 
+static LatencyPlan compile_latency_plan_one(const Graph& g0, const LatencyOptions& lo);
+
+// The S-box link rewrite shortens a Poseidon chain that has the SM to itself (Poseidon(1): 0.206 -> 0.177 ms) and costs
+// a graph that keeps every warp busy anyway (authV2, three hashes side by side: 17.0 -> 21.4 ms; profiles/r02x): it adds
+// two packets per round.  Both plans are built and the timing model, which gets both directions right, picks one.
 LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
+  if (lo.fuse && lo.sbox_links && lo.force_sbox_links) return compile_latency_plan_one(g0, lo);
+  LatencyOptions plain = lo;
+  plain.sbox_links = false;
+  // (dataflow plans only: the level plan's cost model is not calibrated for the choice -- it prefers the rewrite on authV2,
+  // where the kernel then measures 19.9 instead of 18.9 ms)
+  if (!(lo.fuse && lo.sbox_links && lo.dataflow)) return compile_latency_plan_one(g0, plain);
+  LatencyPlan a = compile_latency_plan_one(g0, plain);
+  try {
+    LatencyPlan b = compile_latency_plan_one(g0, lo);
+    if (b.n_sbox_links > 0 && b.est_cycles < a.est_cycles) return b;
+  } catch (const Error&) { }       // e.g. the rewritten graph keeps more values alive than the slot file holds
+  return a;
+}
+
+static LatencyPlan compile_latency_plan_one(const Graph& g0, const LatencyOptions& lo) {
   if (lo.n_warps < 1 || lo.n_warps > 16 || lo.n_slow_warps < 1 || lo.n_slow_warps > 6) throw Error("latency plan: warp counts out of range");
   if (lo.max_slots > 0xFFFFu) throw Error("latency plan: value file too large for 16-bit slot numbers");
   PlanOptions po;
@@ -855,6 +988,8 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
   MacroProgram mp;
   build_macro_program(g0, po, pst, mp);
   if (lo.fuse) fuse_pow5(mp);
+  uint64_t n_links = 0;
+  if (lo.fuse && lo.sbox_links) n_links = rewrite_sbox_links(mp);
   const Graph& g = mp.g;
   const size_t N = g.nodes.size();
   const std::vector<uint8_t>& is_const = mp.is_const;
@@ -901,7 +1036,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
         if (m.opc == OP_DOT) { for (const PTerm& t : m.terms) if (t.kind != 2) rd(t.node); }
         else for (int k = 0; k < m.n_in; k++) if (!is_const[m.in[k]]) rd(m.in[k]);
         const uint32_t no = n_out(m.node);
-        if (no > ((no >= 1 && m.opc != OP_TERN) ? 1u : 0u)) n_readers[m.node] += 2;      // separate stores read the slot later
+        if (no > ((no >= 1 && m.opc != OP_TERN && m.opc != OP_MULADD) ? 1u : 0u)) n_readers[m.node] += 2;      // separate stores read the slot later
       }
     }
     std::vector<int32_t> def_op(N, -1);
@@ -974,7 +1109,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       else { chain_head[ops.size()] = (uint32_t)ops.size(); chain_slots[ops.size()] = mop_slots(m); }
       if (o.slow) { lp.n_slow++; n_levels = std::max(n_levels, lv + D); }
       const uint32_t no = n_out(m.node);
-      const bool inline_out = no >= 1 && m.opc != OP_TERN;     // .w is operand c for TernCond
+      const bool inline_out = no >= 1 && m.opc != OP_TERN && m.opc != OP_MULADD;     // .w is operand c for TernCond and OP_MULADD
       if (inline_out) { o.has_out = true; o.out_pos = mp.out_list[mp.out_start[m.node]]; }
       n_levels = std::max(n_levels, lv + 1);
       ops.push_back(std::move(o));
@@ -1038,6 +1173,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       }
       if (o.opc == OP_SHRAND) return make_instr(OP_SHRAND, flags, dst, slot(o.in[0]), o.shift | (inline_const(o.mask) << 8), o.out_pos);
       if (o.opc == OP_POW5) return make_instr(OP_POW5, flags, dst, slot(o.in[0]) | ((o.pos4 == NO_POS ? 0xFFFFu : o.pos4 - o.pos2) << 16), o.pos2, o.out_pos);
+      if (o.opc == OP_POW4) return make_instr(OP_POW4, o.pos4 != NO_POS ? (uint32_t)F_OUT : 0u, dst, slot(o.in[0]), o.pos2, o.pos4 != NO_POS ? o.pos4 : 0u);
       if (o.opc == OP_DOT) {
         // terms ordered by kind so that the lanes of a warp walk the same code path
         std::vector<PTerm> ts = o.terms;
@@ -1070,17 +1206,17 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
         if (o.in[k] < N && is_const[o.in[k]]) { enc[k] = inline_const(mp.const_val[o.in[k]]); flags |= (F_A_CONST << k); }
         else enc[k] = slot(o.in[k]);
       }
-      return make_instr(o.opc, flags, dst, enc[0], enc[1], o.opc == OP_TERN ? enc[2] : o.out_pos);
+      return make_instr(o.opc, flags, dst, enc[0], enc[1], (o.opc == OP_TERN || o.opc == OP_MULADD) ? enc[2] : o.out_pos);
     };
     // header() emits offsets relative to the start of the instruction's own extras; a packet places them at `rb`
     auto rebase_header = [&](Instr h, uint32_t rb) {
       const uint32_t op = h.x & 0xFFu;
       if (op == OP_DOT) { h.z += rb; return h; }
       if (op == OP_SHRAND) { h.z = (h.z & 0xFFu) | (((h.z >> 8) + rb) << 8); return h; }
-      if (op == OP_INPUT || op == OP_POW5) return h;
+      if (op == OP_INPUT || op == OP_POW5 || op == OP_POW4) return h;
       if (h.x & F_A_CONST) h.y += rb;
       if ((h.x & F_B_CONST) && op_has_b_host(op)) h.z += rb;
-      if ((h.x & F_C_CONST) && op == OP_TERN) h.w += rb;
+      if ((h.x & F_C_CONST) && (op == OP_TERN || op == OP_MULADD)) h.w += rb;
       return h;
     };
     // appends a packet with the chains headed by list[from ..] to lp.code: at most 32 of them (one lane each), fewer
@@ -1196,7 +1332,7 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
       const uint64_t HOP = 150, ROW = 300;                 // a value crossing warps (publish + poll); descriptor + wait between two packets
       auto df_cost = [&](const LOp& o) -> uint64_t {
         switch (o.opc) {
-          case OP_MUL: return 1870; case OP_SQR: return 1580; case OP_POW5: return 3420;
+          case OP_MUL: return 1870; case OP_SQR: return 1580; case OP_POW5: return 3420; case OP_POW4: return 2510; case OP_MULADD: return 1950;
           case OP_DOT: { uint32_t n = 0; for (const PTerm& t : o.terms) n += t.kind == 0; return 1300 + 750ull * n + 60ull * (uint32_t)o.terms.size(); }
           case OP_ADD: case OP_SUB: return 720;
           case OP_DIV: return 53700; case OP_INV: return 52700; case OP_POW: return 500000; case OP_IDIV: case OP_MOD: return 50000;
@@ -1493,8 +1629,10 @@ LatencyPlan compile_latency_plan(const Graph& g0, const LatencyOptions& lo) {
   // chains trade levels for lane parallelism (instructions of different shapes cannot share a warp): keep whichever
   // schedule the cost model likes better (Poseidon / EdDSA graphs: chains; bit-level graphs like SHA-256: none)
   LatencyPlan a = plan_for(false);
+  a.n_sbox_links = n_links;
   if (!lo.chain || lo.dataflow) return a;      // dataflow: an S-box is one OP_POW5 already; other chains would only serialise a lane
   LatencyPlan b = plan_for(true);
+  b.n_sbox_links = n_links;
   return b.est_cycles < a.est_cycles ? b : a;
 }
 

@@ -87,6 +87,8 @@ struct LatencyOptions {
   bool fuse = true;              // OP_DOT / OP_SHRAND fusion (off: one instruction per graph node)
   bool chain = true;             // run single-reader chains (x^2 -> x^4 -> x^5) in one lane inside one level
   uint32_t max_chain = 4;        // instructions per chain
+  bool force_sbox_links = false; // apply the rewrite below whatever the timing model says (tests)
+  bool sbox_links = true;        // S*x^5 on the path from one S-box to the next becomes (S*x)*x^4: OP_POW4 + OP_MULADD (plan.cpp: rewrite_sbox_links)
   bool dataflow = false;         // per-warp packet streams with wait vectors instead of level barriers (eval_dataflow_kernel)
   bool exclusive_warp0 = false;  // dataflow: warp 0 takes the critical instructions and shares its SM sub-partition with nobody (measured: no gain)
 };
@@ -110,6 +112,7 @@ struct LatencyPlan {
   std::vector<uint32_t> stream_off, stream_chunks;
   uint32_t chunk_slots = 0, n_phys_warps = 0;     // stream_off / stream_chunks have n_phys_warps entries (some may be empty)
   uint64_t n_rows = 0, n_waits_df = 0;
+  uint64_t n_sbox_links = 0;          // S-box to S-box links rewritten (LatencyOptions::sbox_links)
 };
 LatencyPlan compile_latency_plan(const Graph& g, const LatencyOptions& opt);
 

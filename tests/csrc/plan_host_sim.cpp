@@ -189,7 +189,7 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
   LatencyPlan lp;
   try {
     LatencyOptions o;
-    if (opts) { if (opts[0]) o.n_warps = opts[0]; if (opts[1]) o.n_slow_warps = opts[1]; o.slow_levels = opts[2]; o.split_dot = opts[3] != 0; o.fuse = opts[4] != 0; if (opts[5]) o.packet_slots = opts[5]; o.chain = opts[6] != 0; o.dataflow = opts[7] != 0; }
+    if (opts) { if (opts[0]) o.n_warps = opts[0]; if (opts[1]) o.n_slow_warps = opts[1]; o.slow_levels = opts[2]; o.split_dot = opts[3] != 0; o.fuse = opts[4] != 0; if (opts[5]) o.packet_slots = opts[5]; o.chain = opts[6] != 0; o.dataflow = opts[7] != 0; o.sbox_links = opts[8] != 0; o.force_sbox_links = opts[8] == 2; }
     lp = compile_latency_plan(s->g, o);
   } catch (const std::exception& e) { s->err = e.what(); return -2; }
   std::vector<fe> slots(lp.n_slots, fe_zero());
@@ -233,6 +233,14 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
       if (ins.z != NO_POS) { if (ins.z >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.z, x2.l, 32); }
       if (d4 != 0xFFFF) { if (ins.z == NO_POS || ins.z + d4 >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)(ins.z + d4), x4.l, 32); }
       R = fe_mul(x4, x);
+    } else if (op == OP_POW4) {
+      if (ins.y >= lp.n_slots) return false;
+      const fe x2 = fe_sqr(rslot(ins.y));
+      if (ins.z != NO_POS) { if (ins.z >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.z, x2.l, 32); }
+      R = fe_sqr(x2);
+    } else if (op == OP_MULADD) {
+      if (!load(pk, ins.y, ins.x & F_A_CONST, &A) || !load(pk, ins.z, ins.x & F_B_CONST, &B) || !load(pk, ins.w, ins.x & F_C_CONST, &C)) return false;
+      R = fe_add(fe_mul(A, B), C);
     } else if (op == OP_SHRAND) {
       fe c;
       if (ins.y >= lp.n_slots || !pconst(pk, ins.z >> 8, &c)) return false;
@@ -245,7 +253,7 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
       R = alu_exec(op, A, B, C, st);
     }
     if (dst != NO_DST) { if (dst >= lp.n_slots) return false; writes.push_back({dst, R}); overlay[dst] = R; }
-    if ((ins.x & F_OUT) && op != OP_TERN) { if (ins.w >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
+    if ((ins.x & F_OUT) && op != OP_TERN && op != OP_MULADD) { if (ins.w >= lp.n_witness) return false; memcpy(witness + 32 * (size_t)ins.w, R.l, 32); }
     return true;
   };
   if (lp.dataflow) {
@@ -300,7 +308,7 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
       off[w] += d.x;
     }
     out8[0] = lp.n_levels; out8[1] = lp.n_slots; out8[2] = lp.n_instrs; out8[3] = lp.max_level_width; out8[4] = st;
-    out8[5] = lp.est_cycles; out8[6] = lp.n_rows; out8[7] = lp.slow_levels; out8[8] = lp.n_waits_df;
+    out8[5] = lp.est_cycles; out8[6] = lp.n_rows; out8[7] = lp.slow_levels; out8[8] = lp.n_waits_df; out8[9] = lp.n_sbox_links;
     return 0;
   }
   std::vector<uint32_t> next_job(lp.n_slow_warps, 0);
@@ -353,11 +361,11 @@ int64_t sim_eval_latency2(SimGraph* s, const uint8_t* inputs, uint8_t* witness, 
   }
   for (uint32_t w = 0; w < lp.n_slow_warps; w++) while (next_job[w] < lp.n_jobs[w]) { if (!run_job(w, next_job[w])) return -1; next_job[w]++; }
   out8[0] = lp.n_levels; out8[1] = lp.n_slots; out8[2] = lp.n_instrs; out8[3] = lp.max_level_width; out8[4] = st;
-  out8[5] = lp.est_cycles; out8[6] = lp.n_split; out8[7] = lp.slow_levels; out8[8] = lp.n_chained;
+  out8[5] = lp.est_cycles; out8[6] = lp.n_split; out8[7] = lp.slow_levels; out8[8] = lp.n_chained; out8[9] = lp.n_sbox_links;
   return 0;
 }
 int64_t sim_eval_latency(SimGraph* s, const uint8_t* inputs, uint8_t* witness, uint64_t* out5) {
-  uint64_t o8[9];
+  uint64_t o8[10];
   int64_t rc = sim_eval_latency2(s, inputs, witness, o8, 0, nullptr);
   if (rc == 0) for (int k = 0; k < 5; k++) out5[k] = o8[k];
   return rc;

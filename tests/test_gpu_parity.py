@@ -169,7 +169,7 @@ LATENCY_ENVS = [{}, {"GW_LAT_MODE": "level"}, {"GW_LAT_BIT": "0"}, {"GW_LAT_MODE
                 {"GW_LAT_WARPS": "2", "GW_LAT_SLOW_WARPS": "1", "GW_LAT_D": "1"}, {"GW_LAT_MODE": "level", "GW_LAT_WARPS": "2", "GW_LAT_SLOW_WARPS": "1", "GW_LAT_D": "1"},
                 {"GW_LAT_WARPS": "5", "GW_LAT_D": "60", "GW_LAT_SPLIT": "0", "GW_LAT_BIT": "0"},
                 {"GW_LAT_MODE": "level", "GW_LAT_WARPS": "5", "GW_LAT_D": "60", "GW_LAT_SPLIT": "0", "GW_LAT_BIT": "0"}, {"GW_LAT_FUSE": "0"},
-                {"GW_LAT_MODE": "level", "GW_LAT_FUSE": "0"}]
+                {"GW_LAT_MODE": "level", "GW_LAT_FUSE": "0"}, {"GW_LAT_LINKS": "2"}, {"GW_LAT_LINKS": "0"}]
 
 
 @pytest.mark.parametrize("env", LATENCY_ENVS)

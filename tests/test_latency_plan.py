@@ -23,6 +23,10 @@ VARIANTS = [
     dict(dataflow=True, n_warps=3, slow_levels=3, packet_slots=24),
     dict(dataflow=True, n_warps=8, n_slow_warps=4, fuse=False),
     dict(dataflow=True, split_dot=False),
+    # S-box link rewrite forced (OP_POW4 + OP_MULADD, side sums written out), both plan kinds
+    dict(dataflow=True, sbox_links=2),
+    dict(sbox_links=2),
+    dict(dataflow=True, sbox_links=0),
 ]
 
 
@@ -118,3 +122,29 @@ def test_poseidon_like_graphs():
         want = po.evaluate(nodes, row, wit, "circom")
         for mode in (0, 1, 2 + seed):
             assert g.eval_latency(row, mode=mode, **VARIANTS[seed % len(VARIANTS)])[0] == want, (seed, mode)
+
+
+def test_sbox_link_rewrite_on_poseidon_graphs():
+    """S*x^5 on the path from one S-box to the next becomes (S*x)*x^4 (plan.cpp: rewrite_sbox_links): every partial round
+    of the circomlib Poseidons is rewritten, values unchanged; left to itself the compiler keeps the rewrite for a lone
+    Poseidon and drops it for authV2 (timing model)."""
+    for name, rounds in (("circuit5_poseidon", 57), ("poseidon2", 57), ("circuit7_poseidon4", 60)):
+        data = util.golden_graph(name)
+        nodes, wit, imap = po.deserialize_graph(data)
+        buf = po.build_input_buffer(nodes, imap, po.deserialize_inputs(util.golden_inputs(name)))
+        want = po.parse_wtns(util.golden_wtns(name))
+        g = util.SimGraph(data, 12)
+        for kw in (dict(dataflow=True, sbox_links=2), dict(sbox_links=2), dict(dataflow=True)):
+            for mode in (0, 1, 4):
+                got, info = g.eval_latency(buf, mode=mode, **kw)
+                assert got == want, (name, kw, mode)
+            assert info["n_sbox_links"] >= rounds, (name, kw, info)
+    g = util.SimGraph(util.golden_graph("circuit9_authV2"), 12)
+    data = util.golden_graph("circuit9_authV2")
+    nodes, wit, imap = po.deserialize_graph(data)
+    buf = po.build_input_buffer(nodes, imap, po.deserialize_inputs(util.golden_inputs("circuit9_authV2")))
+    want = po.parse_wtns(util.golden_wtns("circuit9_authV2"))
+    got, info = g.eval_latency(buf, mode=2, dataflow=True, sbox_links=2)
+    assert got == want and info["n_sbox_links"] > 4000
+    got, info = g.eval_latency(buf, mode=2, dataflow=True)
+    assert got == want and info["n_sbox_links"] == 0

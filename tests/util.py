@@ -322,17 +322,17 @@ class SimGraph:
         return unpack_u256(out.raw), int(st)
 
     def eval_latency(self, inputs, mode=0, n_warps=0, n_slow_warps=0, slow_levels=0, split_dot=True, fuse=True, packet_slots=0, chain=True,
-                     dataflow=False):
+                     dataflow=False, sbox_links=True):
         """latency-mode plan on the host simulator -> (witness list, info dict).  Level plan: mode 0 / 1 = the slow-warp
         jobs run as early / as late as the protocol allows.  dataflow=True: per-warp packet streams with wait vectors;
         mode 0 / 1 / >= 2 = the next runnable warp is the lowest / the highest / a pseudo-random one
         (tests/csrc/plan_host_sim.cpp)."""
         out = ctypes.create_string_buffer(32 * self.info["W"])
-        o8 = (ctypes.c_uint64 * 9)()
-        opts = (ctypes.c_uint32 * 8)(n_warps, n_slow_warps, slow_levels, int(split_dot), int(fuse), packet_slots, int(chain), int(dataflow))
+        o8 = (ctypes.c_uint64 * 10)()
+        opts = (ctypes.c_uint32 * 9)(n_warps, n_slow_warps, slow_levels, int(split_dot), int(fuse), packet_slots, int(chain), int(dataflow), int(sbox_links))
         rc = self.L.sim_eval_latency2(self.h, pack_u256(inputs), out, o8, mode, opts)
         assert rc == 0, f"latency plan failed ({rc})"
-        keys = ["n_levels", "n_slots", "n_instrs", "max_width", "status", "est_cycles", "n_split", "slow_levels", "n_chained"]
+        keys = ["n_levels", "n_slots", "n_instrs", "max_width", "status", "est_cycles", "n_split", "slow_levels", "n_chained", "n_sbox_links"]
         if dataflow:
             keys[6], keys[8] = "n_rows", "n_waits"
         return unpack_u256(out.raw), dict(zip(keys, [int(x) for x in o8]))
