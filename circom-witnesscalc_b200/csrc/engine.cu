@@ -550,9 +550,7 @@ __device__ __forceinline__ fe lds_fe(uint32_t a) { return fe_from(lds128(a), lds
 // serialise); the block-level fences around them order the value-file accesses they publish.
 __device__ __forceinline__ void flag_publish(uint32_t a, uint32_t v) {
   __threadfence_block();
-  uint32_t old;
-  asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
-  (void)old;
+  asm volatile("{ .reg .b32 old; atom.shared.exch.b32 old, [%0], %1; }" ::"r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t flag_read(uint32_t a) {
   uint32_t v;

@@ -284,7 +284,7 @@ struct MOp {
   uint32_t in[3] = {0, 0, 0}; int n_in = 0;   // operand nodes of a regular op (constants included)
   std::vector<PTerm> terms;       // OP_DOT
   uint32_t ncs = 1;
-  uint32_t shift = 0; U256 mask;  // OP_SHRAND
+  uint32_t shift = 0; U256 mask = U256();  // OP_SHRAND
   bool narrow = false;            // F_NARROW: int64 operands and result
   uint32_t pos2 = NO_POS, pos4 = NO_POS;   // OP_POW5: witness positions of a^2 and a^4
 };
@@ -909,7 +909,7 @@ struct LOp {
   uint32_t val = 0xFFFFFFFFu;          // value it defines: a graph node, or N + k for the early part of a split OP_DOT
   uint32_t in[3] = {0, 0, 0}; int n_in = 0;   // operands of a regular op (graph nodes, constants included); OP_OUT: in[0]
   std::vector<PTerm> terms; uint32_t ncs = 1; // OP_DOT
-  uint32_t shift = 0; U256 mask;       // OP_SHRAND
+  uint32_t shift = 0; U256 mask = U256();   // OP_SHRAND
   uint32_t input = 0;                  // OP_INPUT
   uint32_t level = 0;
   bool has_out = false; uint32_t out_pos = 0;  // inline witness store (F_OUT), or the position of an OP_OUT
